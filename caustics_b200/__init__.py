@@ -1,0 +1,12 @@
+"""caustics_b200 -- B200 (sm_100a) implementation of the data-parallel hot path of
+fbartolic/caustics behind the reference's own API names.
+
+The compute lives in hand-written CUDA kernels behind the C ABI of include/caustics_b200.h
+(libcaustics_b200.so, built in-tree by `python -m caustics_b200.build`).  There is no CPU fallback.
+"""
+from .primitive import poly_roots, ehrlich_aberth, roots_jvp
+from .point_source import mag_point_source, lens_eq, lens_eq_det_jac, lens_params
+
+__all__ = ["poly_roots", "ehrlich_aberth", "roots_jvp", "mag_point_source", "lens_eq",
+           "lens_eq_det_jac", "lens_params"]
+__version__ = "0.1.0"

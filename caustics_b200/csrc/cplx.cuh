@@ -1,0 +1,57 @@
+// Complex-double helpers for the sm_100a kernels.  Plain structs (no thrust): everything lives in
+// registers, arithmetic is written out so that nvcc can contract to DFMA where contraction is
+// harmless, and the error-free transformations use the _rn intrinsics so it never can.
+#pragma once
+#ifndef CB200_HOSTSIM
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+namespace cb200 {
+
+struct cd {
+  double re, im;
+};
+
+__device__ __forceinline__ cd mk(double re, double im) { cd r; r.re = re; r.im = im; return r; }
+__device__ __forceinline__ cd operator+(cd a, cd b) { return mk(a.re + b.re, a.im + b.im); }
+__device__ __forceinline__ cd operator-(cd a, cd b) { return mk(a.re - b.re, a.im - b.im); }
+__device__ __forceinline__ cd operator-(cd a) { return mk(-a.re, -a.im); }
+__device__ __forceinline__ cd operator*(cd a, cd b) {
+  return mk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+__device__ __forceinline__ cd operator*(double s, cd a) { return mk(s * a.re, s * a.im); }
+__device__ __forceinline__ cd conj(cd a) { return mk(a.re, -a.im); }
+__device__ __forceinline__ double norm2(cd a) { return a.re * a.re + a.im * a.im; }
+__device__ __forceinline__ double cabs_fast(cd a) { return sqrt(norm2(a)); }
+// a*b + c with all four products fused
+__device__ __forceinline__ cd cfma(cd a, cd b, cd c) {
+  return mk(fma(a.re, b.re, fma(-a.im, b.im, c.re)), fma(a.re, b.im, fma(a.im, b.re, c.im)));
+}
+// 1/a: one real reciprocal.  Inputs here are O(1)-scaled (coefficients are normalised by a power
+// of two on load), so |a|^2 neither overflows nor underflows for anything the path produces.
+__device__ __forceinline__ cd crecip(cd a) {
+  double inv = 1.0 / norm2(a);
+  return mk(a.re * inv, -a.im * inv);
+}
+__device__ __forceinline__ cd cdiv(cd a, cd b) {
+  double inv = 1.0 / norm2(b);
+  return mk((a.re * b.re + a.im * b.im) * inv, (a.im * b.re - a.re * b.im) * inv);
+}
+__device__ __forceinline__ cd csel(bool c, cd a, cd b) { return mk(c ? a.re : b.re, c ? a.im : b.im); }
+
+// ---- error-free transformations (reference: lib/ehrlich_aberth/horner.h:44-84) ---------------
+// _rn intrinsics are never contracted or re-associated by nvcc.
+__device__ __forceinline__ void two_sum(double a, double b, double& s, double& e) {
+  double x = __dadd_rn(a, b);
+  double t = __dsub_rn(x, a);
+  e = __dadd_rn(__dsub_rn(a, __dsub_rn(x, t)), __dsub_rn(b, t));
+  s = x;
+}
+__device__ __forceinline__ void two_prod(double a, double b, double& p, double& e) {
+  double x = __dmul_rn(a, b);
+  e = __fma_rn(a, b, -x);
+  p = x;
+}
+
+}  // namespace cb200

@@ -1,0 +1,308 @@
+// Ehrlich-Aberth polynomial root solver, one thread per polynomial (device code for sm_100a).
+//
+// Behaviour follows the reference solver (/root/reference/lib/ehrlich_aberth/ehrlich_aberth.h:60-292,
+// horner.h, init_est.h): the same Gauss-Seidel sweep over the roots in index order, the same
+// reversed-polynomial evaluation for |z| > 1, the same stopping tests and -- when `compensated` --
+// the same second polishing phase built on error-free transformations with a running error bound.
+// What is B200-specific is the execution shape:
+//   * coefficients and |coefficients| live in registers (Horner loops fully unrolled, static
+//     register indices); the roots live in shared memory in [root][thread] planes so that the
+//     rolled loop over roots can index them dynamically without bank conflicts;
+//   * the standard and the reversed evaluation are ONE instruction stream: the branch of the
+//     reference (|z| > 1) becomes per-lane selects of the evaluation point and the coefficient
+//     order, so a warp never executes both paths;
+//   * convergence is a per-lane bit mask; a (sweep, root) step is skipped when a warp vote says no
+//     lane needs it, and the sweep loop ends on a warp vote (the reference's per-polynomial loop
+//     exit, lifted to the warp).  Each lane still stops updating a root exactly when the reference
+//     would, so the iteration path of every polynomial is the reference's.
+//   * coefficients are normalised by a power of two on load (exact, roots unchanged) so that |.|^2
+//     comparisons can replace hypot() everywhere.
+#pragma once
+#include "cplx.cuh"
+
+namespace cb200 {
+
+constexpr double EA_EPS = 1.1102230246251565e-16;  // 2^-53, horner.h:21
+
+// gamma_const(n), horner.h:30-35
+__host__ __device__ constexpr double ea_gamma(int n) {
+  return ((2.0 * n * 1.1102230246251565e-16) * 1.41421356237309504880) /
+         ((1.0 - 2.220446049250313e-16) - (2.0 * n * 1.1102230246251565e-16) * 1.41421356237309504880);
+}
+
+enum : int { EA_INIT_REFERENCE = 0, EA_INIT_BINI = 1 };
+
+// Power-of-two normalisation of the coefficients: p_i *= 2^-e with e = exponent of max |component|.
+template <int DEG>
+__device__ __forceinline__ void ea_normalise(cd (&p)[DEG + 1]) {
+  double m = 0.0;
+#pragma unroll
+  for (int i = 0; i <= DEG; ++i) m = fmax(m, fmax(fabs(p[i].re), fabs(p[i].im)));
+  int hi = __double2hiint(m);
+  int ex = (hi >> 20) & 0x7ff;
+  if (ex != 0 && ex != 0x7ff) {
+    double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex)
+#pragma unroll
+    for (int i = 0; i <= DEG; ++i) { p[i].re *= sc; p[i].im *= sc; }
+  }
+}
+
+// Bini initial estimates from the upper convex hull of (i, log|p_i|) -- init_est.h:57-102.
+// mode EA_INIT_REFERENCE reproduces the reference's purely real guesses r*sin(.) (the comma
+// expression at init_est.h:95), so sweep counts and root order match the reference; EA_INIT_BINI
+// uses the intended r*(cos, sin) which converges in 10-30 % fewer updates.
+template <int DEG, int NT>
+__device__ __noinline__ void ea_init_est(const double (&al)[DEG + 1], double* zre, double* zim,
+                                         int mode) {
+  double ly[DEG + 1];
+  int hx[DEG + 1];
+#pragma unroll
+  for (int i = 0; i <= DEG; ++i) ly[i] = al[i] > 0 ? log(al[i]) : -1e30;
+  int k = 0;
+  for (int i = DEG; i >= 0; --i) {
+    while (k >= 2) {
+      int x1 = hx[k - 2], x2 = hx[k - 1];
+      double ccw = (double)(x2 - x1) * (ly[i] - ly[x1]) - (ly[x2] - ly[x1]) * (double)(i - x1);
+      if (ccw <= 0) --k; else break;
+    }
+    hx[k++] = i;
+  }
+  const double pi2 = 6.28318530717958647693, sigma = 0.7, th = pi2 / DEG;
+  int pos = 0;
+  for (int i = k - 2; i >= 0; --i) {
+    int lo = hx[i + 1], up = hx[i];
+    int nz = up - lo;
+    // (|p_lo| / |p_up|)^(1/nz), from the logs already at hand
+    double r = exp((ly[lo] - ly[up]) / nz);
+    double ang = pi2 / nz;
+    for (int j = 0; j < nz; ++j) {
+      double s, c;
+      sincos(ang * j + th * i + sigma, &s, &c);
+      zre[(pos + j) * NT] = (mode == EA_INIT_REFERENCE) ? r * s : r * c;
+      zim[(pos + j) * NT] = (mode == EA_INIT_REFERENCE) ? 0.0 : r * s;
+    }
+    pos += nz;
+  }
+}
+
+// sort four values by decreasing magnitude with the tie behaviour of the reference's selection
+// sort (horner.h:164-188: the first maximum wins), written with static indices only.
+__device__ __forceinline__ void sort4_desc_abs(double (&p)[4]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double mx = fabs(p[i]);
+    int ind = i;
+#pragma unroll
+    for (int j = i + 1; j < 4; ++j) {
+      double t = fabs(p[j]);
+      if (t > mx) { mx = t; ind = j; }
+    }
+    double head = p[i], best = p[i];
+#pragma unroll
+    for (int j = i + 1; j < 4; ++j)
+      if (ind == j) { best = p[j]; p[j] = head; }
+    p[i] = best;
+  }
+}
+// Priest's doubly compensated summation of 4 terms, horner.h:190-208
+__device__ __forceinline__ double priest_sum4(double (&p)[4]) {
+  sort4_desc_abs(p);
+  double s = p[0], c = 0.0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i) {
+    double y = __dadd_rn(c, p[i]);
+    double u = __dsub_rn(p[i], __dsub_rn(y, c));
+    double t = __dadd_rn(y, s);
+    double v = __dsub_rn(y, __dsub_rn(t, s));
+    double z = __dadd_rn(u, v);
+    s = __dadd_rn(t, z);
+    c = __dsub_rn(z, __dsub_rn(s, t));
+  }
+  return s;
+}
+
+// One compensated Horner step  acc <- acc*x + add  (horner.h:58-84,296-328): returns the rounded
+// result, the Priest-summed complex error `err` and leaves the four error terms' moduli in `ab`.
+__device__ __forceinline__ cd comp_step(cd acc, cd x, cd add, cd& err, double (&ab)[4]) {
+  double p0, e0, p1, e1, p2, e2, p3, e3, sr, er, si, ei, vr, fr, vi, fi;
+  two_prod(acc.re, x.re, p0, e0);
+  two_prod(acc.im, x.im, p1, e1);
+  two_prod(acc.re, x.im, p2, e2);
+  two_prod(acc.im, x.re, p3, e3);
+  two_sum(p0, -p1, sr, er);
+  two_sum(p2, p3, si, ei);
+  two_sum(sr, add.re, vr, fr);
+  two_sum(si, add.im, vi, fi);
+  // error terms: (e0, e2), (-e1, e3), (er, ei), (fr, fi)
+  double re4[4] = {e0, -e1, er, fr};
+  double im4[4] = {e2, e3, ei, fi};
+  ab[0] = sqrt(e0 * e0 + e2 * e2);
+  ab[1] = sqrt(e1 * e1 + e3 * e3);
+  ab[2] = sqrt(er * er + ei * ei);
+  ab[3] = sqrt(fr * fr + fi * fi);
+  err = mk(priest_sum4(re4), priest_sum4(im4));
+  return mk(vr, vi);
+}
+
+// Shared-memory planes owned by one CTA of NT threads.
+template <int DEG, bool COMP, int NT>
+struct EASmem {
+  double zre[DEG][NT];
+  double zim[DEG][NT];
+  // compensated phase only: coefficient planes for the rolled compensated Horner loop
+  double cre[COMP ? DEG + 1 : 1][COMP ? NT : 1];
+  double cim[COMP ? DEG + 1 : 1][COMP ? NT : 1];
+};
+
+struct EAResult {
+  int sweeps;      // sweeps this polynomial used (== itmax when not converged)
+  bool converged;  // all roots satisfied the stopping test
+};
+
+// Solve one polynomial per thread.  p: coefficients low->high (already normalised) in registers.
+// Roots are read from / left in sm.zre/zim[.][tid] (the caller stores custom initial roots there
+// when custom_init).  All 32 lanes of a warp must call this together; `active` = false lanes idle.
+template <int DEG, bool COMP, int NT>
+__device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASmem<DEG, COMP, NT>& sm,
+                                                    int tid, bool active, bool custom_init,
+                                                    int init_mode, int itmax) {
+  constexpr unsigned FULL = (1u << DEG) - 1u;
+  double* zre = &sm.zre[0][tid];
+  double* zim = &sm.zim[0][tid];
+
+  double al[DEG + 1];
+#pragma unroll
+  for (int i = 0; i <= DEG; ++i) al[i] = cabs_fast(p[i]);  // ehrlich_aberth.h:77-82
+  if (active && !custom_init) {
+    // A polynomial whose coefficients are all exactly real keeps the reference's real-axis guesses
+    // on the real axis in exact arithmetic; the reference only escapes through rounding noise in
+    // thrust::pow (exp(2 log z) of a negative real), taking ~30 sweeps.  Use the complex Bini
+    // guesses for those polynomials instead (e.g. every binary-lens source on the lens axis).
+    double imsum = 0.0;
+#pragma unroll
+    for (int i = 0; i <= DEG; ++i) imsum += fabs(p[i].im);
+    ea_init_est<DEG, NT>(al, zre, zim, imsum == 0.0 ? (int)EA_INIT_BINI : init_mode);
+  }
+#pragma unroll
+  for (int i = 0; i <= DEG; ++i) al[i] *= fma(3.8284271247461900976, (double)i, 1.0);  // :96-99
+  if (COMP) {
+#pragma unroll
+    for (int i = 0; i <= DEG; ++i) { sm.cre[i][tid] = p[i].re; sm.cim[i][tid] = p[i].im; }
+  }
+
+  unsigned c1 = active ? 0u : FULL;  // plain-phase convergence bits
+  unsigned c2 = c1;                  // compensated-phase bits
+  EAResult res;
+  res.sweeps = 0;
+  res.converged = !active;
+  int it = 0;
+  for (; it < itmax; ++it) {
+    const unsigned done_bits = COMP ? c2 : c1;
+    if (__all_sync(0xffffffffu, done_bits == FULL)) break;
+#pragma unroll 1
+    for (int j = 0; j < DEG; ++j) {
+      const bool need1 = !((c1 >> j) & 1u);
+      const bool need2 = COMP && !need1 && !((c2 >> j) & 1u);
+      if (!__any_sync(0xffffffffu, need1 || need2)) continue;
+
+      const cd z = mk(zre[j * NT], zim[j * NT]);
+      const double az2 = norm2(z);
+      const bool rev = az2 > 1.0;  // |z| > 1, ehrlich_aberth.h:106
+      cd x = z;
+      double ax = sqrt(az2);
+      if (rev) {
+        const double inv = 1.0 / az2;
+        x = mk(z.re * inv, -z.im * inv);
+        ax = 1.0 / ax;
+      }
+      cd h, hd;
+      bool upd = false;
+      if (need1) {
+        // value, derivative and the real bound polynomial in one unrolled Horner pass;
+        // reversed lanes walk the coefficients from index 0 (horner.h:219-267)
+        h = csel(rev, p[0], p[DEG]);
+        double b = rev ? al[0] : al[DEG];
+        hd = h;
+        {
+          const cd c = csel(rev, p[1], p[DEG - 1]);
+          h = cfma(h, x, c);
+          b = fma(b, ax, rev ? al[1] : al[DEG - 1]);
+        }
+#pragma unroll
+        for (int k = 2; k <= DEG; ++k) {
+          const cd c = csel(rev, p[k], p[DEG - k]);
+          hd = cfma(hd, x, h);
+          h = cfma(h, x, c);
+          b = fma(b, ax, rev ? al[k] : al[DEG - k]);
+        }
+        const double thr = EA_EPS * b;
+        if (norm2(h) > thr * thr) upd = true;  // |h| > EPS*b, :109/:122
+        else c1 |= (1u << j);
+      }
+      if (COMP) {
+        if (need2) {
+          // compensated Horner with running error bound, horner.h:281-385 (rolled; coefficients
+          // come from the shared planes so the loop index can be dynamic)
+          cd e = mk(0, 0), ed = mk(0, 0), err;
+          double eb = 0.0, ab[4], abd[4];
+          h = mk(sm.cre[rev ? 0 : DEG][tid], sm.cim[rev ? 0 : DEG][tid]);
+          hd = mk(0, 0);
+#pragma unroll 1
+          for (int k = 1; k <= DEG; ++k) {
+            const int idx = rev ? k : DEG - k;
+            const cd c = mk(sm.cre[idx][tid], sm.cim[idx][tid]);
+            hd = comp_step(hd, x, h, err, abd);
+            ed = (ed * x + e) + err;
+            h = comp_step(h, x, c, err, ab);
+            e = e * x + err;
+            eb = eb * ax + priest_sum4(ab);
+          }
+          h = h + e;
+          hd = hd + ed;
+          const double ah = cabs_fast(h);
+          const double bound = EA_EPS * ah + (ea_gamma(4 * DEG + 2) * eb + 2.0 * EA_EPS * EA_EPS * ah);
+          if (ah > 4.0 * bound) upd = true;  // :235/:257
+          else c2 |= (1u << j);
+        }
+      }
+      if (__any_sync(0xffffffffu, upd)) {
+        if (upd) {
+          // Aberth sum over the other roots (:31-40) and the (reversed) correction (:41,:56-57)
+          cd s = mk(0, 0);
+#pragma unroll
+          for (int i = 0; i < DEG; ++i) {
+            if (i != j) s = s + crecip(z - mk(zre[i * NT], zim[i * NT]));
+          }
+          cd num = h, den = hd;
+          if (rev) {
+            const cd z2 = z * z;
+            num = z2 * h;
+            den = ((double)DEG * z) * h - hd;
+          }
+          den = den - num * s;
+          const cd corr = cdiv(num, den);
+          bool apply = true;
+          if (COMP) {
+            if (need2) {
+              // relative test on the reversed branch, absolute on the standard one (:238 vs :260)
+              const double t = rev ? 4.0 * EA_EPS * sqrt(az2) : 4.0 * EA_EPS;
+              if (!(norm2(corr) > t * t)) { apply = false; c2 |= (1u << j); }
+            }
+          }
+          if (apply) {
+            zre[j * NT] = z.re - corr.re;
+            zim[j * NT] = z.im - corr.im;
+          }
+        }
+      }
+    }
+    const unsigned now = COMP ? c2 : c1;
+    if (active && !res.converged) {
+      res.sweeps = it + 1;
+      if (now == FULL) res.converged = true;
+    }
+  }
+  return res;
+}
+
+}  // namespace cb200

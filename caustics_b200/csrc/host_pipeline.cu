@@ -1,0 +1,161 @@
+// HOST-buffer entry points: the call a reference-side binding makes with host arrays
+// (the shape of lib/ehrlich_aberth/cpu_ops.cc:15-81, whose operands are host pointers).
+// The batch is cut into chunks that flow through NSLOT streams as H2D -> kernel -> D2H, so copies
+// in both directions overlap compute when the caller's memory is pinned (pageable memory works,
+// the driver then stages the copies itself).  The device workspace is owned here, per device,
+// grown on demand and reused across calls; nothing else in the library allocates.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <mutex>
+
+#include "../../include/caustics_b200.h"
+
+namespace {
+
+constexpr int NSLOT = 3;
+constexpr int MAXDEV = 16;
+
+struct Slot {
+  cudaStream_t st = nullptr;
+  void* d_in = nullptr;
+  void* d_in2 = nullptr;
+  void* d_out = nullptr;
+  void* d_out2 = nullptr;
+  size_t cap_in = 0, cap_in2 = 0, cap_out = 0, cap_out2 = 0;
+};
+struct Workspace {
+  bool init = false;
+  Slot slot[NSLOT];
+};
+Workspace g_ws[MAXDEV];
+std::mutex g_mu;
+
+inline int rc_of(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUSTICS_ERR_CUDA_BASE + (int)e; }
+
+#define CK(expr)                      \
+  do {                                \
+    cudaError_t e__ = (expr);         \
+    if (e__ != cudaSuccess) return rc_of(e__); \
+  } while (0)
+
+int ensure(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return CAUSTICS_OK;
+  if (*p) CK(cudaFree(*p));
+  *p = nullptr; *cap = 0;
+  CK(cudaMalloc(p, need));
+  *cap = need;
+  return CAUSTICS_OK;
+}
+
+int get_ws(Workspace** out) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAXDEV) return CAUSTICS_ERR_BAD_ARG;
+  Workspace& w = g_ws[dev];
+  if (!w.init) {
+    for (int i = 0; i < NSLOT; ++i) CK(cudaStreamCreateWithFlags(&w.slot[i].st, cudaStreamNonBlocking));
+    w.init = true;
+  }
+  *out = &w;
+  return CAUSTICS_OK;
+}
+
+// chunk length: large enough to amortise launch + copy latency, small enough to pipeline
+int64_t pick_chunk(int64_t n) {
+  int64_t c = (n + 2 * NSLOT - 1) / (2 * NSLOT);
+  const int64_t lo = 1 << 14, hi = 1 << 18;
+  if (c < lo) c = lo;
+  if (c > hi) c = hi;
+  return c < n ? c : n;
+}
+
+}  // namespace
+
+extern "C" {
+
+void caustics_release_workspace(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int cur = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return; }
+  for (int d = 0; d < MAXDEV; ++d) {
+    Workspace& w = g_ws[d];
+    if (!w.init) continue;
+    cudaSetDevice(d);
+    for (int i = 0; i < NSLOT; ++i) {
+      Slot& s = w.slot[i];
+      cudaStreamSynchronize(s.st);
+      cudaFree(s.d_in); cudaFree(s.d_in2); cudaFree(s.d_out); cudaFree(s.d_out2);
+      cudaStreamDestroy(s.st);
+      s = Slot();
+    }
+    w.init = false;
+  }
+  cudaSetDevice(cur);
+}
+
+int caustics_ea_solve_host(const void* coeffs, const void* roots_init, void* roots, int32_t* sweeps,
+                           int64_t size, int deg, int itmax, int compensated, int custom_init,
+                           int flags) {
+  if (size < 0 || itmax < 0) return CAUSTICS_ERR_BAD_ARG;
+  if (!caustics_ea_degree_supported(deg)) return CAUSTICS_ERR_UNSUPPORTED_DEGREE;
+  if (size == 0) return CAUSTICS_OK;
+  if (!coeffs || !roots || (custom_init && !roots_init)) return CAUSTICS_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Workspace* w;
+  int rc = get_ws(&w);
+  if (rc) return rc;
+  const int64_t chunk = pick_chunk(size);
+  const size_t bc = (size_t)(deg + 1) * 16, br = (size_t)deg * 16;
+  for (int i = 0; i < NSLOT; ++i) {
+    Slot& s = w->slot[i];
+    if ((rc = ensure(&s.d_in, &s.cap_in, chunk * bc))) return rc;
+    if ((rc = ensure(&s.d_out, &s.cap_out, chunk * br))) return rc;
+    if (custom_init && (rc = ensure(&s.d_in2, &s.cap_in2, chunk * br))) return rc;
+    if (sweeps && (rc = ensure(&s.d_out2, &s.cap_out2, chunk * 4))) return rc;
+  }
+  int k = 0;
+  for (int64_t off = 0; off < size; off += chunk, ++k) {
+    Slot& s = w->slot[k % NSLOT];
+    const int64_t m = (size - off < chunk) ? size - off : chunk;
+    CK(cudaMemcpyAsync(s.d_in, (const char*)coeffs + off * bc, m * bc, cudaMemcpyHostToDevice, s.st));
+    if (custom_init)
+      CK(cudaMemcpyAsync(s.d_in2, (const char*)roots_init + off * br, m * br, cudaMemcpyHostToDevice, s.st));
+    rc = caustics_ea_solve(s.d_in, custom_init ? s.d_in2 : nullptr, s.d_out, sweeps ? (int32_t*)s.d_out2 : nullptr,
+                           m, deg, itmax, compensated, custom_init, flags, s.st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync((char*)roots + off * br, s.d_out, m * br, cudaMemcpyDeviceToHost, s.st));
+    if (sweeps) CK(cudaMemcpyAsync(sweeps + off, s.d_out2, m * 4, cudaMemcpyDeviceToHost, s.st));
+  }
+  for (int i = 0; i < NSLOT; ++i) CK(cudaStreamSynchronize(w->slot[i].st));
+  return CAUSTICS_OK;
+}
+
+int caustics_mag_point_source_host(const void* wpts, double* mag, int64_t n, const caustics_lens* lens,
+                                   int itmax, int compensated, int flags) {
+  if (n < 0 || itmax < 0 || !lens) return CAUSTICS_ERR_BAD_ARG;
+  if (n == 0) return CAUSTICS_OK;
+  if (!wpts || !mag) return CAUSTICS_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Workspace* w;
+  int rc = get_ws(&w);
+  if (rc) return rc;
+  const int64_t chunk = pick_chunk(n);
+  for (int i = 0; i < NSLOT; ++i) {
+    Slot& s = w->slot[i];
+    if ((rc = ensure(&s.d_in, &s.cap_in, chunk * 16))) return rc;
+    if ((rc = ensure(&s.d_out, &s.cap_out, chunk * 8))) return rc;
+  }
+  int k = 0;
+  for (int64_t off = 0; off < n; off += chunk, ++k) {
+    Slot& s = w->slot[k % NSLOT];
+    const int64_t m = (n - off < chunk) ? n - off : chunk;
+    CK(cudaMemcpyAsync(s.d_in, (const char*)wpts + off * 16, m * 16, cudaMemcpyHostToDevice, s.st));
+    rc = caustics_mag_point_source(s.d_in, (double*)s.d_out, nullptr, m, lens, itmax, compensated, flags, s.st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(mag + off, s.d_out, m * 8, cudaMemcpyDeviceToHost, s.st));
+  }
+  for (int i = 0; i < NSLOT; ++i) CK(cudaStreamSynchronize(w->slot[i].st));
+  return CAUSTICS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,358 @@
+// Kernels 1 and 2 of the hot path and their C-ABI launchers (include/caustics_b200.h).
+//   kernel 1  ea_kernel<DEG, COMP>      coeffs -> roots            (the `ehrlich_aberth` primitive)
+//   kernel 2  ps_kernel<NL, COMP, MODE> w -> images / magnification (coefficients, solve, lens-
+//             equation filter and Jacobian fused: nothing but w and the result touches HBM)
+// One thread per polynomial / source position; see ea_core.cuh for the execution shape.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/caustics_b200.h"
+#include "ea_core.cuh"
+#include "lens_core.cuh"
+
+using namespace cb200;
+
+namespace {
+
+constexpr int NT = 128;  // threads per CTA (4 warps): 20 KB (deg 10) of root planes per CTA
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUSTICS_ERR_CUDA_BASE + (int)e; }
+
+// ------------------------------------------------------------------------------------------
+template <int DEG, bool COMP>
+__global__ void __launch_bounds__(NT)
+ea_kernel(const double2* __restrict__ coeffs, const double2* __restrict__ roots_init,
+          double2* __restrict__ roots, int32_t* __restrict__ sweeps, int64_t size, int itmax,
+          int custom_init, int flags) {
+  __shared__ EASmem<DEG, COMP, NT> sm;
+  const int tid = threadIdx.x;
+  const int64_t idx = (int64_t)blockIdx.x * NT + tid;
+  const bool active = idx < size;
+  const int init_mode = flags & CAUSTICS_FLAG_INIT_BINI ? EA_INIT_BINI : EA_INIT_REFERENCE;
+  const bool high_first = (flags & CAUSTICS_FLAG_COEFFS_HIGH_FIRST) != 0;
+  cd p[DEG + 1];
+  if (active) {
+    const double2* src = coeffs + idx * (DEG + 1);
+#pragma unroll
+    for (int k = 0; k <= DEG; ++k) {
+      const double2 v = __ldg(src + (high_first ? DEG - k : k));
+      p[k] = mk(v.x, v.y);
+    }
+    ea_normalise<DEG>(p);
+    if (custom_init) {
+      const double2* ri = roots_init + idx * DEG;
+#pragma unroll
+      for (int j = 0; j < DEG; ++j) {
+        const double2 v = __ldg(ri + j);
+        sm.zre[j][tid] = v.x;
+        sm.zim[j][tid] = v.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k <= DEG; ++k) p[k] = mk(k == 0 ? -1.0 : (k == DEG ? 1.0 : 0.0), 0.0);
+  }
+  const EAResult r = ea_solve_thread<DEG, COMP, NT>(p, sm, tid, active, custom_init != 0, init_mode, itmax);
+  if (active) {
+    double2* dst = roots + idx * DEG;
+#pragma unroll
+    for (int j = 0; j < DEG; ++j) dst[j] = make_double2(sm.zre[j][tid], sm.zim[j][tid]);
+    if (sweeps) sweeps[idx] = r.converged ? r.sweeps : -r.sweeps;
+  }
+}
+
+template <int DEG>
+int launch_ea(const void* coeffs, const void* roots_init, void* roots, int32_t* sweeps, int64_t size,
+              int itmax, int compensated, int custom_init, int flags, cudaStream_t st) {
+  const int64_t nblk = (size + NT - 1) / NT;
+  if (nblk > 0x7fffffffLL) return CAUSTICS_ERR_BAD_ARG;
+  dim3 grid((unsigned)nblk), block(NT);
+  if (compensated)
+    ea_kernel<DEG, true><<<grid, block, 0, st>>>((const double2*)coeffs, (const double2*)roots_init,
+                                                 (double2*)roots, sweeps, size, itmax, custom_init, flags);
+  else
+    ea_kernel<DEG, false><<<grid, block, 0, st>>>((const double2*)coeffs, (const double2*)roots_init,
+                                                  (double2*)roots, sweeps, size, itmax, custom_init, flags);
+  return cuda_rc(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 2.  MODE 0: magnification only; MODE 1: images + mask (root axis first, like the reference)
+enum { PS_MAG = 0, PS_IMAGES = 1 };
+
+struct GridSpec {
+  double x0, y0, dx, dy;
+  int64_t nx, row_begin;
+  int use;  // 1: generate w from the grid instead of reading it
+};
+
+template <int NL, bool COMP, int MODE>
+__global__ void __launch_bounds__(NT)
+ps_kernel(const double2* __restrict__ w_in, GridSpec g, const double2* __restrict__ z_init,
+          double2* __restrict__ z_out, uint8_t* __restrict__ mask_out, double* __restrict__ mag,
+          uint8_t* __restrict__ nimg, int64_t n, LensConst L, int itmax, int custom_init, int flags) {
+  constexpr int DEG = NL * NL + 1;
+  __shared__ EASmem<DEG, COMP, NT> sm;
+  const int tid = threadIdx.x;
+  const int64_t idx = (int64_t)blockIdx.x * NT + tid;
+  const bool active = idx < n;
+  const int init_mode = flags & CAUSTICS_FLAG_INIT_BINI ? EA_INIT_BINI : EA_INIT_REFERENCE;
+  cd w = mk(0.3, 0.2);
+  if (active) {
+    if (g.use) {
+      const int64_t iy = idx / g.nx, ix = idx - iy * g.nx;
+      w = mk(fma((double)ix, g.dx, g.x0), fma((double)(iy + g.row_begin), g.dy, g.y0));
+    } else {
+      const double2 v = __ldg(w_in + idx);
+      w = mk(v.x, v.y);
+    }
+    w.re += L.x_cm;
+  }
+  cd p[DEG + 1];
+  lens_poly<NL>(L, w, p);
+  ea_normalise<DEG>(p);
+  if (MODE == PS_IMAGES) {
+    if (active && custom_init) {
+      const double2* ri = z_init + idx * DEG;
+#pragma unroll
+      for (int j = 0; j < DEG; ++j) {
+        const double2 v = __ldg(ri + j);
+        sm.zre[j][tid] = v.x;
+        sm.zim[j][tid] = v.y;
+      }
+    }
+  }
+  ea_solve_thread<DEG, COMP, NT>(p, sm, tid, active, MODE == PS_IMAGES && custom_init != 0, init_mode, itmax);
+  if (!active) return;
+  double mu = 0.0;
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < DEG; ++j) {
+    const cd z = mk(sm.zre[j][tid], sm.zim[j][tid]);
+    bool real_image;
+    double detj;
+    image_eval<NL>(L, z, w, real_image, detj);
+    if (MODE == PS_IMAGES) {
+      z_out[(int64_t)j * n + idx] = make_double2(z.re, z.im);
+      mask_out[(int64_t)j * n + idx] = real_image ? 1 : 0;
+    } else {
+      // (1/|det J|) * mask, point_source.py:1829 -- a false image contributes exactly 0
+      if (real_image) { mu += 1.0 / fabs(detj); ++cnt; }
+    }
+  }
+  if (MODE == PS_MAG) {
+    mag[idx] = mu;
+    if (nimg) nimg[idx] = (uint8_t)cnt;
+  }
+}
+
+int make_lens_const(const caustics_lens* lens, LensConst* out) {
+  if (!lens) return CAUSTICS_ERR_BAD_ARG;
+  LensConst L;
+  memset(&L, 0, sizeof(L));
+  L.nlenses = lens->nlenses;
+  L.x_cm = lens->x_cm;
+  struct hc { double re, im; };
+  auto mul = [](hc a, hc b) { return hc{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; };
+  hc r[3] = {{lens->a, 0.0}, {-lens->a, 0.0}, {lens->r3_re, lens->r3_im}};
+  double eps[3];
+  int n = lens->nlenses;
+  if (n == 2) { eps[0] = lens->e1; eps[1] = 1.0 - lens->e1; eps[2] = 0.0; }
+  else if (n == 3) { eps[0] = lens->e1; eps[1] = lens->e2; eps[2] = 1.0 - lens->e1 - lens->e2; }
+  else return CAUSTICS_ERR_BAD_ARG;
+  // H = prod (z - r_i), low->high
+  hc H[4] = {{1, 0}, {0, 0}, {0, 0}, {0, 0}};
+  int dh = 0;
+  for (int i = 0; i < n; ++i) {
+    hc nH[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    for (int k = 0; k <= dh; ++k) {
+      hc t = mul(H[k], hc{-r[i].re, -r[i].im});
+      nH[k].re += t.re; nH[k].im += t.im;
+      nH[k + 1].re += H[k].re; nH[k + 1].im += H[k].im;
+    }
+    ++dh;
+    for (int k = 0; k <= dh; ++k) H[k] = nH[k];
+  }
+  // G = sum_j eps_j prod_{i != j} (z - r_i)
+  hc G[3] = {{0, 0}, {0, 0}, {0, 0}};
+  for (int j = 0; j < n; ++j) {
+    hc t[3] = {{eps[j], 0}, {0, 0}, {0, 0}};
+    int dt = 0;
+    for (int i = 0; i < n; ++i) {
+      if (i == j) continue;
+      hc nt[3] = {{0, 0}, {0, 0}, {0, 0}};
+      for (int k = 0; k <= dt; ++k) {
+        hc u = mul(t[k], hc{-r[i].re, -r[i].im});
+        nt[k].re += u.re; nt[k].im += u.im;
+        nt[k + 1].re += t[k].re; nt[k + 1].im += t[k].im;
+      }
+      ++dt;
+      for (int k = 0; k <= dt; ++k) t[k] = nt[k];
+    }
+    for (int k = 0; k < n; ++k) { G[k].re += t[k].re; G[k].im += t[k].im; }
+  }
+  for (int i = 0; i < 3; ++i) { L.eps[i] = eps[i]; L.r[i].re = r[i].re; L.r[i].im = r[i].im; }
+  for (int k = 0; k < 4; ++k) { L.H[k].re = H[k].re; L.H[k].im = H[k].im; }
+  for (int k = 0; k < 3; ++k) { L.G[k].re = G[k].re; L.G[k].im = G[k].im; }
+  *out = L;
+  return CAUSTICS_OK;
+}
+
+template <int NL, int MODE>
+int launch_ps(const double2* w, GridSpec g, const double2* z_init, double2* z, uint8_t* mask, double* mag,
+              uint8_t* nimg, int64_t n, const LensConst& L, int itmax, int compensated, int custom_init,
+              int flags, cudaStream_t st) {
+  const int64_t nblk = (n + NT - 1) / NT;
+  if (nblk > 0x7fffffffLL) return CAUSTICS_ERR_BAD_ARG;
+  if (nblk == 0) return CAUSTICS_OK;
+  dim3 grid((unsigned)nblk), block(NT);
+  if (compensated)
+    ps_kernel<NL, true, MODE><<<grid, block, 0, st>>>(w, g, z_init, z, mask, mag, nimg, n, L, itmax, custom_init, flags);
+  else
+    ps_kernel<NL, false, MODE><<<grid, block, 0, st>>>(w, g, z_init, z, mask, mag, nimg, n, L, itmax, custom_init, flags);
+  return cuda_rc(cudaGetLastError());
+}
+
+thread_local int g_last_xla_error = 0;
+
+// DFMA-saturating microbenchmark: 8 independent FMA chains per thread.  Used by bench.py to measure
+// the FP64 (non-tensor) roofline denominator on the device the numbers are taken on.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 1.0000001, c = 1e-9 * threadIdx.x;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123.456) sink[0] = r;  // never true: keeps the chains alive
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int caustics_bench_fp64_peak(double* sink, int blocks, int iters, void* stream) {
+  if (!sink || blocks <= 0 || iters <= 0) return CAUSTICS_ERR_BAD_ARG;
+  fp64_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters, 0.5);
+  return cuda_rc(cudaGetLastError());
+}
+
+const char* caustics_version(void) { return "caustics_b200 0.1 (sm_100a)"; }
+
+int caustics_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int caustics_ea_degree_supported(int deg) { return deg >= 2 && deg <= 10; }
+
+const char* caustics_error_string(int code) {
+  switch (code) {
+    case CAUSTICS_OK: return "ok";
+    case CAUSTICS_ERR_BAD_ARG: return "bad argument";
+    case CAUSTICS_ERR_UNSUPPORTED_DEGREE: return "polynomial degree has no instantiated kernel (supported: 2..10)";
+    case CAUSTICS_ERR_BAD_DESCRIPTOR: return "opaque descriptor has the wrong size";
+    default:
+      if (code >= CAUSTICS_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(code - CAUSTICS_ERR_CUDA_BASE));
+      return "unknown error";
+  }
+}
+
+int caustics_ea_solve(const void* coeffs, const void* roots_init, void* roots, int32_t* sweeps,
+                      int64_t size, int deg, int itmax, int compensated, int custom_init,
+                      int flags, void* stream) {
+  if (size < 0 || itmax < 0) return CAUSTICS_ERR_BAD_ARG;
+  if (!caustics_ea_degree_supported(deg)) return CAUSTICS_ERR_UNSUPPORTED_DEGREE;
+  if (size == 0) return CAUSTICS_OK;
+  if (!coeffs || !roots || (custom_init && !roots_init)) return CAUSTICS_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CB200_CASE(D) \
+  case D: return launch_ea<D>(coeffs, roots_init, roots, sweeps, size, itmax, compensated, custom_init, flags, st);
+  switch (deg) {
+    CB200_CASE(2) CB200_CASE(3) CB200_CASE(4) CB200_CASE(5) CB200_CASE(6)
+    CB200_CASE(7) CB200_CASE(8) CB200_CASE(9) CB200_CASE(10)
+  }
+#undef CB200_CASE
+  return CAUSTICS_ERR_UNSUPPORTED_DEGREE;
+}
+
+size_t caustics_ea_make_descriptor(caustics_ea_descriptor* out, int64_t size, int deg, int itmax,
+                                   int compensated, int custom_init, int flags) {
+  if (out) {
+    memset(out, 0, sizeof(*out));
+    out->size = size; out->deg = deg; out->itmax = itmax;
+    out->compensated = compensated ? 1 : 0; out->custom_init = custom_init ? 1 : 0;
+    out->flags = (uint8_t)flags;
+  }
+  return sizeof(caustics_ea_descriptor);
+}
+
+int caustics_last_xla_error(void) { return g_last_xla_error; }
+
+void caustics_ea_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len) {
+  if (opaque_len != sizeof(caustics_ea_descriptor) || !opaque || !buffers) {
+    g_last_xla_error = CAUSTICS_ERR_BAD_DESCRIPTOR;  // the reference throws here (kernel_helpers.h:37-42)
+    return;
+  }
+  caustics_ea_descriptor d;
+  memcpy(&d, opaque, sizeof(d));
+  g_last_xla_error = caustics_ea_solve(buffers[0], buffers[1], buffers[2], nullptr, d.size, d.deg, d.itmax,
+                                       d.compensated, d.custom_init, d.flags, stream);
+}
+
+int caustics_images_point_source(const void* w, const void* z_init, void* z, uint8_t* mask,
+                                 int64_t n, const caustics_lens* lens, int itmax, int compensated,
+                                 int custom_init, int flags, void* stream) {
+  LensConst L;
+  int rc = make_lens_const(lens, &L);
+  if (rc) return rc;
+  if (n < 0 || itmax < 0) return CAUSTICS_ERR_BAD_ARG;
+  if (n == 0) return CAUSTICS_OK;
+  if (!w || !z || !mask || (custom_init && !z_init)) return CAUSTICS_ERR_BAD_ARG;
+  GridSpec g; memset(&g, 0, sizeof(g));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L.nlenses == 2)
+    return launch_ps<2, PS_IMAGES>((const double2*)w, g, (const double2*)z_init, (double2*)z, mask, nullptr, nullptr, n, L, itmax, compensated, custom_init, flags, st);
+  return launch_ps<3, PS_IMAGES>((const double2*)w, g, (const double2*)z_init, (double2*)z, mask, nullptr, nullptr, n, L, itmax, compensated, custom_init, flags, st);
+}
+
+int caustics_mag_point_source(const void* w, double* mag, uint8_t* nimages, int64_t n,
+                              const caustics_lens* lens, int itmax, int compensated, int flags,
+                              void* stream) {
+  LensConst L;
+  int rc = make_lens_const(lens, &L);
+  if (rc) return rc;
+  if (n < 0 || itmax < 0) return CAUSTICS_ERR_BAD_ARG;
+  if (n == 0) return CAUSTICS_OK;
+  if (!w || !mag) return CAUSTICS_ERR_BAD_ARG;
+  GridSpec g; memset(&g, 0, sizeof(g));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L.nlenses == 2)
+    return launch_ps<2, PS_MAG>((const double2*)w, g, nullptr, nullptr, nullptr, mag, nimages, n, L, itmax, compensated, 0, flags, st);
+  return launch_ps<3, PS_MAG>((const double2*)w, g, nullptr, nullptr, nullptr, mag, nimages, n, L, itmax, compensated, 0, flags, st);
+}
+
+int caustics_mag_point_source_grid(double x0, double y0, double dx, double dy, int64_t nx,
+                                   int64_t row_begin, int64_t row_end, double* mag,
+                                   const caustics_lens* lens, int itmax, int compensated,
+                                   int flags, void* stream) {
+  LensConst L;
+  int rc = make_lens_const(lens, &L);
+  if (rc) return rc;
+  if (nx <= 0 || row_end < row_begin || itmax < 0) return CAUSTICS_ERR_BAD_ARG;
+  const int64_t n = (row_end - row_begin) * nx;
+  if (n == 0) return CAUSTICS_OK;
+  if (!mag) return CAUSTICS_ERR_BAD_ARG;
+  GridSpec g; g.x0 = x0; g.y0 = y0; g.dx = dx; g.dy = dy; g.nx = nx; g.row_begin = row_begin; g.use = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L.nlenses == 2)
+    return launch_ps<2, PS_MAG>(nullptr, g, nullptr, nullptr, nullptr, mag, nullptr, n, L, itmax, compensated, 0, flags, st);
+  return launch_ps<3, PS_MAG>(nullptr, g, nullptr, nullptr, nullptr, mag, nullptr, n, L, itmax, compensated, 0, flags, st);
+}
+
+}  // extern "C"

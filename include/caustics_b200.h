@@ -1,0 +1,134 @@
+/*
+ * caustics_b200 -- C ABI of the B200 (sm_100a) implementation of caustics' hot path.
+ *
+ * Plain pointers and sizes only.  Every launcher BORROWS its buffers, enqueues on the caller's
+ * stream and returns without synchronising; none allocates device memory (the *_host entry points,
+ * which own an internal pinned/device workspace, are the exception and say so).  Return value:
+ * 0 on success, CAUSTICS_ERR_* for bad arguments, 1000 + cudaError_t for CUDA failures.  Nothing
+ * throws across this boundary and there is no CPU fallback: without a CUDA device every compute
+ * entry point returns 1000 + cudaErrorNoDevice (or the launch error).
+ *
+ * Reference interfaces replaced (paths under /root/reference):
+ *   caustics_ea_xla            lib/ehrlich_aberth/kernels.h:19-20  gpu_ehrlich_aberth(stream, buffers,
+ *                              opaque, opaque_len), registered by gpu_ops.cc:14-19 and bound in
+ *                              src/caustics/ehrlich_aberth_primitive.py:22-28,223-242
+ *   caustics_ea_descriptor     lib/ehrlich_aberth/kernels.h:11-17 EhrlichAberthDescriptor +
+ *                              gpu_ops.cc:24-25 build_ehrlich_aberth_descriptor
+ *   caustics_ea_solve[_host]   lib/ehrlich_aberth/cpu_ops.cc:15-81 cpu_ehrlich_aberth (same operands:
+ *                              size, deg, itmax, compensated, custom_init, coeffs, roots_init -> roots)
+ *   caustics_images_point_source  src/caustics/point_source.py:1655-1709 _images_point_source
+ *   caustics_mag_point_source     src/caustics/point_source.py:1762-1830 mag_point_source
+ *   caustics_mag_extended_source  src/caustics/extended_source.py:741-904 mag_extended_source
+ *   caustics_mag                  src/caustics/lightcurve.py:99-254 mag
+ *
+ * complex128 arrays are passed as `const void*` to interleaved (re, im) doubles, C order.
+ */
+#ifndef CAUSTICS_B200_H_
+#define CAUSTICS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAUSTICS_OK 0
+#define CAUSTICS_ERR_BAD_ARG 1
+#define CAUSTICS_ERR_UNSUPPORTED_DEGREE 2
+#define CAUSTICS_ERR_BAD_DESCRIPTOR 3
+#define CAUSTICS_ERR_CUDA_BASE 1000
+
+/* `flags` bits.  Default (0): initial estimates exactly as the reference computes them, including
+ * the real-axis quirk of init_est.h:95 (same sweep counts and root ORDER as the reference);
+ * coefficients stored low->high as the reference primitive expects. */
+#define CAUSTICS_FLAG_INIT_BINI 1         /* intended complex Bini estimates: 10-30 % fewer updates, other root order */
+#define CAUSTICS_FLAG_COEFFS_HIGH_FIRST 2 /* coeffs rows are high->low (saves poly_roots' flip, primitive.py:73) */
+
+/* Low-level lens parameters, exactly the reference's `_params` dict plus the centre-of-mass shift
+ * its public functions add to the source positions (point_source.py:1796-1819).
+ * nlenses = 1: nothing else used.  2: a, e1.  3: a, e1, e2, r3. */
+typedef struct caustics_lens {
+  int32_t nlenses;
+  int32_t reserved;
+  double a;
+  double e1;
+  double e2;
+  double r3_re, r3_im;
+  double x_cm;
+} caustics_lens;
+
+/* Opaque descriptor for the XLA custom call (the reference's descriptor, kernels.h:11-17, extended
+ * by custom_init which the reference's GPU path silently dropped, and by flags). */
+typedef struct caustics_ea_descriptor {
+  int64_t size;
+  int32_t deg;
+  int32_t itmax;
+  uint8_t compensated;
+  uint8_t custom_init;
+  uint8_t flags;
+  uint8_t reserved;
+  int32_t pad;
+} caustics_ea_descriptor;
+
+/* library / device queries (no compute) */
+const char* caustics_version(void);
+int caustics_device_count(void);
+/* degrees for which a kernel is instantiated: 1 if supported */
+int caustics_ea_degree_supported(int deg);
+const char* caustics_error_string(int code);
+
+/* ---- kernel 1: Ehrlich-Aberth roots --------------------------------------------------------
+ * coeffs (size, deg+1) complex128 LOW->HIGH, roots_init (size, deg) complex128 (may be NULL when
+ * custom_init == 0), roots (size, deg) complex128, sweeps (size) int32 or NULL: sweeps used per
+ * polynomial, negated when the polynomial did not converge within itmax.  Device pointers. */
+int caustics_ea_solve(const void* coeffs, const void* roots_init, void* roots, int32_t* sweeps,
+                      int64_t size, int deg, int itmax, int compensated, int custom_init,
+                      int flags, void* stream);
+
+/* Same contract with HOST pointers: chunked H2D -> kernel -> D2H pipeline over an internal pinned +
+ * device workspace on the current device (grows on demand, freed by caustics_release_workspace).
+ * Synchronous: returns when `roots` is complete. */
+int caustics_ea_solve_host(const void* coeffs, const void* roots_init, void* roots, int32_t* sweeps,
+                           int64_t size, int deg, int itmax, int compensated, int custom_init,
+                           int flags);
+void caustics_release_workspace(void);
+
+/* XLA GPU custom call (legacy api_version 0 signature, kernels.h:19-20).
+ * buffers = [coeffs, roots_init, roots]; opaque = caustics_ea_descriptor bytes.  On a bad descriptor
+ * nothing is launched and the sticky error is readable with caustics_last_xla_error(). */
+void caustics_ea_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+int caustics_last_xla_error(void);
+/* fills *out; returns sizeof(caustics_ea_descriptor) */
+size_t caustics_ea_make_descriptor(caustics_ea_descriptor* out, int64_t size, int deg, int itmax,
+                                   int compensated, int custom_init, int flags);
+
+/* ---- kernel 2: fused point-source images / magnification -----------------------------------
+ * w (n) complex128 source positions (the x_cm shift in `lens` is added inside).
+ * images: z (deg, n) complex128 with the root axis FIRST like the reference, mask (deg, n) uint8,
+ *         z_init (n, deg) complex128 root axis LAST like the reference's z_init (custom_init).
+ * mag:    mag (n) float64 = sum over real images of 1/|det J|.  nimages (n) uint8 or NULL. */
+int caustics_images_point_source(const void* w, const void* z_init, void* z, uint8_t* mask,
+                                 int64_t n, const caustics_lens* lens, int itmax, int compensated,
+                                 int custom_init, int flags, void* stream);
+int caustics_mag_point_source(const void* w, double* mag, uint8_t* nimages, int64_t n,
+                              const caustics_lens* lens, int itmax, int compensated, int flags,
+                              void* stream);
+/* magnification map: w generated on the fly, w[iy*nx + ix] = (x0 + ix*dx) + i (y0 + iy*dy),
+ * rows [row_begin, row_end) written to mag[(iy-row_begin)*nx + ix]. */
+int caustics_mag_point_source_grid(double x0, double y0, double dx, double dy, int64_t nx,
+                                   int64_t row_begin, int64_t row_end, double* mag,
+                                   const caustics_lens* lens, int itmax, int compensated,
+                                   int flags, void* stream);
+int caustics_mag_point_source_host(const void* w, double* mag, int64_t n, const caustics_lens* lens,
+                                   int itmax, int compensated, int flags);
+
+/* ---- measurement aid -----------------------------------------------------------------------
+ * Launches blocks x 256 threads, each running 8 independent chains of `iters` double-precision
+ * FMAs (2 * 8 * 256 * blocks * iters flop).  bench.py times it to get the FP64 roofline peak. */
+int caustics_bench_fp64_peak(double* sink, int blocks, int iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAUSTICS_B200_H_ */

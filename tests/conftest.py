@@ -1,0 +1,58 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def ea_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "ea_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def ps_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "ps_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """Build (if stale) and load the product library."""
+    from caustics_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def set_distance(a, b):
+    """Per-polynomial distance between two unordered root sets (rows), relative to max(1, |z|):
+    greedy nearest matching without reuse."""
+    a, b = np.asarray(a), np.asarray(b)
+    out = np.zeros(a.shape[0])
+    for n in range(a.shape[0]):
+        rem = list(b[n])
+        worst = 0.0
+        for x in a[n]:
+            d = [abs(x - y) for y in rem]
+            i = int(np.argmin(d))
+            worst = max(worst, d[i] / max(1.0, abs(x)))
+            rem.pop(i)
+        out[n] = worst
+    return out
+
+
+# workloads of SURVEY 8(d), deterministic
+def c1_w(n=10000):
+    return np.linspace(-2, 2, n) + 0.1j
+
+
+C1_LENS = dict(s=0.9, q=0.2)
+C2_PARAMS = dict(a=0.698, e1=0.02809, e2=0.9687, r3=-0.0197 - 0.95087j)
+TRIPLE_HP = dict(s=0.9, q=0.2, q3=0.1, r3=0.8, psi=1.0)

@@ -1,0 +1,94 @@
+"""CPU tier: the C-ABI library builds, loads, and exports every symbol include/caustics_b200.h
+declares (no compute calls).  Also the host-side argument checking and the loud failure without
+a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "caustics_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(caustics_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from caustics_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(built_lib, n), f"{n} declared in include/caustics_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in caustics_b200/_lib.py"
+
+
+def test_struct_layouts(built_lib):
+    from caustics_b200 import _lib
+    d = _lib.EADescriptor()
+    assert built_lib.caustics_ea_make_descriptor(ctypes.byref(d), 123456789012, 10, 2500, 1, 0, 3) == ctypes.sizeof(d) == 24
+    assert (d.size, d.deg, d.itmax, d.compensated, d.custom_init, d.flags) == (123456789012, 10, 2500, 1, 0, 3)
+    assert ctypes.sizeof(_lib.Lens) == 56
+
+
+def test_argument_errors_without_compute(built_lib):
+    from caustics_b200 import _lib
+    L = built_lib
+    assert L.caustics_ea_solve(None, None, None, None, 10, 11, 100, 0, 0, 0, None) == 2  # unsupported degree
+    assert L.caustics_ea_solve(None, None, None, None, -1, 5, 100, 0, 0, 0, None) == 1
+    assert L.caustics_ea_solve(None, None, None, None, 0, 5, 100, 0, 0, 0, None) == 0    # empty batch: no launch
+    assert L.caustics_ea_solve(None, None, None, None, 4, 5, 100, 0, 0, 0, None) == 1    # null buffers
+    for deg in range(2, 11):
+        assert L.caustics_ea_degree_supported(deg) == 1
+    assert L.caustics_ea_degree_supported(11) == 0
+    bad = _lib.Lens(); bad.nlenses = 4
+    assert L.caustics_mag_point_source(None, None, None, 0, ctypes.byref(bad), 10, 0, 0, None) == 1
+    # bad opaque descriptor: nothing launched, sticky error instead of the reference's C++ throw
+    bufs = (ctypes.c_void_p * 3)()
+    L.caustics_ea_xla(None, bufs, b"xx", 2)
+    assert L.caustics_last_xla_error() == 3
+    assert b"degree" in L.caustics_error_string(2)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu(built_lib):
+    import caustics_b200 as cb
+    from caustics_b200._lib import CausticsError
+    with pytest.raises(CausticsError):
+        cb.poly_roots(np.ones((3, 6), dtype=np.complex128))
+    with pytest.raises(CausticsError):
+        cb.mag_point_source(np.zeros(4, dtype=np.complex128) + 0.1, nlenses=2, s=0.9, q=0.2)
+
+
+def test_product_never_imports_oracle():
+    """The product path must not import, link or execute anything under oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "caustics_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "libea_oracle" not in src and "oracle/_ref" not in src, f
+
+
+def test_jvp_rule_host():
+    """roots_jvp (the Python JVP rule that stays in Python) against finite differences with
+    numpy.roots as the solver -- runs without a GPU."""
+    import caustics_b200 as cb
+    rng = np.random.default_rng(3)
+    c = rng.standard_normal((20, 6)) + 1j * rng.standard_normal((20, 6))
+    dc = rng.standard_normal((20, 6)) + 1j * rng.standard_normal((20, 6))
+    def roots(cc, ref=None):
+        out = np.array([np.roots(row[::-1]) for row in cc])
+        if ref is not None:  # align with ref ordering
+            out = np.array([[o[np.argmin(abs(o - r))] for r in rr] for o, rr in zip(out, ref)])
+        return out
+    z = roots(c)
+    h = 1e-6
+    fd = (roots(c + h * dc, z) - roots(c - h * dc, z)) / (2 * h)
+    assert np.allclose(cb.roots_jvp(c, z, dc), fd, rtol=1e-4, atol=1e-4)
+    zt = cb.roots_jvp(torch.from_numpy(c), torch.from_numpy(z), torch.from_numpy(dc))
+    assert np.allclose(zt.numpy(), cb.roots_jvp(c, z, dc))

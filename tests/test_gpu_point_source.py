@@ -1,0 +1,120 @@
+"""GPU tier: kernel 2 (fused point-source images / magnification) vs the oracle and the golden
+vectors generated from the reference.  Tolerance: rtol 1e-10."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import set_distance, c1_w, C2_PARAMS, TRIPLE_HP
+from oracle import lens
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb(built_lib):
+    import caustics_b200
+    assert torch.cuda.is_available()
+    return caustics_b200
+
+
+def test_mag_binary_reference_grid(cb, ps_golden):
+    """tests/test_point_source.py:32-49 grid, against the reference's own values"""
+    w = ps_golden["grid_w"]
+    got = cb.mag_point_source(torch.from_numpy(w).cuda(), nlenses=2, s=0.9, q=0.2).cpu().numpy()
+    assert np.allclose(got, ps_golden["grid_mag_binary"], rtol=1e-10, atol=0)
+    got = cb.mag_point_source(ps_golden["w"], nlenses=2, s=0.9, q=0.2)   # host arrays
+    assert isinstance(got, np.ndarray)
+    assert np.allclose(got, ps_golden["mag_binary"], rtol=1e-10, atol=0)
+
+
+def test_mag_triple_reference(cb, ps_golden):
+    w = torch.from_numpy(ps_golden["w"]).cuda()
+    got = cb.mag_point_source(w, nlenses=3, **TRIPLE_HP).cpu().numpy()
+    assert np.allclose(got, ps_golden["mag_triple"], rtol=1e-9, atol=0)
+    got = cb.mag_point_source(w, nlenses=3, roots_compensated=True, **TRIPLE_HP).cpu().numpy()
+    assert np.allclose(got, ps_golden["mag_triple_comp"], rtol=1e-9, atol=0)
+    assert (np.abs(got / ps_golden["mag_triple_comp"] - 1) < 1e-10).mean() > 0.99
+
+
+def test_c1_trajectory(cb):
+    """config 1 through the fused kernel: magnification rtol 1e-10, image counts in {3, 5}"""
+    w = c1_w()
+    want = lens.mag_point_source(w, 2, **dict(s=0.9, q=0.2))
+    for flags in (0, 1):
+        got = cb.mag_point_source(torch.from_numpy(w).cuda(), nlenses=2, flags=flags, s=0.9, q=0.2).cpu().numpy()
+        assert np.allclose(got, want, rtol=1e-10, atol=0)
+    p, x_cm = lens.lens_params(2, s=0.9, q=0.2)
+    z, mask = cb.point_source._images_point_source(torch.from_numpy(w + x_cm).cuda(), nlenses=2, **p)
+    assert z.shape == (5, w.size) and mask.dtype == torch.bool
+    counts = np.bincount(mask.sum(0).cpu().numpy(), minlength=6)
+    assert counts[3] + counts[5] == w.size and counts[5] == 632
+    zo, mo = lens.images_point_source(w + x_cm, 2, roots_compensated=True, **p)
+    assert set_distance(z.cpu().numpy().T, zo.T).max() < 1e-10
+    assert np.array_equal(np.sort(mask.cpu().numpy(), axis=0), np.sort(mo, axis=0))
+
+
+def test_c2_triple_trajectory_subset(cb):
+    """config 2 lens (tests/test_extended_source.py:100).  This lens has a 0.3 % third mass: some
+    false roots sit within 1e-6 of satisfying the lens equation, so the reference's own image
+    classification is ambiguous there.  Parity is asserted where the oracle's
+    classification margin is clear, and the rest is bounded."""
+    w = np.linspace(-2, 2, 1000000)[::50] + 0.1j
+    z, mask = lens.images_point_source(w, 3, roots_compensated=True, **C2_PARAMS)
+    res = np.abs(lens.lens_eq(z, 3, **C2_PARAMS) - w)
+    clear = ~((res > 1e-7) & (res < 1e-5)).any(axis=0)
+    want = (mask / np.abs(lens.lens_eq_det_jac(z, 3, **C2_PARAMS))).sum(0)
+    L = cb._lib.lib()
+    lens_c = cb.point_source._c_lens(3, 0.0, **C2_PARAMS)
+    wd = torch.from_numpy(w).cuda()
+    mag = torch.empty(w.size, dtype=torch.float64, device="cuda")
+    cb._lib.check(L.caustics_mag_point_source(wd.data_ptr(), mag.data_ptr(), None, w.size, lens_c, 2500, 1, 0, None))
+    got = mag.cpu().numpy()
+    assert clear.mean() > 0.5
+    assert np.allclose(got[clear], want[clear], rtol=1e-9, atol=0)
+    assert np.abs(got / want - 1).max() < 1e-4
+
+
+def test_images_custom_init_and_layout(cb):
+    p, x_cm = lens.lens_params(3, **TRIPLE_HP)
+    rng = np.random.default_rng(3)
+    w = rng.uniform(-1, 1, (7, 33)) + 1j * rng.uniform(-1, 1, (7, 33))
+    wd = torch.from_numpy(w).cuda()
+    z, mask = cb.point_source._images_point_source(wd, nlenses=3, roots_compensated=True, **p)
+    assert z.shape == (10, 7, 33) and mask.shape == (10, 7, 33)
+    zo, mo = lens.images_point_source(w, 3, roots_compensated=True, **p)
+    assert set_distance(z.reshape(10, -1).T.cpu().numpy(), zo.reshape(10, -1).T).max() < 1e-9
+    # warm start from the solution itself: unchanged order
+    z2, _ = cb.point_source._images_point_source(wd, nlenses=3, custom_init=True,
+                                                 z_init=torch.movedim(z, 0, -1), **p)
+    assert torch.abs(z2 - z).max().item() < 1e-9
+    assert set(np.unique(mask.sum(0).cpu().numpy())) <= {4, 6, 8, 10}
+
+
+def test_mag_grid_equals_explicit(cb):
+    """magnification-map entry (config 5 shape): w generated on device == explicit w"""
+    L = cb._lib.lib()
+    p, x_cm = lens.lens_params(2, s=0.9, q=0.2)
+    lens_c = cb.point_source._c_lens(2, x_cm, **p)
+    nx, ny = 257, 64
+    x0, y0, dx, dy = -1.5, -1.5, 3.0 / 9999, 3.0 / 9999
+    out = torch.empty(nx * 20, dtype=torch.float64, device="cuda")
+    cb._lib.check(L.caustics_mag_point_source_grid(x0, y0, dx, dy, nx, 10, 30, out.data_ptr(), lens_c, 2500, 0, 0, None))
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(10, 30))
+    w = (x0 + ix * dx) + 1j * (y0 + iy * dy)
+    want = cb.mag_point_source(torch.from_numpy(w.reshape(-1)).cuda(), nlenses=2, s=0.9, q=0.2)
+    assert torch.allclose(out, want, rtol=1e-12, atol=0)
+
+
+def test_single_lens_and_grad(cb):
+    w = torch.tensor([0.3 + 0.1j, 1.2 - 0.4j], dtype=torch.complex128, device="cuda")
+    u = torch.abs(w)
+    assert torch.allclose(cb.mag_point_source(w, nlenses=1), (u**2 + 2) / (u * torch.sqrt(u**2 + 4)), rtol=1e-12)
+    # tests/test_point_source.py:52-57: gradient of the magnification w.r.t. s
+    s = torch.tensor(0.9, dtype=torch.float64, device="cuda", requires_grad=True)
+    w = torch.tensor([0.05 + 0.3j, -0.4 + 0.2j, 0.6 - 0.1j], dtype=torch.complex128, device="cuda")
+    m = cb.mag_point_source(w, nlenses=2, s=s, q=0.2)
+    m.sum().backward()
+    h = 1e-6
+    fd = (cb.mag_point_source(w, nlenses=2, s=0.9 + h, q=0.2).sum() -
+          cb.mag_point_source(w, nlenses=2, s=0.9 - h, q=0.2).sum()) / (2 * h)
+    assert abs(s.grad.item() - fd.item()) < 1e-4 * max(1.0, abs(fd.item()))

@@ -1,0 +1,167 @@
+"""GPU tier: kernel 1 (Ehrlich-Aberth) through the C ABI vs the oracle and the golden vectors.
+Tolerances are BASELINE.md section 3: roots as unordered sets <= 1e-12 relative against the
+COMPENSATED reference; residual |p(z)| <= 1e-10 on the reference fixture."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import set_distance, c1_w, C2_PARAMS
+from oracle import lens, solver
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb(built_lib):
+    import caustics_b200
+    assert torch.cuda.is_available()
+    return caustics_b200
+
+
+def _polyval_high_low(c, z):
+    out = np.zeros_like(z)
+    for k in range(c.shape[-1]):
+        out = out * z + c[..., k:k + 1]
+    return out
+
+
+@pytest.mark.parametrize("comp", [False, True])
+def test_poly_roots_fixture(cb, ea_golden, comp):
+    """tests/test_ehrlich_aberth_primitive.py:30-35 on its own fixture, shape (5, 2, 6)"""
+    coeffs = ea_golden["fixture_coeffs"]
+    roots = cb.poly_roots(torch.from_numpy(coeffs).cuda(), compensated=comp).cpu().numpy()
+    assert roots.shape == (5, 2, 5)
+    assert np.abs(_polyval_high_low(coeffs, roots)).max() < 1e-10
+    want = ea_golden["fixture_roots_comp"]
+    assert set_distance(roots.reshape(-1, 5), want).max() < 1e-12
+    # host (numpy) entry point gives the same roots
+    roots_h = cb.poly_roots(coeffs, compensated=comp)
+    assert isinstance(roots_h, np.ndarray) and np.array_equal(roots_h, roots)
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "rand4", "rand5", "rand6", "rand10"])
+@pytest.mark.parametrize("comp", [False, True])
+def test_roots_vs_reference_golden(cb, ea_golden, name, comp):
+    c = ea_golden[name + "_coeffs"]
+    c = c.reshape(-1, c.shape[-1])
+    got, sweeps = cb.primitive._solve_flat(torch.from_numpy(c).cuda(), None, 2500, comp, False,
+                                           cb._lib.FLAG_COEFFS_HIGH_FIRST, return_sweeps=True)
+    got, sweeps = got.cpu().numpy(), sweeps.cpu().numpy()
+    assert (sweeps > 0).all()                      # every polynomial converged
+    want = ea_golden[name + ("_roots_comp" if comp else "_roots_plain")]
+    if comp:
+        assert set_distance(got, ea_golden[name + "_roots_comp"]).max() < 1e-12
+    if comp or name != "c2":                        # (plain c2: ill-conditioned)
+        assert np.abs(got - want).max() < 1e-11    # same root ORDER as the reference, too
+    # sweep counts follow the reference's iteration path
+    _, psw, _ = solver.port_solve(np.ascontiguousarray(c[:, ::-1]), compensated=comp, return_stats=True)
+    assert (sweeps == psw).mean() > (0.8 if comp else 0.95)
+
+
+@pytest.mark.parametrize("deg", [2, 3, 4, 5, 6, 7, 8, 9, 10])
+def test_all_degrees_random(cb, deg):
+    rng = np.random.default_rng(deg)
+    n = 4099  # ragged tail: not a multiple of the CTA size
+    c = rng.standard_normal((n, deg + 1)) + 1j * rng.standard_normal((n, deg + 1))
+    want = solver.solve(c, compensated=True)
+    for flags in (0, 1):
+        got = cb.ehrlich_aberth(torch.from_numpy(c).cuda(), torch.empty(0), itmax=2500, compensated=True,
+                                flags=flags).reshape(n, deg).cpu().numpy()
+        assert set_distance(got, want).max() < 1e-12
+    got = cb.ehrlich_aberth(torch.from_numpy(c).cuda(), torch.empty(0), itmax=2500, compensated=False)
+    assert got.shape == (n * deg,)                  # flat, like the primitive
+    assert set_distance(got.reshape(n, deg).cpu().numpy(), want).max() < 1e-9
+
+
+def test_c1_full_size(cb):
+    """config 1: 10^4 degree-5 polynomials of the binary trajectory, plain + compensated"""
+    p, x_cm = lens.lens_params(2, s=0.9, q=0.2)
+    c = lens.poly_coeffs(c1_w() + x_cm, 2, **p)
+    want = solver.solve(np.ascontiguousarray(c[:, ::-1]), compensated=True)
+    for comp in (False, True):
+        got = cb.poly_roots(torch.from_numpy(c).cuda(), itmax=2500, compensated=comp).cpu().numpy()
+        assert set_distance(got, want).max() < 1e-12
+
+
+def test_custom_init_continuity(cb):
+    """custom_init: root j stays the continuation of roots_init[j] and the
+    result equals the reference's on the same warm start."""
+    p, x_cm = lens.lens_params(2, s=0.9, q=0.2)
+    w = c1_w(4000) + x_cm
+    c = lens.poly_coeffs(w, 2, **p)
+    z_prev = solver.solve(np.ascontiguousarray(c[:-1, ::-1]), compensated=True)
+    want = solver.solve(np.ascontiguousarray(c[1:, ::-1]), custom_init=True, roots_init=z_prev)
+    got = cb.poly_roots(torch.from_numpy(c[1:]).cuda(), itmax=2500, custom_init=True,
+                        roots_init=torch.from_numpy(z_prev).cuda()).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-10         # ordered: same track per column
+    got_h = cb.poly_roots(c[1:], itmax=2500, custom_init=True, roots_init=z_prev)
+    assert np.array_equal(got_h, got)
+
+
+def test_itmax_and_empty_and_dtype(cb):
+    c = np.random.default_rng(0).standard_normal((64, 6)) + 0j
+    c[:, 1] += 1j
+    got, sw = cb.primitive._solve_flat(torch.from_numpy(c).cuda(), None, 2, False, False, 0, return_sweeps=True)
+    assert (sw.cpu().numpy() == -2).all()            # itmax reached: reported, not an error
+    assert np.isfinite(got.cpu().numpy().view(float)).all()
+    out = cb.poly_roots(torch.empty((0, 6), dtype=torch.complex128, device="cuda"))
+    assert out.shape == (0, 5)
+    with pytest.raises(NotImplementedError):
+        cb.poly_roots(torch.ones((4, 6), dtype=torch.complex64, device="cuda"))
+    from caustics_b200._lib import CausticsError
+    with pytest.raises(CausticsError):
+        cb.poly_roots(torch.ones((4, 13), dtype=torch.complex128, device="cuda"))
+
+
+def test_real_coefficients_and_scaling(cb):
+    """all-real polynomials (sources on the lens axis) and badly scaled coefficients"""
+    rng = np.random.default_rng(7)
+    c = rng.standard_normal((512, 6)) + 0j
+    want = solver.solve(c, compensated=True)
+    got, sw = cb.primitive._solve_flat(torch.from_numpy(c).cuda(), None, 2500, True, False, 0, return_sweeps=True)
+    assert (sw.cpu().numpy() > 0).all() and sw.max().item() < 40
+    assert set_distance(got.cpu().numpy(), want).max() < 1e-12
+    for scale in (1e-200, 1e200):
+        got = cb.primitive._solve_flat(torch.from_numpy(c * scale).cuda(), None, 2500, True, False, 0)
+        assert set_distance(got.cpu().numpy(), want).max() < 1e-12
+
+
+def test_xla_custom_call_entry(cb, ea_golden):
+    """caustics_ea_xla: the symbol an XLA custom call binds (buffers + opaque descriptor)"""
+    import ctypes
+    L = cb._lib.lib()
+    c = np.ascontiguousarray(ea_golden["rand5_coeffs"][:, ::-1])
+    dc = torch.from_numpy(c).cuda()
+    dri = torch.zeros((c.shape[0], 5), dtype=torch.complex128, device="cuda")
+    out = torch.empty((c.shape[0] * 5,), dtype=torch.complex128, device="cuda")
+    d = cb._lib.EADescriptor()
+    n = L.caustics_ea_make_descriptor(ctypes.byref(d), c.shape[0], 5, 2500, 1, 0, 0)
+    bufs = (ctypes.c_void_p * 3)(dc.data_ptr(), dri.data_ptr(), out.data_ptr())
+    L.caustics_ea_xla(torch.cuda.current_stream().cuda_stream, bufs, bytes(d), n)
+    assert L.caustics_last_xla_error() == 0
+    torch.cuda.synchronize()
+    assert set_distance(out.cpu().numpy().reshape(-1, 5), ea_golden["rand5_roots_comp"]).max() < 1e-12
+
+
+def test_autograd_matches_finite_differences(cb):
+    """tests/test_ehrlich_aberth_primitive.py:59-64: gradients atol=rtol=1e-4"""
+    rng = np.random.default_rng(11)
+    c = torch.from_numpy(rng.standard_normal((6, 6)) + 1j * rng.standard_normal((6, 6))).cuda().requires_grad_()
+    wgt = torch.from_numpy(rng.standard_normal((6, 5)) + 1j * rng.standard_normal((6, 5))).cuda()
+    def f(cc):
+        z = cb.poly_roots(cc, compensated=True)
+        return (z * wgt).real.sum() + (z * z).imag.sum()
+    f(c).backward()
+    g = c.grad.clone()
+    h = 1e-6
+    base = c.detach()
+    z0 = cb.poly_roots(base, compensated=True)
+    for idx in [(0, 0), (2, 3), (5, 5)]:
+        for d in (1.0, 1j):
+            e = torch.zeros_like(base); e[idx] = d * h
+            def fz(cc):
+                z = cb.poly_roots(cc, compensated=True, custom_init=True, roots_init=z0)
+                return ((z * wgt).real.sum() + (z * z).imag.sum()).item()
+            fd = (fz(base + e) - fz(base - e)) / (2 * h)
+            an = g[idx].real.item() if d == 1.0 else g[idx].imag.item()
+            assert abs(fd - an) <= 1e-4 + 1e-4 * abs(fd)
