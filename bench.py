@@ -67,10 +67,14 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+        # wait for the first sample so the timed region is covered from its start
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < 3.0 and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.02)
 
     def stop(self):
         if self.p is None:
@@ -130,7 +134,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -203,7 +207,7 @@ def main():
         step_e2e()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(3, min(50, args.steps // 2))
     for _ in range(e2e_steps):
         step_e2e()
     barrier()

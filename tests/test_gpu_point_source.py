@@ -54,24 +54,43 @@ def test_c1_trajectory(cb):
 
 
 def test_c2_triple_trajectory_subset(cb):
-    """config 2 lens (tests/test_extended_source.py:100).  This lens has a 0.3 % third mass: some
-    false roots sit within 1e-6 of satisfying the lens equation, so the reference's own image
-    classification is ambiguous there.  Parity is asserted where the oracle's
-    classification margin is clear, and the rest is bounded."""
+    """config 2 lens (tests/test_extended_source.py:100).  This lens has a 0.3 % third mass whose
+    images are badly conditioned: the reference's own magnification moves by up to ~1e-6 when its
+    polynomial coefficients are perturbed in the last bit, and some roots sit within a decade of
+    the 1e-6 image threshold (DESIGN.md "conditioning of C2").  Parity is therefore asserted to
+    rtol 1e-9 PLUS the oracle's own measured sensitivity at each point."""
+    from oracle import solver
     w = np.linspace(-2, 2, 1000000)[::50] + 0.1j
-    z, mask = lens.images_point_source(w, 3, roots_compensated=True, **C2_PARAMS)
-    res = np.abs(lens.lens_eq(z, 3, **C2_PARAMS) - w)
-    clear = ~((res > 1e-7) & (res < 1e-5)).any(axis=0)
-    want = (mask / np.abs(lens.lens_eq_det_jac(z, 3, **C2_PARAMS))).sum(0)
+    c = lens.poly_coeffs(w, 3, **C2_PARAMS)
+
+    def oracle_mag(coeffs):
+        z = solver.solve(np.ascontiguousarray(coeffs[:, ::-1]), itmax=2500, compensated=True).T
+        res = np.abs(lens.lens_eq(z, 3, **C2_PARAMS) - w)
+        inv_det = 1.0 / np.abs(lens.lens_eq_det_jac(z, 3, **C2_PARAMS))
+        amb = (res > 1e-8) & (res < 1e-4)           # may be classified either way
+        return ((res < 1e-6) * inv_det).sum(0), (amb * inv_det).sum(0)
+
+    want, slack = oracle_mag(c)
+    rng = np.random.default_rng(0)
+    spread = np.zeros_like(want)
+    for _ in range(4):                               # 1-ulp-level relative perturbations
+        pert = c * (1 + 2.2e-16 * (rng.standard_normal(c.shape) + 1j * rng.standard_normal(c.shape)))
+        m2, s2 = oracle_mag(pert)
+        spread = np.maximum(spread, np.abs(m2 - want))
+        slack = np.maximum(slack, s2)
     L = cb._lib.lib()
     lens_c = cb.point_source._c_lens(3, 0.0, **C2_PARAMS)
     wd = torch.from_numpy(w).cuda()
     mag = torch.empty(w.size, dtype=torch.float64, device="cuda")
-    cb._lib.check(L.caustics_mag_point_source(wd.data_ptr(), mag.data_ptr(), None, w.size, lens_c, 2500, 1, 0, None))
-    got = mag.cpu().numpy()
-    assert clear.mean() > 0.5
-    assert np.allclose(got[clear], want[clear], rtol=1e-9, atol=0)
-    assert np.abs(got / want - 1).max() < 1e-4
+    for comp in (1, 0):
+        cb._lib.check(L.caustics_mag_point_source(wd.data_ptr(), mag.data_ptr(), None, w.size, lens_c, 2500, comp, 0, None))
+        got = mag.cpu().numpy()
+        tol = 1e-9 * want + 50 * spread + 1.001 * slack
+        assert (np.abs(got - want) <= tol).all()
+        assert np.abs(got / want - 1).max() < 1e-4
+        well = (spread < 1e-12) & (slack == 0)       # well-conditioned points: the plain 1e-9 bar
+        if well.any():
+            assert np.allclose(got[well], want[well], rtol=1e-9, atol=0)
 
 
 def test_images_custom_init_and_layout(cb):
