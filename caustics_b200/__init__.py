@@ -6,7 +6,8 @@ The compute lives in hand-written CUDA kernels behind the C ABI of include/caust
 """
 from .primitive import poly_roots, ehrlich_aberth, roots_jvp
 from .point_source import mag_point_source, lens_eq, lens_eq_det_jac, lens_params
+from .extended_source import mag_extended_source, mag
 
 __all__ = ["poly_roots", "ehrlich_aberth", "roots_jvp", "mag_point_source", "lens_eq",
-           "lens_eq_det_jac", "lens_params"]
+           "lens_eq_det_jac", "lens_params", "mag_extended_source", "mag"]
 __version__ = "0.1.0"

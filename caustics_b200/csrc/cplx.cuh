@@ -28,14 +28,40 @@ __device__ __forceinline__ double cabs_fast(cd a) { return sqrt(norm2(a)); }
 __device__ __forceinline__ cd cfma(cd a, cd b, cd c) {
   return mk(fma(a.re, b.re, fma(-a.im, b.im, c.re)), fma(a.re, b.im, fma(a.im, b.re, c.im)));
 }
-// 1/a: one real reciprocal.  Inputs here are O(1)-scaled (coefficients are normalised by a power
-// of two on load), so |a|^2 neither overflows nor underflows for anything the path produces.
+// Fast double reciprocal / reciprocal square root: the 20-bit hardware seed (MUFU.RCP64H / RSQ64H via
+// the PTX .approx forms) polished by two Newton steps -> <= 2 ulp, branch-free (the compiler's own
+// 1.0/x and sqrt() carry a slow-path call for denormals that costs BSSY/BSYNC/BRA on every use).
+// Valid for normal, finite, non-zero arguments, which is all the path produces: coefficients are
+// normalised by a power of two on load, so |.|^2 neither overflows nor underflows.
+#ifdef CB200_HOSTSIM
+__device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
+__device__ __forceinline__ double rsqrt_fast(double x) { return 1.0 / sqrt(x); }
+#else
+__device__ __forceinline__ double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double h = 0.5 * y;
+  double e = fma(-x * y, y, 1.0);
+  y = fma(h, e, y);
+  h = 0.5 * y;
+  e = fma(-x * y, y, 1.0);
+  return fma(h, e, y);
+}
+#endif
 __device__ __forceinline__ cd crecip(cd a) {
-  double inv = 1.0 / norm2(a);
+  double inv = rcp_fast(norm2(a));
   return mk(a.re * inv, -a.im * inv);
 }
 __device__ __forceinline__ cd cdiv(cd a, cd b) {
-  double inv = 1.0 / norm2(b);
+  double inv = rcp_fast(norm2(b));
   return mk((a.re * b.re + a.im * b.im) * inv, (a.im * b.re - a.re * b.im) * inv);
 }
 __device__ __forceinline__ cd csel(bool c, cd a, cd b) { return mk(c ? a.re : b.re, c ? a.im : b.im); }

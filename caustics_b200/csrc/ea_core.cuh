@@ -31,6 +31,7 @@ __host__ __device__ constexpr double ea_gamma(int n) {
 }
 
 enum : int { EA_INIT_REFERENCE = 0, EA_INIT_BINI = 1 };
+constexpr unsigned EA_COMP_CAP = 12;  // see ea_solve_thread
 
 // Power-of-two normalisation of the coefficients: p_i *= 2^-e with e = exponent of max |component|.
 template <int DEG>
@@ -144,6 +145,30 @@ __device__ __forceinline__ cd comp_step(cd acc, cd x, cd add, cd& err, double (&
   return mk(vr, vi);
 }
 
+// Value, derivative and the real bound polynomial in one unrolled Horner pass (horner.h:219-267).
+// MODE 0: every lane evaluates p at x (coefficients high->low); MODE 1: every lane evaluates the
+// reversed polynomial (coefficients from index 0, reference's rhorner_*); MODE 2: per-lane select.
+// MODE 0/1 are taken when a warp vote finds the lanes agree, which saves the 6 selects per step.
+template <int DEG, int MODE>
+__device__ __forceinline__ void horner_plain(const cd (&p)[DEG + 1], const double (&al)[DEG + 1], cd x,
+                                             double ax, bool rev, cd& h, cd& hd, double& b) {
+#define CB200_COEF(k) (MODE == 0 ? p[DEG - (k)] : MODE == 1 ? p[k] : csel(rev, p[k], p[DEG - (k)]))
+#define CB200_ALPH(k) (MODE == 0 ? al[DEG - (k)] : MODE == 1 ? al[k] : (rev ? al[k] : al[DEG - (k)]))
+  h = CB200_COEF(0);
+  b = CB200_ALPH(0);
+  hd = h;
+  h = cfma(h, x, CB200_COEF(1));
+  b = fma(b, ax, CB200_ALPH(1));
+#pragma unroll
+  for (int k = 2; k <= DEG; ++k) {
+    hd = cfma(hd, x, h);
+    h = cfma(h, x, CB200_COEF(k));
+    b = fma(b, ax, CB200_ALPH(k));
+  }
+#undef CB200_COEF
+#undef CB200_ALPH
+}
+
 // Shared-memory planes owned by one CTA of NT threads.
 template <int DEG, bool COMP, int NT>
 struct EASmem {
@@ -192,6 +217,13 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
 
   unsigned c1 = active ? 0u : FULL;  // plain-phase convergence bits
   unsigned c2 = c1;                  // compensated-phase bits
+  // Compensated updates applied per root, 4 bits each.  The reference's polishing phase can
+  // limit-cycle between neighbouring doubles (|corr| stays just above its 4*EPS exit test) until
+  // itmax = 2500 sweeps (~1e-4 of lens polynomials); a lane doing that would pin
+  // its whole warp for ~10^3 x the normal run time.  A root that has taken EA_COMP_CAP polishing
+  // updates (legitimate roots need 1-3) is inside such a cycle -- every iterate of the cycle is
+  // within a few ulp of the others -- and is declared converged.
+  unsigned long long ncomp = 0ull;
   EAResult res;
   res.sweeps = 0;
   res.converged = !active;
@@ -208,33 +240,26 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
       const cd z = mk(zre[j * NT], zim[j * NT]);
       const double az2 = norm2(z);
       const bool rev = az2 > 1.0;  // |z| > 1, ehrlich_aberth.h:106
+      // |z| and (reversed lanes) 1/z, 1/|z| from one reciprocal square root
+      const double rs = az2 > 0.0 ? rsqrt_fast(az2) : 0.0;
+      const double absz = az2 * rs;
       cd x = z;
-      double ax = sqrt(az2);
+      double ax = absz;
       if (rev) {
-        const double inv = 1.0 / az2;
+        const double inv = rs * rs;
         x = mk(z.re * inv, -z.im * inv);
-        ax = 1.0 / ax;
+        ax = rs;
       }
       cd h, hd;
       bool upd = false;
+      // warp votes are taken by all lanes, outside the per-lane branch
+      const bool all_std = __all_sync(0xffffffffu, !need1 || !rev);
+      const bool all_rev = __all_sync(0xffffffffu, !need1 || rev);
       if (need1) {
-        // value, derivative and the real bound polynomial in one unrolled Horner pass;
-        // reversed lanes walk the coefficients from index 0 (horner.h:219-267)
-        h = csel(rev, p[0], p[DEG]);
-        double b = rev ? al[0] : al[DEG];
-        hd = h;
-        {
-          const cd c = csel(rev, p[1], p[DEG - 1]);
-          h = cfma(h, x, c);
-          b = fma(b, ax, rev ? al[1] : al[DEG - 1]);
-        }
-#pragma unroll
-        for (int k = 2; k <= DEG; ++k) {
-          const cd c = csel(rev, p[k], p[DEG - k]);
-          hd = cfma(hd, x, h);
-          h = cfma(h, x, c);
-          b = fma(b, ax, rev ? al[k] : al[DEG - k]);
-        }
+        double b;
+        if (all_std) horner_plain<DEG, 0>(p, al, x, ax, rev, h, hd, b);
+        else if (all_rev) horner_plain<DEG, 1>(p, al, x, ax, rev, h, hd, b);
+        else horner_plain<DEG, 2>(p, al, x, ax, rev, h, hd, b);
         const double thr = EA_EPS * b;
         if (norm2(h) > thr * thr) upd = true;  // |h| > EPS*b, :109/:122
         else c1 |= (1u << j);
@@ -270,8 +295,9 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
           // Aberth sum over the other roots (:31-40) and the (reversed) correction (:41,:56-57)
           cd s = mk(0, 0);
 #pragma unroll
-          for (int i = 0; i < DEG; ++i) {
-            if (i != j) s = s + crecip(z - mk(zre[i * NT], zim[i * NT]));
+          for (int i = 0; i < DEG - 1; ++i) {
+            const int ii = i + (i >= j ? 1 : 0);  // skip root j without a branch
+            s = s + crecip(z - mk(zre[ii * NT], zim[ii * NT]));
           }
           cd num = h, den = hd;
           if (rev) {
@@ -285,8 +311,15 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
           if (COMP) {
             if (need2) {
               // relative test on the reversed branch, absolute on the standard one (:238 vs :260)
-              const double t = rev ? 4.0 * EA_EPS * sqrt(az2) : 4.0 * EA_EPS;
+              const double t = rev ? 4.0 * EA_EPS * absz : 4.0 * EA_EPS;
               if (!(norm2(corr) > t * t)) { apply = false; c2 |= (1u << j); }
+            }
+          }
+          if (COMP) {
+            if (need2 && apply) {
+              const unsigned cnt = (unsigned)(ncomp >> (4 * j)) & 15u;
+              if (cnt + 1u >= EA_COMP_CAP) c2 |= (1u << j);
+              ncomp += 1ull << (4 * j);
             }
           }
           if (apply) {

@@ -1,0 +1,196 @@
+// Kernel family 3: contour-integration extended-source magnification (and the `mag` gate).
+//
+// Reference behaviour (paths under /root/reference/src/caustics): extended_source.py (all),
+// integrate.py, utils.py:15-99, multipole.py, lightcurve.py:24-254.  The reference evaluates one
+// source position at a time through ~200 size-1 custom calls and padded XLA scans; here a batch of
+// S source positions flows through a short sequence of embarrassingly parallel phases whose state
+// lives in HBM as structure-of-arrays with the SOURCE index fastest, so every phase is coalesced:
+//
+//   k_limb_walk      thread / source        N0 warm-started solves along the limb (:100-107)
+//   k_refine_select  thread / source   x10  top-n widest track gaps -> new theta (:114-127)
+//   k_refine_solve   thread / (source, new point) x10   warm-started solves (:76-98,127)
+//   k_tracks         thread / source        theta order, duplicate guard, greedy track matching
+//                                           (:34-53,139-151, utils.py:15-40)
+//   k_contours       thread / source        closed/open tracks, splitting, stitching, Green's
+//                                           theorem for a uniform disk (:156-727, integrate.py:23-27)
+//   k_ld_pq          thread / (source, contour vertex)  Dominik P/Q Gauss-Legendre integrals
+//   k_ld_sum         thread / source        trapezoid of P dx + Q dy (integrate.py:47-121)
+//   k_gate           thread / point         images + hexadecapole + validity tests + compaction
+//
+// Every solve is the same Gauss-Seidel Ehrlich-Aberth device function as kernels 1/2 (ea_core.cuh)
+// so root labelling along the limb follows the reference's iteration.  Nothing here allocates: the
+// caller provides one workspace (caustics_ext_workspace_bytes).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/caustics_b200.h"
+#include "extended_core.cuh"
+#include "extended_host.h"
+
+using namespace cb200;
+
+namespace {
+
+constexpr int NT = 128;
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUSTICS_ERR_CUDA_BASE + (int)e; }
+
+// ---- kernels: thin wrappers around the phase bodies of extended_core.cuh ------------------------
+template <int NL>
+__global__ void __launch_bounds__(NT) k_limb_walk(ExtCfg cfg, ExtBuf b, LensConst L) {
+  __shared__ EASmem<NL * NL + 1, false, NT> sm;
+  limb_walk_body<NL, NT>(cfg, b, L, sm, threadIdx.x, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+__global__ void __launch_bounds__(NT) k_limb_walk_single(ExtCfg cfg, ExtBuf b, LensConst L) {
+  limb_walk_single_body(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+template <int D>
+__global__ void __launch_bounds__(NT) k_refine_select(ExtCfg cfg, ExtBuf b, int round) {
+  refine_select_body<D>(cfg, b, round, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+template <int NL, bool COMP>
+__global__ void __launch_bounds__(NT) k_refine_solve(ExtCfg cfg, ExtBuf b, LensConst L, int round) {
+  __shared__ EASmem<NL * NL + 1, COMP, NT> sm;
+  refine_solve_body<NL, COMP, NT>(cfg, b, L, round, sm, threadIdx.x, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+__global__ void __launch_bounds__(NT) k_refine_solve_single(ExtCfg cfg, ExtBuf b, LensConst L, int round) {
+  refine_solve_single_body(cfg, b, L, round, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+template <int D>
+__global__ void __launch_bounds__(NT) k_tracks(ExtCfg cfg, ExtBuf b) {
+  tracks_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+template <int D>
+__global__ void __launch_bounds__(NT) k_contours(ExtCfg cfg, ExtBuf b, LensConst L) {
+  contours_body<D>(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+template <int NL>
+__global__ void __launch_bounds__(NT) k_ld_pq(ExtCfg cfg, ExtBuf b, LensConst L) {
+  ld_pq_body<NL>(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+__global__ void __launch_bounds__(NT) k_ld_sum(ExtCfg cfg, ExtBuf b) {
+  ld_sum_body(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+template <bool COMP>
+__global__ void __launch_bounds__(NT) k_gate(const double2* w_in, double* mag, uint8_t* test_out, int32_t* list,
+                                              int32_t* count, int64_t n, LensConst L, double rho, double q, int itmax) {
+  __shared__ EASmem<5, COMP, NT> sm;
+  gate_body<COMP, NT>(w_in, mag, test_out, list, count, n, L, rho, q, itmax, sm, threadIdx.x,
+                      (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+
+// fills list = 0..n-1 and count = n (nlenses != 2: full integration everywhere, lightcurve.py:226-227)
+__global__ void k_iota(int32_t* list, int32_t* count, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) list[i] = (int32_t)i;
+  if (i == 0) *count = (int32_t)n;
+}
+
+template <int NL>
+int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t st) {
+  constexpr int D = NL == 1 ? 2 : NL * NL + 1;
+  const unsigned gs = (unsigned)((cfg.S + NT - 1) / NT);
+  const unsigned gr = (unsigned)(((int64_t)cfg.nadd * cfg.S + NT - 1) / NT);
+  if (NL == 1) k_limb_walk_single<<<gs, NT, 0, st>>>(cfg, b, L);
+  else k_limb_walk<(NL == 1 ? 2 : NL)><<<gs, NT, 0, st>>>(cfg, b, L);
+  for (int r = 0; r < NITER; ++r) {
+    k_refine_select<D><<<gs, NT, 0, st>>>(cfg, b, r);
+    if (NL == 1) k_refine_solve_single<<<gr, NT, 0, st>>>(cfg, b, L, r);
+    else if (cfg.comp) k_refine_solve<(NL == 1 ? 2 : NL), true><<<gr, NT, 0, st>>>(cfg, b, L, r);
+    else k_refine_solve<(NL == 1 ? 2 : NL), false><<<gr, NT, 0, st>>>(cfg, b, L, r);
+  }
+  k_tracks<D><<<gs, NT, 0, st>>>(cfg, b);
+  k_contours<D><<<gs, NT, 0, st>>>(cfg, b, L);
+  if (cfg.ld) {
+    const unsigned gv = (unsigned)(((int64_t)cfg.VMAX * cfg.S + NT - 1) / NT);
+    k_ld_pq<NL><<<gv, NT, 0, st>>>(cfg, b, L);
+    k_ld_sum<<<gs, NT, 0, st>>>(cfg, b);
+  }
+  return cuda_rc(cudaGetLastError());
+}
+
+}  // namespace
+
+// defined in kernels.cu (anonymous-namespace helper re-exported for this TU)
+extern "C" int caustics_internal_lens_const(const caustics_lens* lens, void* out);
+
+extern "C" {
+
+size_t caustics_ext_workspace_bytes(int64_t n, int nlenses, int npts_limb, int limb_darkening, int npts_ld) {
+  ExtCfg c;
+  if (make_cfg(n, 1.0, nlenses, npts_limb, limb_darkening, 0.0, npts_ld, 1, 0, &c)) return 0;
+  return make_layout(c).total;
+}
+
+// Shared driver: `gate` != 0 runs the lightcurve.py dispatch (hexadecapole where valid), else every
+// point gets the full contour integration (mag_extended_source).
+static int ext_driver(const void* w, double* mag, uint8_t* test_out, int64_t n, double rho, const caustics_lens* lens,
+                      double q_for_gate, int gate, int npts_limb, int limb_darkening, double u1, int npts_ld,
+                      int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!lens || n < 0) return CAUSTICS_ERR_BAD_ARG;
+  ExtCfg cfg;
+  int rc = make_cfg(n, rho, lens->nlenses, npts_limb, limb_darkening, u1, npts_ld, itmax, compensated, &cfg);
+  if (rc) return rc;
+  if (n == 0) return CAUSTICS_OK;
+  if (n > 0x7fffffffLL / (cfg.VMAX > NADD_MAX ? cfg.VMAX : NADD_MAX)) return CAUSTICS_ERR_BAD_ARG;  // index range of one call
+  if (!w || !mag || !workspace) return CAUSTICS_ERR_BAD_ARG;
+  const Layout lay = make_layout(cfg);
+  if (workspace_bytes < lay.total) return CAUSTICS_ERR_BAD_ARG;
+  LensConst L;
+  memset(&L, 0, sizeof(L));
+  if (lens->nlenses == 1) { L.nlenses = 1; L.x_cm = 0.0; L.eps[0] = 1.0; }
+  else if ((rc = caustics_internal_lens_const(lens, &L))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  ExtBuf b = bind(cfg, lay, workspace);
+  b.w = (const double2*)w;
+  b.mag = mag;
+  char* base = (char*)workspace;
+  int32_t* list = (int32_t*)(base + lay.list);
+  int32_t* count = (int32_t*)(base + lay.count);
+  if (cfg.ld) {
+    // Gauss-Legendre tables: computed on the host, copied with the stream (pageable source: the copy
+    // is staged before the call returns, so the stack buffer may go out of scope)
+    double tab[2 * 2048];
+    const int nn = cfg.n1 + cfg.n2;
+    leggauss(cfg.n1, tab, tab + nn);
+    leggauss(cfg.n2, tab + cfg.n1, tab + nn + cfg.n1);
+    cudaError_t e = cudaMemcpyAsync(base + lay.gl, tab, (size_t)nn * 16, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+  }
+  if (gate && lens->nlenses == 2) {
+    cudaError_t e = cudaMemsetAsync(count, 0, 4, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    if (compensated)
+      k_gate<true><<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>((const double2*)w, mag, test_out, list, count, n, L, rho, q_for_gate, itmax);
+    else
+      k_gate<false><<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>((const double2*)w, mag, test_out, list, count, n, L, rho, q_for_gate, itmax);
+    b.list = list; b.count = count;
+  } else if (gate) {
+    k_iota<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(list, count, n);
+    if (test_out) { cudaError_t e = cudaMemsetAsync(test_out, 0, (size_t)n, st); if (e != cudaSuccess) return cuda_rc(e); }
+    b.list = list; b.count = count;
+  }
+  switch (lens->nlenses) {
+    case 1: return run_pipeline<1>(cfg, b, L, st);
+    case 2: return run_pipeline<2>(cfg, b, L, st);
+    default: return run_pipeline<3>(cfg, b, L, st);
+  }
+}
+
+int caustics_mag_extended_source(const void* w, double* mag, int64_t n, double rho, const caustics_lens* lens,
+                                 int npts_limb, int limb_darkening, double u1, int npts_ld, int itmax,
+                                 int compensated, void* workspace, size_t workspace_bytes, void* stream) {
+  return ext_driver(w, mag, nullptr, n, rho, lens, 0.0, 0, npts_limb, limb_darkening, u1, npts_ld, itmax,
+                    compensated, workspace, workspace_bytes, stream);
+}
+
+int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t n, double rho,
+                 const caustics_lens* lens, double q, int npts_limb, int limb_darkening, double u1, int npts_ld,
+                 int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream) {
+  return ext_driver(w, mag, used_hexadecapole, n, rho, lens, q, 1, npts_limb, limb_darkening, u1, npts_ld, itmax,
+                    compensated, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"

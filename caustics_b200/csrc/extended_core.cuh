@@ -1,0 +1,715 @@
+// Device code of kernel family 3 (extended-source magnification).  See extended.cu for the phase
+// structure; every phase body is a function of the source index `s` (and, for the solver phases, of
+// the thread's lane in the CTA-wide shared root planes), so the same code is driven by the CUDA
+// kernels in extended.cu and -- with one "lane" -- by the host logic tests (tests/hostsim).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "ea_core.cuh"
+#include "lens_core.cuh"
+#include "multipole.cuh"
+
+namespace cb200 {
+
+#ifdef CB200_HOSTSIM
+struct cb200_d2 { double x, y; };
+__device__ __forceinline__ cb200_d2 make_cb200_d2(double x, double y) { cb200_d2 r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ int cb200_atomic_inc(int32_t* p) { return (*p)++; }
+__device__ __forceinline__ double rsqrt(double x) { return 1.0 / sqrt(x); }
+#else
+typedef double2 cb200_d2;
+__device__ __forceinline__ cb200_d2 make_cb200_d2(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ int cb200_atomic_inc(int32_t* p) { return atomicAdd(p, 1); }
+#endif
+
+constexpr int NADD_MAX = 64;       // new limb points per refinement round (npts_limb <= 1280)
+constexpr int NITER = 10;          // refinement rounds, extended_source.py:71
+constexpr int MAXSEG = 30;         // 3 * (nlenses^2 + 1), extended_source.py:279-280
+constexpr int MAXPARTS = 10;       // per track, extended_source.py:202-203
+constexpr double JIT_RE = 3.1e-7, JIT_IM = -5.3e-7;  // fixed stand-ins for U(+-1e-6) (:83-85)
+constexpr double DUP_JIT = 7.0e-10;                  // stand-in for U(+-1e-9) (:146)
+
+struct ExtCfg {
+  int nl, D, N0, nadd, NP;
+  double rho;
+  int itmax, comp, ld, n1, n2, VMAX, CMAX;
+  double u1;
+  int64_t S;        // capacity (stride) of the source axis
+};
+
+struct ExtBuf {
+  const cb200_d2* w;       // source positions (all points of the call)
+  const int32_t* list;     // optional: indices into w of the sources to integrate (else identity)
+  const int32_t* count;    // optional: device-side number of sources (else S)
+  double* theta;           // [NP][S]   by arrival slot
+  double* zre; double* zim; uint8_t* flg;   // [NP][D][S] by arrival slot; flg bit0 real, bit1 det>0
+  uint16_t* order;         // [NP][S]   arrival slot of the p-th point in theta order
+  uint16_t* left;          // [NADD][S] warm-start slot of each new point of the current round
+  double* sre; double* sim; uint8_t* sflg;  // [NP][D][S] theta-ordered, rows = image tracks
+  cb200_d2* vz; double* vP; double* vQ; uint8_t* vcid;   // [VMAX][S] limb-darkening vertex lists
+  int32_t* vcount;         // [S]
+  int32_t* ncont;          // [S] number of contours emitted
+  cb200_d2* cz0; double* cpar; int32_t* cstart;   // [CMAX(+1)][S] per contour: centroid, parity, first vertex
+  const double* glx; const double* glw;          // Gauss-Legendre nodes/weights, n1 then n2
+  double* mag;             // result, indexed like w (through list)
+};
+
+__device__ __forceinline__ int64_t nsrc(const ExtCfg& c, const ExtBuf& b) {
+  return b.count ? (int64_t)*b.count : c.S;
+}
+#define I2(p, s) ((int64_t)(p) * cfg.S + (s))
+#define I3(p, j, s) (((int64_t)(p) * cfg.D + (j)) * cfg.S + (s))
+
+__device__ __forceinline__ cd source_centre(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s) {
+  const int64_t k = b.list ? (int64_t)b.list[s] : s;
+  const cb200_d2 v = b.w[k];
+  return mk(v.x + L.x_cm, v.y);
+}
+__device__ __forceinline__ cd limb_point(cd w0, double rho, double theta) {
+  double sn, cs;
+  sincos(theta, &sn, &cs);
+  return mk(fma(rho, cs, w0.re), fma(rho, sn, w0.im));
+}
+__device__ __forceinline__ double theta_init(int k, int N0) {
+  // linspace(-pi, pi, N0-1, endpoint=False) ++ [pi - 1e-8], extended_source.py:101-102
+  const double pi = 3.14159265358979323846;
+  return k < N0 - 1 ? fma((double)k, (2.0 * pi) / (double)(N0 - 1), -pi) : pi - 1e-8;
+}
+
+// single lens: the two images analytically (point_source.py:1665-1672)
+__device__ __forceinline__ void single_lens_images(cd w, cd (&z)[2]) {
+  const double sq = sqrt(1.0 + 4.0 / norm2(w));
+  z[0] = (0.5 * (1.0 + sq)) * w;
+  z[1] = (0.5 * (1.0 - sq)) * w;
+}
+
+// Solve the lens polynomial at w (warm start when `warm`: roots already in the shared planes) and
+// write the roots, real-image flags and parity signs to arrival slot `slot`.
+template <int NL, bool COMP, int NT>
+__device__ __forceinline__ void solve_and_store(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,
+                                                EASmem<NL * NL + 1, COMP, NT>& sm, int tid, bool active,
+                                                cd w, bool warm, int slot, int64_t s) {
+  constexpr int D = NL * NL + 1;
+  cd p[D + 1];
+  lens_poly<NL>(L, w, p);
+  ea_normalise<D>(p);
+  ea_solve_thread<D, COMP, NT>(p, sm, tid, active, warm, EA_INIT_REFERENCE, cfg.itmax);
+  if (!active) return;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const cd z = mk(sm.zre[j][tid], sm.zim[j][tid]);
+    bool real_image;
+    double detj;
+    image_eval<NL>(L, z, w, real_image, detj);
+    b.zre[I3(slot, j, s)] = z.re;
+    b.zim[I3(slot, j, s)] = z.im;
+    b.flg[I3(slot, j, s)] = (real_image ? 1 : 0) | (detj > 0 ? 2 : 0) | (detj == 0 ? 4 : 0);
+  }
+}
+
+__device__ __forceinline__ void store_single(const ExtCfg& cfg, const ExtBuf& b, cd w, int slot, int64_t s) {
+  cd z[2];
+  single_lens_images(w, z);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const double det = 1.0 - 1.0 / (norm2(z[j]) * norm2(z[j]));  // 1 - 1/|zbar^2|^2, point_source.py:1562
+    b.zre[I3(slot, j, s)] = z[j].re;
+    b.zim[I3(slot, j, s)] = z[j].im;
+    b.flg[I3(slot, j, s)] = 1 | (det > 0 ? 2 : 0) | (det == 0 ? 4 : 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int NL, int NT>
+__device__ void limb_walk_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, EASmem<NL * NL + 1, false, NT>& sm, int tid, int64_t s) {
+  const bool active = s < nsrc(cfg, b);
+  const cd w0 = active ? source_centre(cfg, b, L, s) : mk(0.3, 0.2);
+  for (int k = 0; k < cfg.N0; ++k) {
+    const double th = theta_init(k, cfg.N0);
+    const cd w = limb_point(w0, cfg.rho, th);
+    // roots_compensated is not forwarded to the sequential walk (extended_source.py:104-106)
+    solve_and_store<NL, false, NT>(cfg, b, L, sm, tid, active, w, k > 0, k, s);
+    if (active) {
+      b.theta[I2(k, s)] = th;
+      b.order[I2(k, s)] = (uint16_t)k;
+    }
+  }
+}
+
+__device__ void limb_walk_single_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s) {
+  if (s >= nsrc(cfg, b)) return;
+  const cd w0 = source_centre(cfg, b, L, s);
+  for (int k = 0; k < cfg.N0; ++k) {
+    const double th = theta_init(k, cfg.N0);
+    store_single(cfg, b, limb_point(w0, cfg.rho, th), k, s);
+    b.theta[I2(k, s)] = th;
+    b.order[I2(k, s)] = (uint16_t)k;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One refinement round, selection part: rank the intervals of the current theta order by the largest
+// image displacement across them (only tracks where at least one end is a real image), take the
+// nadd widest -- ties to the higher index, like argsort(...)[::-1] -- put a new point at each
+// midpoint and splice the new arrival slots into the order.
+template <int D>
+__device__ void refine_select_body(const ExtCfg& cfg, const ExtBuf& b, int round, int64_t s) {
+  if (s >= nsrc(cfg, b)) return;
+  const int cur = cfg.N0 + round * cfg.nadd, n = cfg.nadd;
+  double val[NADD_MAX];
+  int idx[NADD_MAX];
+  int cnt = 0;
+  double pre[D], pim[D];
+  uint8_t pf[D];
+  {
+    const int slot = b.order[I2(0, s)];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { pre[j] = b.zre[I3(slot, j, s)]; pim[j] = b.zim[I3(slot, j, s)]; pf[j] = b.flg[I3(slot, j, s)]; }
+  }
+  for (int i = 0; i + 1 < cur; ++i) {
+    const int slot = b.order[I2(i + 1, s)];
+    double dmax = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double re = b.zre[I3(slot, j, s)], im = b.zim[I3(slot, j, s)];
+      const uint8_t f = b.flg[I3(slot, j, s)];
+      const double dx = re - pre[j], dy = im - pim[j];
+      const double d2 = ((f | pf[j]) & 1) ? dx * dx + dy * dy : 0.0;
+      dmax = fmax(dmax, d2);
+      pre[j] = re; pim[j] = im; pf[j] = f;
+    }
+    // descending list; a later interval with an equal value ranks BEFORE earlier ones
+    if (cnt < n || dmax >= val[cnt - 1]) {
+      int pos = cnt < n ? cnt : n - 1;
+      while (pos > 0 && val[pos - 1] <= dmax) { val[pos] = val[pos - 1]; idx[pos] = idx[pos - 1]; --pos; }
+      val[pos] = dmax; idx[pos] = i;
+      if (cnt < n) ++cnt;
+    }
+  }
+  // new points: rank r -> arrival slot cur + r; theta at the interval midpoint, warm start from the left end
+  for (int r = 0; r < n; ++r) {
+    const int i = idx[r];
+    const int sl = b.order[I2(i, s)], sr = b.order[I2(i + 1, s)];
+    b.theta[I2(cur + r, s)] = 0.5 * (b.theta[I2(sl, s)] + b.theta[I2(sr, s)]);
+    b.left[I2(r, s)] = (uint16_t)sl;
+  }
+  // splice: jnp.insert(x, idcs + 1, new) -- element for interval i lands right after position i.
+  // Work from the back so nothing is overwritten before it is moved.  rk[] = ranks sorted by interval.
+  int rk[NADD_MAX];
+  for (int r = 0; r < n; ++r) {
+    int pos = r;
+    while (pos > 0 && idx[rk[pos - 1]] < idx[r]) { rk[pos] = rk[pos - 1]; --pos; }
+    rk[pos] = r;   // descending by interval index
+  }
+  int shift = n, q = 0;   // q walks rk[] (largest interval first)
+  for (int pth = cur - 1; pth >= 0; --pth) {
+    // every selected interval i >= pth has its new element after position i >= pth
+    while (q < n && idx[rk[q]] >= pth) {
+      b.order[I2(idx[rk[q]] + shift, s)] = (uint16_t)(cur + rk[q]);
+      --shift; ++q;
+    }
+    if (shift == 0) break;
+    b.order[I2(pth + shift, s)] = b.order[I2(pth, s)];
+  }
+}
+
+template <int NL, bool COMP, int NT>
+__device__ void refine_solve_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int round, EASmem<NL * NL + 1, COMP, NT>& sm, int tid, int64_t g) {
+  constexpr int D = NL * NL + 1;
+  const int64_t ns = nsrc(cfg, b);
+  // consecutive threads = consecutive sources of the same new point (coalesced)
+  const int r = (int)(g / cfg.S);
+  const int64_t s = g - (int64_t)r * cfg.S;
+  const bool active = r < cfg.nadd && s < ns;
+  const int slot = cfg.N0 + round * cfg.nadd + r;
+  cd w = mk(0.3, 0.2);
+  if (active) {
+    const cd w0 = source_centre(cfg, b, L, s);
+    w = limb_point(w0, cfg.rho, b.theta[I2(slot, s)]);
+    const int lf = b.left[I2(r, s)];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      sm.zre[j][tid] = b.zre[I3(lf, j, s)] + JIT_RE;
+      sm.zim[j][tid] = b.zim[I3(lf, j, s)] + JIT_IM;
+    }
+  }
+  solve_and_store<NL, COMP, NT>(cfg, b, L, sm, tid, active, w, true, slot, s);
+}
+
+__device__ void refine_solve_single_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int round, int64_t g) {
+  const int r = (int)(g / cfg.S);
+  const int64_t s = g - (int64_t)r * cfg.S;
+  if (r >= cfg.nadd || s >= nsrc(cfg, b)) return;
+  const int slot = cfg.N0 + round * cfg.nadd + r;
+  store_single(cfg, b, limb_point(source_centre(cfg, b, L, s), cfg.rho, b.theta[I2(slot, s)]), slot, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// theta order + duplicate guard + greedy nearest-neighbour track matching (utils.py:15-40): for each
+// track i in order, the nearest not-yet-taken root of the next limb point (ties: lowest index).
+template <int D>
+__device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
+  if (s >= nsrc(cfg, b)) return;
+  double cre[D], cim[D];   // carry: previous column in track order
+  for (int p = 0; p < cfg.NP; ++p) {
+    const int slot = b.order[I2(p, s)];
+    double zr[D], zi[D];
+    uint8_t f[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { zr[j] = b.zre[I3(slot, j, s)]; zi[j] = b.zim[I3(slot, j, s)]; f[j] = b.flg[I3(slot, j, s)]; }
+    // exact duplicates (inside the column, or an unchanged warm start) get a tiny real offset
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      bool dup = false;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        if (k < j && zr[k] == zr[j] && zi[k] == zi[j]) dup = true;
+        if (p > 0 && cre[k] == zr[j] && cim[k] == zi[j]) dup = true;
+      }
+      if (dup) zr[j] += DUP_JIT;
+    }
+    unsigned used = 0;
+    double nre[D], nim[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      int best = i;
+      if (p > 0) {
+        double bd = 1e300;
+        best = 0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double dx = zr[k] - cre[i], dy = zi[k] - cim[i];
+          const double d2 = dx * dx + dy * dy;
+          if (!((used >> k) & 1u) && d2 < bd) { bd = d2; best = k; }
+        }
+        if (bd == 1e300) {   // NaNs: take the first free slot
+#pragma unroll
+          for (int k = D - 1; k >= 0; --k) if (!((used >> k) & 1u)) best = k;
+        }
+      }
+      used |= 1u << best;
+      double vr = 0, vi = 0; uint8_t vf = 0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) if (k == best) { vr = zr[k]; vi = zi[k]; vf = f[k]; }
+      nre[i] = vr; nim[i] = vi;
+      b.sre[I3(p, i, s)] = vr;
+      b.sim[I3(p, i, s)] = vi;
+      b.sflg[I3(p, i, s)] = vf;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) { cre[i] = nre[i]; cim[i] = nim[i]; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Contours.  A segment is an index range [lo, hi) of one track; a stitched contour is a chain of
+// (segment, reversed) pieces.  Points are read from the theta-ordered arrays on demand.
+struct Seg { int16_t track, lo, hi; int8_t par; double len; };
+
+struct Tracks {
+  const ExtCfg& cfg; const ExtBuf& b; int64_t s;
+  __device__ __forceinline__ cd pt(int track, int p) const {
+    return mk(b.sre[(((int64_t)p * cfg.D + track) * cfg.S + s)], b.sim[(((int64_t)p * cfg.D + track) * cfg.S + s)]);
+  }
+  __device__ __forceinline__ uint8_t fl(int track, int p) const {
+    return b.sflg[(((int64_t)p * cfg.D + track) * cfg.S + s)];
+  }
+};
+
+struct Chain {
+  // pieces live in a deque so that H-T / H-H connections can prepend (extended_source.py:445-492)
+  int8_t seg[64]; int8_t rev[64]; int head, tail;   // pieces [head, tail)
+  int npts;
+  __device__ void init(int sg, int n) { head = 32; tail = 33; seg[32] = (int8_t)sg; rev[32] = 0; npts = n; }
+};
+
+__device__ __forceinline__ int seg_n(const Seg& g) { return g.hi - g.lo; }
+__device__ __forceinline__ cd seg_pt(const Tracks& T, const Seg& g, int k, bool reversed) {
+  return T.pt(g.track, reversed ? g.hi - 1 - k : g.lo + k);
+}
+// k-th point of the chain counted from its head (from_tail: from its tail); 0 beyond the ends, like
+// the reference's zero padding
+__device__ cd chain_pt(const Tracks& T, const Seg* segs, const Chain& c, int k, bool from_tail) {
+  if (k < 0 || k >= c.npts) return mk(0, 0);
+  if (!from_tail) {
+    for (int q = c.head; q < c.tail; ++q) {
+      const Seg& g = segs[c.seg[q]];
+      const int n = seg_n(g);
+      if (k < n) return seg_pt(T, g, k, c.rev[q]);
+      k -= n;
+    }
+  } else {
+    for (int q = c.tail - 1; q >= c.head; --q) {
+      const Seg& g = segs[c.seg[q]];
+      const int n = seg_n(g);
+      if (k < n) return seg_pt(T, g, n - 1 - k, c.rev[q]);
+      k -= n;
+    }
+  }
+  return mk(0, 0);
+}
+__device__ __forceinline__ double chain_parity(const Seg* segs, const Chain& c) {
+  const double p = segs[c.seg[c.head]].par;
+  return c.rev[c.head] ? -p : p;
+}
+// the two points that define the direction at an end, connection point last; a near-duplicate end
+// vertex (< 1e-5) is skipped (extended_source.py:368-390)
+__device__ void end_line(const Tracks& T, const Seg* segs, const Chain& c, bool tail, cd& a, cd& bb) {
+  const int t = c.npts - 1;
+  const cd p0 = chain_pt(T, segs, c, 0, tail), p1 = chain_pt(T, segs, c, 1, tail);
+  if (norm2(p1 - p0) > 1e-10 || t <= 1) { a = p1; bb = p0; }
+  else { a = chain_pt(T, segs, c, 2, tail); bb = p1; }
+}
+__device__ bool connect_ok(const Tracks& T, const Seg* segs, const Chain& c1, const Chain& c2, int ctype) {
+  const bool same = chain_parity(segs, c1) * chain_parity(segs, c2) > 0.0;
+  if ((ctype < 2) != same) return false;
+  cd a1, b1, a2, b2;
+  end_line(T, segs, c1, ctype == 0 || ctype == 3, a1, b1);
+  end_line(T, segs, c2, ctype == 1 || ctype == 3, a2, b2);
+  const double dist2 = norm2(b1 - b2);
+  if (dist2 < 1e-10) return true;                       // dist < min_dist
+  if (!(dist2 < 1e-2)) return false;                    // dist < max_dist = 0.1
+  const cd v1 = b1 - a1, v2 = b2 - a2;
+  const double cosang = (v1.re * v2.re + v1.im * v2.im) * rsqrt(norm2(v1) * norm2(v2));
+  // 180 - deg(acos(c)) < 60  <=>  acos(c) > 120 deg  <=>  c < -1/2
+  if (!(cosang < -0.5)) return false;
+  return dist2 < norm2(a1 - a2);                        // ends closer than the points before them
+}
+
+struct GreenAcc {
+  // uniform: 1/2 sum (x_i y_{i+1} - x_{i+1} y_i), the trapezoid rule of integrate.py:23-27
+  double sum; cd first, prev; bool any;
+  __device__ void start() { sum = 0.0; any = false; }
+  __device__ void add(cd z) {
+    if (any) sum += 0.5 * (prev.re * z.im - z.re * prev.im);
+    else { first = z; any = true; }
+    prev = z;
+  }
+  __device__ double close() { if (any) add(first); return sum; }
+};
+
+// limb-darkening vertex emitter: appends the vertices of one closed contour (closing point included)
+struct LdEmit {
+  const ExtCfg& cfg; const ExtBuf& b; int64_t s; int nv, nc; cd first, csum; int cnt0; bool any;
+  __device__ void start() { any = false; csum = mk(0, 0); cnt0 = nv; }
+  __device__ void put(cd z) {
+    if (nv < cfg.VMAX) { b.vz[(int64_t)nv * cfg.S + s] = make_cb200_d2(z.re, z.im); b.vcid[(int64_t)nv * cfg.S + s] = (uint8_t)nc; }
+    ++nv; csum = csum + z;
+  }
+  __device__ void add(cd z) { if (!any) { first = z; any = true; } put(z); }
+  __device__ void close(double parity) {
+    if (!any) return;
+    put(first);
+    if (nc < cfg.CMAX) {
+      const double inv = 1.0 / (double)(nv - cnt0);      // centroid incl. the closing point (integrate.py:112)
+      b.cz0[(int64_t)nc * cfg.S + s] = make_cb200_d2(csum.re * inv, csum.im * inv);
+      b.cpar[(int64_t)nc * cfg.S + s] = parity;
+      b.cstart[(int64_t)nc * cfg.S + s] = cnt0;
+    }
+    ++nc;
+  }
+};
+
+template <int D>
+__device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s) {
+  if (s >= nsrc(cfg, b)) return;
+  const Tracks T{cfg, b, s};
+  const int NP = cfg.NP;
+  const double norm = 1.0 / (3.14159265358979323846 * cfg.rho * cfg.rho);
+  const int64_t out_idx = b.list ? (int64_t)b.list[s] : s;
+  double total = 0.0;
+  LdEmit E{cfg, b, s, 0, 0};
+  GreenAcc G;
+
+  // closed tracks: every image real and the track returns to its start (extended_source.py:290)
+  unsigned closed = 0;
+  for (int i = 0; i < D; ++i) {
+    bool all_real = true;
+    for (int p = 0; p < NP; ++p) all_real = all_real && (T.fl(i, p) & 1);
+    const bool cl = cfg.nl == 1 || (all_real && norm2(T.pt(i, 0) - T.pt(i, NP - 1)) < 1e-10);
+    if (!cl) continue;
+    closed |= 1u << i;
+    const uint8_t f0 = T.fl(i, 0);
+    const double par = (f0 & 4) ? 0.0 : ((f0 & 2) ? 1.0 : -1.0);
+    if (cfg.ld) {
+      E.start();
+      for (int p = 0; p < NP; ++p) E.add(T.pt(i, p));
+      E.close(par);
+    } else {
+      G.start();
+      for (int p = 0; p < NP; ++p) G.add(T.pt(i, p));
+      total += par * G.close();
+    }
+  }
+
+  if (closed != (1u << D) - 1u) {
+    // ---- split the open tracks into runs of real images of one parity without jumps > 0.1
+    Seg parts[MAXSEG];
+    int nparts_total = 0;
+    // The reference keeps, of all parts in (track, start) order REVERSED, the first 3(nl^2+1) that
+    // have at least two points; walk the tracks backwards and each track's parts backwards.
+    const int nseg_max = 3 * (cfg.nl * cfg.nl + 1);
+    for (int i = D - 1; i >= 0 && nparts_total < nseg_max; --i) {
+      if ((closed >> i) & 1u) continue;
+      int16_t lo[MAXPARTS], hi[MAXPARTS];
+      int np_ = 0, nend = 0;
+      // boundaries in increasing order; the first MAXPARTS starts and ends are kept (:202-203)
+      bool prev_real = false; double prev_par = 0.0; cd prev_z = mk(0, 0);
+      for (int p = 0; p <= NP; ++p) {
+        bool real = false; double par = 0.0; cd z = mk(0, 0);
+        if (p < NP) {
+          const uint8_t f = T.fl(i, p);
+          real = f & 1;
+          if (real) { par = (f & 4) ? 0.0 : ((f & 2) ? 1.0 : -1.0); z = T.pt(i, p); }
+        }
+        bool start = false, end = false;
+        if (p == 0) start = real;
+        else if (p == NP) end = prev_real;
+        else {
+          const double dm = (real ? 1.0 : 0.0) - (prev_real ? 1.0 : 0.0);
+          const bool change = norm2(z - prev_z) > 0.01 || par != prev_par || dm != 0.0;
+          start = change && dm >= 0.0;
+          end = change && dm <= 0.0;
+        }
+        if (end && nend < MAXPARTS) hi[nend++] = (int16_t)p;
+        if (start && np_ < MAXPARTS) lo[np_++] = (int16_t)p;
+        prev_real = real; prev_par = par; prev_z = z;
+      }
+      const int npair = np_ < nend ? np_ : nend;   // k-th start pairs with k-th end
+      for (int k = npair - 1; k >= 0 && nparts_total < nseg_max; --k) {
+        // a pair (0, 0) is the reference's "empty" marker; fewer than two points are dropped (:232)
+        if (hi[k] - lo[k] < 2 || (lo[k] == 0 && hi[k] == 0)) continue;
+        Seg g; g.track = (int16_t)i; g.lo = lo[k]; g.hi = hi[k];
+        const uint8_t f = T.fl(i, lo[k]);
+        g.par = (f & 4) ? 0 : ((f & 2) ? 1 : -1);
+        double len = 0.0; cd q0 = T.pt(i, lo[k]);
+        for (int p = lo[k] + 1; p < hi[k]; ++p) { const cd q1 = T.pt(i, p); len += sqrt(norm2(q1 - q0)); q0 = q1; }
+        g.len = len;
+        parts[nparts_total++] = g;
+      }
+    }
+    // ---- stitch (extended_source.py:495-667): three rounds; the active chain starts from the
+    // shortest remaining segment and grows by the closest admissible connection
+    bool alive[MAXSEG];
+    for (int k = 0; k < nparts_total; ++k) alive[k] = true;
+    int pool_size = nseg_max;                 // fixed-shape pool incl. empty slots, shrinks by one per round
+    int max_in = 20;
+    for (int round = 0; round < 3; ++round, max_in -= 2) {
+      int a = -1;
+      for (int k = 0; k < nparts_total; ++k)
+        if (alive[k] && parts[k].len != 0.0 && (a < 0 || parts[k].len < parts[a].len)) a = k;
+      --pool_size;
+      if (a < 0) break;                       // only empty segments left: the remaining contours are empty
+      alive[a] = false;
+      Chain act; act.init(a, seg_n(parts[a]));
+      for (int step = 0; step < max_in; ++step) {
+        int nreal = 0;
+        for (int k = 0; k < nparts_total; ++k) nreal += alive[k] ? 1 : 0;
+        if (nreal == 0) break;
+        const int nempty = pool_size - nreal;
+        const cd ah = chain_pt(T, parts, act, 0, false), at = chain_pt(T, parts, act, 0, true);
+        const double dh0 = norm2(ah), dt0 = norm2(at);   // distance^2 to an empty segment's (0, 0) ends
+        // the four closest (connection type, segment) pairs in increasing distance; empty slots
+        // take up places in that ranking exactly as the reference's zero rows do
+        double lastd = -1.0; int lastc = -1, lastk = -1;
+        bool merged = false, exhausted = false;
+        for (int rank = 0; rank < 4 && !merged && !exhausted; ) {
+          double bd = 1e300; int bc = -1, bk = -1;
+          for (int c = 0; c < 4; ++c)
+            for (int k = 0; k < nparts_total; ++k) {
+              if (!alive[k]) continue;
+              const cd mine = (c == 0 || c == 3) ? at : ah;
+              const Seg& g = parts[k];
+              const cd theirs = (c == 0 || c == 2) ? T.pt(g.track, g.lo) : T.pt(g.track, g.hi - 1);
+              const double d2 = norm2(mine - theirs);
+              const bool after_last = d2 > lastd || (d2 == lastd && (c > lastc || (c == lastc && k > lastk)));
+              if (after_last && d2 < bd) { bd = d2; bc = c; bk = k; }
+            }
+          if (bc < 0) { exhausted = true; break; }
+          // empty slots closer than this candidate: T-H and T-T at |tail|, H-T and H-H at |head|
+          int ahead = 0;
+          if (nempty > 0) ahead = (dt0 < bd ? 2 * nempty : 0) + (dh0 < bd ? 2 * nempty : 0);
+          // (rank counts real candidates already examined)
+          if (rank + ahead >= 4) { exhausted = true; break; }
+          Chain other; other.init(bk, seg_n(parts[bk]));
+          if (connect_ok(T, parts, act, other, bc)) {
+            const int n2 = seg_n(parts[bk]);
+            if (bc == 0) { act.seg[act.tail] = (int8_t)bk; act.rev[act.tail] = 0; ++act.tail; }
+            else if (bc == 1) { --act.head; act.seg[act.head] = (int8_t)bk; act.rev[act.head] = 0; }
+            else if (bc == 2) { --act.head; act.seg[act.head] = (int8_t)bk; act.rev[act.head] = 1; }
+            else { act.seg[act.tail] = (int8_t)bk; act.rev[act.tail] = 1; ++act.tail; }
+            act.npts += n2;
+            alive[bk] = false;
+            merged = true;
+          }
+          lastd = bd; lastc = bc; lastk = bk; ++rank;
+        }
+        if (!merged) break;                    // nothing can change in the remaining scan steps
+      }
+      // close the contour (:724-725) and integrate
+      const double par = chain_parity(parts, act);
+      if (cfg.ld) E.start(); else G.start();
+      for (int q = act.head; q < act.tail; ++q) {
+        const Seg& g = parts[act.seg[q]];
+        const int n = seg_n(g);
+        for (int k = 0; k < n; ++k) {
+          const cd z = seg_pt(T, g, k, act.rev[q]);
+          if (cfg.ld) E.add(z); else G.add(z);
+        }
+      }
+      if (cfg.ld) E.close(par); else total += par * G.close();
+    }
+  }
+  if (cfg.ld) {
+    b.vcount[s] = E.nv < cfg.VMAX ? E.nv : cfg.VMAX;
+    b.cstart[(int64_t)(E.nc < cfg.CMAX ? E.nc : cfg.CMAX) * cfg.S + s] = E.nv < cfg.VMAX ? E.nv : cfg.VMAX;
+    b.ncont[s] = E.nc < cfg.CMAX ? E.nc : cfg.CMAX;
+  } else {
+    b.mag[out_idx] = fabs(total) * norm;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Limb darkening (integrate.py:29-121).  I(r) = 3/(3-u1) (u1 B(r) + 1 - 2 u1), B = 1 + sqrt(1-r^2)
+// inside the disk, 1 - sqrt(1 - 1/r^2) outside.
+template <int NL>
+__device__ __forceinline__ double brightness(const LensConst& L, cd z, cd w0, double inv_rho2, double u1) {
+  cd s1 = mk(0, 0);
+  const cd zb = conj(z);
+  if (NL == 1) s1 = crecip(zb);
+  else {
+#pragma unroll
+    for (int j = 0; j < NL; ++j) s1 = s1 + L.eps[j] * crecip(zb - conj(L.r[j]));
+  }
+  const double r2 = norm2((z - s1) - w0) * inv_rho2;
+  double B;
+  if (r2 <= 1.0) B = 1.0 + sqrt(fmax(1.0 - r2, 0.0));
+  else B = 1.0 - sqrt(fmax(1.0 - 1.0 / r2, 0.0));
+  return 3.0 / (3.0 - u1) * (u1 * B + 1.0 - 2.0 * u1);
+}
+// two Gauss-Legendre panels [a, split] (n1 nodes) and [split, b] (n2 nodes), integrate.py:56-75.
+// `along_y`: integrate I(x + i t) dt, else I(t + i y) dt.
+template <int NL>
+__device__ double two_panel(const ExtCfg& cfg, const ExtBuf& bf, const LensConst& L, double a, double b,
+                            double fixed, bool along_y, cd w0) {
+  const double rho = cfg.rho, inv_rho2 = 1.0 / (rho * rho);
+  const double ad = fabs(b - a);
+  double split = b > a ? b - 2.0 * rho : b + 2.0 * rho;
+  if (0.5 * ad <= 2.0 * rho) split = a + 0.5 * ad;   // NB lies outside [b, a] when b < a (App. C-10)
+  double tot = 0.0;
+  for (int panel = 0; panel < 2; ++panel) {
+    const double lo = panel == 0 ? a : split, hi = panel == 0 ? split : b;
+    const int n = panel == 0 ? cfg.n1 : cfg.n2, off = panel == 0 ? 0 : cfg.n1;
+    const double hw = 0.5 * (hi - lo), mid = 0.5 * (hi + lo);
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const double t = fma(hw, bf.glx[off + k], mid);
+      const cd z = along_y ? mk(fixed, t) : mk(t, fixed);
+      acc += (hw * brightness<NL>(L, z, w0, inv_rho2, cfg.u1)) * bf.glw[off + k];
+    }
+    tot += acc;
+  }
+  return tot;
+}
+
+template <int NL>
+__device__ void ld_pq_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t g) {
+  const int v = (int)(g / cfg.S);
+  const int64_t s = g - (int64_t)v * cfg.S;
+  if (v >= cfg.VMAX || s >= nsrc(cfg, b)) return;
+  if (v >= b.vcount[s]) return;
+  const cd w0 = source_centre(cfg, b, L, s);
+  const cb200_d2 zz = b.vz[(int64_t)v * cfg.S + s];
+  const int c = b.vcid[(int64_t)v * cfg.S + s];
+  const cb200_d2 z0 = b.cz0[(int64_t)c * cfg.S + s];
+  // P = -1/2 int_{y0}^{y} I(x + i y') dy',  Q = +1/2 int_{x0}^{x} I(x' + i y) dx'
+  b.vP[(int64_t)v * cfg.S + s] = -0.5 * two_panel<NL>(cfg, b, L, z0.y, zz.y, zz.x, true, w0);
+  b.vQ[(int64_t)v * cfg.S + s] = 0.5 * two_panel<NL>(cfg, b, L, z0.x, zz.x, zz.y, false, w0);
+}
+
+__device__ void ld_sum_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
+  if (s >= nsrc(cfg, b)) return;
+  const int nc = b.ncont[s];
+  double total = 0.0;
+  for (int c = 0; c < nc; ++c) {
+    const int v0 = b.cstart[(int64_t)c * cfg.S + s], v1 = b.cstart[(int64_t)(c + 1) * cfg.S + s];
+    double acc = 0.0;
+    for (int v = v0; v + 1 < v1; ++v) {
+      const cb200_d2 za = b.vz[(int64_t)v * cfg.S + s], zb = b.vz[(int64_t)(v + 1) * cfg.S + s];
+      const double Pa = b.vP[(int64_t)v * cfg.S + s], Pb = b.vP[(int64_t)(v + 1) * cfg.S + s];
+      const double Qa = b.vQ[(int64_t)v * cfg.S + s], Qb = b.vQ[(int64_t)(v + 1) * cfg.S + s];
+      acc += 0.5 * (Pa + Pb) * (zb.x - za.x) + 0.5 * (Qa + Qb) * (zb.y - za.y);
+    }
+    total += acc * b.cpar[(int64_t)c * cfg.S + s];
+  }
+  const int64_t out_idx = b.list ? (int64_t)b.list[s] : s;
+  b.mag[out_idx] = fabs(total) / (3.14159265358979323846 * cfg.rho * cfg.rho);
+}
+
+// ---------------------------------------------------------------------------------------------
+// `mag` gate for the binary lens (lightcurve.py:202-225): point-source images, hexadecapole value
+// and the validity tests; points that fail are appended to the compact list for full integration.
+__device__ __forceinline__ cd cpow3(cd a) { return a * a * a; }
+
+template <bool COMP, int NT>
+__device__ void gate_body(const cb200_d2* __restrict__ w_in, double* __restrict__ mag, uint8_t* __restrict__ test_out,
+                          int32_t* __restrict__ list, int32_t* __restrict__ count, int64_t n, const LensConst& L,
+                          double rho, double q, int itmax, EASmem<5, COMP, NT>& sm, int tid, int64_t idx) {
+  constexpr int D = 5;
+  const bool active = idx < n;
+  cd w = mk(0.3, 0.2);
+  if (active) { const cb200_d2 v = w_in[idx]; w = mk(v.x + L.x_cm, v.y); }
+  cd p[D + 1];
+  lens_poly<2>(L, w, p);
+  ea_normalise<D>(p);
+  ea_solve_thread<D, COMP, NT>(p, sm, tid, active, false, EA_INIT_REFERENCE, itmax);
+  if (!active) return;
+  const double a = L.r[0].re, e1 = L.eps[0], e2 = L.eps[1];
+  const double rr = rho + 1e-3;  // rho + rho_min
+  double mu = 0.0, dmu = 0.0, mu_cusp = 0.0, ffalse = 0.0;
+  int nfalse = 0;
+#pragma unroll 1
+  for (int j = 0; j < D; ++j) {
+    const cd z = mk(sm.zre[j][tid], sm.zim[j][tid]);
+    bool real_image; double detj;
+    image_eval<2>(L, z, w, real_image, detj);
+    // derivatives of f(z) = -e1/(z-a) - e2/(z+a), lightcurve.py:29-33
+    auto fp = [&](cd x) { const cd u = crecip(x - mk(a, 0)), v = crecip(x + mk(a, 0)); return e1 * (u * u) + e2 * (v * v); };
+    auto fpp = [&](cd x) { const cd u = crecip(mk(a, 0) - x), v = crecip(mk(a, 0) + x); return 2.0 * (e1 * cpow3(u) - e2 * cpow3(v)); };
+    const cd zb = conj(z);
+    const cd fz = -(e1 * crecip(z - mk(a, 0))) - e2 * crecip(z + mk(a, 0));
+    const cd zhat = conj(w) - fz;
+    const cd fp_z = fp(z), fpp_z = fpp(z), fp_zb = fp(zb), fp_zh = fp(zhat), fpp_zb = fpp(zb);
+    const double J = 1.0 - sqrt(norm2(fp_z * fp_zb));
+    if (real_image) {
+      double m0, dq, dh;
+      hexadecapole_terms<2>(L, z, rho, 0.0, m0, dq, dh);   // u1 is not forwarded
+      mu += fabs(m0 + dq + dh);
+      dmu += fabs(dq) + fabs(dh);
+      const cd t = 3.0 * (cpow3(fp_zb) * (fpp_z * fpp_z));
+      const double J5 = J * J * J * J * J;
+      mu_cusp += fabs(6.0 * t.im / J5 * (rr * rr));
+    } else {
+      const double Jh = 1.0 - sqrt(norm2(fp_z * fp_zh));
+      const cd den = (Jh * fpp_zb) * fp_z - (Jh * fpp_z) * (fp_zb * fp_zh);   // conj(Jhat) = Jhat (real)
+      ffalse += fabs(J * Jh * Jh) * rsqrt(norm2(den));
+      ++nfalse;
+    }
+  }
+  bool ok = (0.02 * mu_cusp + dmu < 1e-2) && (nfalse == 0 || 0.5 * ffalse > 4.0 * rr);
+  if (q < 0.01) {
+    // planetary-caustic test, lightcurve.py:78-85
+    const double s_ = 2.0 * a, qq = e1 / (1.0 - e1);
+    const double wpc = -1.0 / s_, dpc = 3.0 * sqrt(qq) / s_;
+    const double dx = wpc - w.re, dy = -w.im;
+    ok = ok && (dx * dx + dy * dy > 2.0 * (rho * rho + dpc * dpc));
+  }
+  mag[idx] = mu;
+  if (test_out) test_out[idx] = ok ? 1 : 0;
+  if (!ok) list[cb200_atomic_inc(count)] = (int32_t)idx;
+}
+
+
+}  // namespace cb200

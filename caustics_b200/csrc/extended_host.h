@@ -1,0 +1,95 @@
+// Host-side configuration / workspace layout of kernel family 3, shared by extended.cu (the CUDA
+// driver) and the host logic tests (tests/hostsim).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/caustics_b200.h"
+#include "extended_core.cuh"
+
+namespace cb200 {
+
+inline void leggauss(int n, double* x, double* w) {
+  // Newton iteration on P_n; nodes ascending like numpy.polynomial.legendre.leggauss
+  for (int i = 0; i < n; ++i) {
+    double t = cos(3.14159265358979323846 * (i + 0.75) / (n + 0.5));
+    double dp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p0 = 1.0, p1 = t;
+      for (int k = 2; k <= n; ++k) { const double p2 = ((2.0 * k - 1.0) * t * p1 - (k - 1.0) * p0) / k; p0 = p1; p1 = p2; }
+      if (n == 1) { p0 = 1.0; p1 = t; }
+      dp = n * (t * p1 - p0) / (t * t - 1.0);
+      const double dt = p1 / dp;
+      t -= dt;
+      if (fabs(dt) < 1e-16) break;
+    }
+    double p0 = 1.0, p1 = t;
+    for (int k = 2; k <= n; ++k) { const double p2 = ((2.0 * k - 1.0) * t * p1 - (k - 1.0) * p0) / k; p0 = p1; p1 = p2; }
+    dp = n * (t * p1 - p0) / (t * t - 1.0);
+    x[n - 1 - i] = t;
+    w[n - 1 - i] = 2.0 / ((1.0 - t * t) * dp * dp);
+  }
+}
+
+struct Layout {
+  size_t theta, zre, zim, flg, order, left, sre, sim, sflg, vz, vP, vQ, vcid, vcount, ncont, cz0, cpar, cstart, gl, list, count, total;
+};
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+inline Layout make_layout(const ExtCfg& c) {
+  Layout l; size_t o = 0;
+  const size_t S = (size_t)c.S, NP = c.NP, D = c.D;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
+  l.theta = take(NP * S * 8);
+  l.zre = take(NP * D * S * 8); l.zim = take(NP * D * S * 8); l.flg = take(NP * D * S);
+  l.order = take(NP * S * 2); l.left = take((size_t)NADD_MAX * S * 2);
+  l.sre = take(NP * D * S * 8); l.sim = take(NP * D * S * 8); l.sflg = take(NP * D * S);
+  if (c.ld) {
+    l.vz = take((size_t)c.VMAX * S * 16); l.vP = take((size_t)c.VMAX * S * 8); l.vQ = take((size_t)c.VMAX * S * 8);
+    l.vcid = take((size_t)c.VMAX * S); l.vcount = take(S * 4); l.ncont = take(S * 4);
+    l.cz0 = take((size_t)c.CMAX * S * 16); l.cpar = take((size_t)c.CMAX * S * 8); l.cstart = take((size_t)(c.CMAX + 1) * S * 4);
+    l.gl = take((size_t)(c.n1 + c.n2) * 16);
+  } else { l.vz = l.vP = l.vQ = l.vcid = l.vcount = l.ncont = l.cz0 = l.cpar = l.cstart = l.gl = 0; }
+  l.list = take(S * 4); l.count = take(256);
+  l.total = o;
+  return l;
+}
+
+inline int make_cfg(int64_t S, double rho, int nlenses, int npts_limb, int limb_darkening, double u1, int npts_ld,
+             int itmax, int compensated, ExtCfg* out) {
+  if (S < 0 || !(rho > 0.0) || nlenses < 1 || nlenses > 3 || itmax < 0) return CAUSTICS_ERR_BAD_ARG;
+  ExtCfg c; memset(&c, 0, sizeof(c));
+  c.nl = nlenses; c.D = nlenses == 1 ? 2 : nlenses * nlenses + 1;
+  c.N0 = (int)(0.5 * npts_limb);
+  c.nadd = (int)((int)(0.5 * npts_limb) / NITER);
+  c.NP = c.N0 + NITER * c.nadd;
+  if (c.N0 < 4 || c.nadd < 1 || c.nadd > NADD_MAX || c.NP > 4000) return CAUSTICS_ERR_BAD_ARG;
+  c.rho = rho; c.itmax = itmax; c.comp = compensated ? 1 : 0;
+  c.ld = limb_darkening ? 1 : 0; c.u1 = u1;
+  c.n1 = npts_ld / 2; c.n2 = npts_ld - c.n1;
+  if (c.ld && (c.n1 < 1 || npts_ld > 2048)) return CAUSTICS_ERR_BAD_ARG;
+  c.CMAX = c.D + 3;
+  c.VMAX = c.D * c.NP + c.CMAX;
+  c.S = S > 0 ? S : 1;
+  *out = c;
+  return CAUSTICS_OK;
+}
+
+inline ExtBuf bind(const ExtCfg& c, const Layout& l, void* ws) {
+  char* base = (char*)ws;
+  ExtBuf b; memset(&b, 0, sizeof(b));
+  b.theta = (double*)(base + l.theta);
+  b.zre = (double*)(base + l.zre); b.zim = (double*)(base + l.zim); b.flg = (uint8_t*)(base + l.flg);
+  b.order = (uint16_t*)(base + l.order); b.left = (uint16_t*)(base + l.left);
+  b.sre = (double*)(base + l.sre); b.sim = (double*)(base + l.sim); b.sflg = (uint8_t*)(base + l.sflg);
+  if (c.ld) {
+    b.vz = (cb200_d2*)(base + l.vz); b.vP = (double*)(base + l.vP); b.vQ = (double*)(base + l.vQ);
+    b.vcid = (uint8_t*)(base + l.vcid); b.vcount = (int32_t*)(base + l.vcount); b.ncont = (int32_t*)(base + l.ncont);
+    b.cz0 = (cb200_d2*)(base + l.cz0); b.cpar = (double*)(base + l.cpar); b.cstart = (int32_t*)(base + l.cstart);
+    b.glx = (const double*)(base + l.gl); b.glw = b.glx + (c.n1 + c.n2);
+  }
+  return b;
+}
+
+}  // namespace cb200

@@ -233,6 +233,11 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters,
 }  // namespace
 
 // ============================================================================================
+// used by extended.cu (same lens constants for every kernel family); not part of the public ABI
+extern "C" __attribute__((visibility("hidden"))) int caustics_internal_lens_const(const caustics_lens* lens, void* out) {
+  return make_lens_const(lens, (LensConst*)out);
+}
+
 extern "C" {
 
 int caustics_bench_fp64_peak(double* sink, int blocks, int iters, void* stream) {

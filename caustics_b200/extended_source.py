@@ -1,0 +1,106 @@
+"""Host-side mirror of the reference's extended-source API
+(/root/reference/src/caustics/extended_source.py:741-904 `mag_extended_source`, and
+/root/reference/src/caustics/lightcurve.py:99-254 `mag`) on top of kernel family 3.
+
+Same names, keyword arguments and defaults as the reference.  `w0` / `w_points` may be a Python
+complex, a NumPy array or a torch tensor (CPU or CUDA) of any shape: every source position is an
+independent unit of work and the whole batch is evaluated by one sequence of kernel launches
+(the reference evaluates them one at a time under lax.map).  Results come back in the same kind of
+container.  All compute runs on the GPU; there is no CPU fallback.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .point_source import _c_lens, lens_params
+
+__all__ = ["mag_extended_source", "mag"]
+
+_MAX_WS_BYTES = 24 << 30      # per-call workspace budget; larger batches are processed in chunks
+
+
+def _to_device(w):
+    """-> (flat complex128 CUDA tensor, restore function)"""
+    if isinstance(w, torch.Tensor):
+        shape, dev = tuple(w.shape), w.device
+        flat = w.detach().to(device="cuda" if not w.is_cuda else dev, dtype=torch.complex128).reshape(-1).contiguous()
+        if w.is_cuda:
+            return flat, lambda m: m.reshape(shape)
+        return flat, lambda m: m.cpu().reshape(shape)
+    arr = np.asarray(w, dtype=np.complex128)
+    shape = arr.shape
+    flat = torch.from_numpy(np.ascontiguousarray(arr.reshape(-1))).cuda()
+    if shape == ():
+        return flat, lambda m: np.float64(m.cpu().numpy()[0])
+    return flat, lambda m: m.cpu().numpy().reshape(shape)
+
+
+def _chunk_len(L, n, nlenses, npts_limb, ld, npts_ld):
+    per1 = L.caustics_ext_workspace_bytes(1, nlenses, npts_limb, int(ld), npts_ld)
+    if per1 == 0:
+        raise ValueError("unsupported extended-source configuration "
+                         "(need 8 <= npts_limb <= 1280, nlenses in 1..3, npts_ld <= 2048)")
+    per = (L.caustics_ext_workspace_bytes(1024, nlenses, npts_limb, int(ld), npts_ld) + 1023) // 1024
+    deg = 2 if nlenses == 1 else nlenses**2 + 1
+    cap_idx = (2**31 - 1) // (deg * (npts_limb + 4) + 16)
+    return max(1, min(n, _MAX_WS_BYTES // per, cap_idx))
+
+
+def _run(w, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax, roots_compensated,
+         gate, q, params, return_test=False):
+    _lib.require_cuda()
+    L = _lib.lib()
+    p, x_cm = lens_params(nlenses, **params) if nlenses > 1 else ({}, 0.0)
+    lens = _c_lens(nlenses, x_cm, **p)
+    flat, restore = _to_device(w)
+    n = flat.numel()
+    mag = torch.empty(n, dtype=torch.float64, device=flat.device)
+    test = torch.empty(n, dtype=torch.uint8, device=flat.device) if gate else None
+    if n == 0:
+        return (restore(mag), restore(test.bool())) if return_test else restore(mag)
+    rho = float(rho)
+    chunk = _chunk_len(L, n, nlenses, npts_limb, limb_darkening, npts_ld)
+    with torch.cuda.device(flat.device):
+        st = torch.cuda.current_stream().cuda_stream
+        nbytes = L.caustics_ext_workspace_bytes(chunk, nlenses, npts_limb, int(limb_darkening), npts_ld)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
+        for off in range(0, n, chunk):
+            m = min(chunk, n - off)
+            wp = flat.data_ptr() + 16 * off
+            mp = mag.data_ptr() + 8 * off
+            if gate:
+                _lib.check(L.caustics_mag(wp, mp, test.data_ptr() + off, m, rho, lens, float(q), int(npts_limb),
+                                          int(bool(limb_darkening)), float(u1), int(npts_ld), int(roots_itmax),
+                                          int(bool(roots_compensated)), ws.data_ptr(), nbytes, st))
+            else:
+                _lib.check(L.caustics_mag_extended_source(wp, mp, m, rho, lens, int(npts_limb),
+                                                          int(bool(limb_darkening)), float(u1), int(npts_ld),
+                                                          int(roots_itmax), int(bool(roots_compensated)),
+                                                          ws.data_ptr(), nbytes, st))
+    if return_test:
+        return restore(mag), restore(test.bool())
+    return restore(mag)
+
+
+def mag_extended_source(w0, rho, nlenses=2, npts_limb=150, limb_darkening=False, u1=0.0, npts_ld=100,
+                        roots_itmax=2500, roots_compensated=False, **params):
+    """Magnification of a (limb-darkened) disk of radius `rho` centred on `w0` by contour
+    integration in the image plane; arguments as in the reference (extended_source.py:741-805)."""
+    if nlenses not in (1, 2, 3):
+        raise ValueError("`nlenses` has to be set to be <= 3.")
+    return _run(w0, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax, roots_compensated,
+                False, 0.0, params)
+
+
+def mag(w_points, rho, nlenses=2, npts_limb=200, limb_darkening=False, u1=0.0, npts_ld=100,
+        roots_itmax=2500, roots_compensated=False, return_test=False, **params):
+    """Light-curve magnification (lightcurve.py:99-254): the hexadecapole approximation where the
+    reference's validity tests pass (binary lens), full contour integration elsewhere.  For the
+    triple lens the reference forces full integration everywhere but leaves `mu_multi` unassigned and
+    cannot run; here it runs, with full integration at every point.
+    `return_test=True` also returns the boolean "hexadecapole was used" per point."""
+    if nlenses not in (1, 2, 3):
+        raise ValueError("nlenses must be <= 3")
+    q = params.get("q", 1.0) if nlenses == 2 else 1.0
+    return _run(w_points, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax,
+                roots_compensated, True, q, params, return_test=return_test)

@@ -123,6 +123,22 @@ int caustics_mag_point_source_grid(double x0, double y0, double dx, double dy, i
 int caustics_mag_point_source_host(const void* w, double* mag, int64_t n, const caustics_lens* lens,
                                    int itmax, int compensated, int flags);
 
+/* ---- kernel family 3: extended-source magnification by contour integration ------------------
+ * w (n) complex128 source-disk centres, rho the source radius, npts_limb / limb_darkening / u1 /
+ * npts_ld as in the reference (extended_source.py:741-753).  The phases keep their per-source state
+ * in `workspace` (device memory, caustics_ext_workspace_bytes(n, ...) bytes, borrowed for the call).
+ * caustics_mag is the light-curve entry (lightcurve.py:99-254): binary lenses use the hexadecapole
+ * approximation wherever the reference's validity tests pass (q is the user's mass ratio, tested
+ * against 0.01 for the planetary-caustic test) and full integration elsewhere; used_hexadecapole
+ * (n) uint8, optional, records the decision.  Limits: npts_limb <= 1280, n * (D*npts_limb) < 2^31. */
+size_t caustics_ext_workspace_bytes(int64_t n, int nlenses, int npts_limb, int limb_darkening, int npts_ld);
+int caustics_mag_extended_source(const void* w, double* mag, int64_t n, double rho, const caustics_lens* lens,
+                                 int npts_limb, int limb_darkening, double u1, int npts_ld, int itmax,
+                                 int compensated, void* workspace, size_t workspace_bytes, void* stream);
+int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t n, double rho,
+                 const caustics_lens* lens, double q, int npts_limb, int limb_darkening, double u1, int npts_ld,
+                 int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement aid -----------------------------------------------------------------------
  * Launches blocks x 256 threads, each running 8 independent chains of `iters` double-precision
  * FMAs (2 * 8 * 256 * blocks * iters flop).  bench.py times it to get the FP64 roofline peak. */

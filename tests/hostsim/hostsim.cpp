@@ -64,3 +64,90 @@ int hostsim_mag_ps(const double* w, double* mag, double* coeffs_out, int64_t n, 
   return 0;
 }
 }
+
+// ---- kernel family 3 (extended source): the phase bodies driven sequentially over the sources ----
+#include "../../caustics_b200/csrc/extended_host.h"
+#include <vector>
+
+static void fill_lens(LensConst& L, int nlenses, const double* eps, const double* r, const double* H,
+                      const double* G, double x_cm) {
+  memset(&L, 0, sizeof(L));
+  L.nlenses = nlenses; L.x_cm = x_cm;
+  for (int i = 0; i < 3; ++i) { L.eps[i] = eps[i]; L.r[i] = mk(r[2 * i], r[2 * i + 1]); }
+  for (int i = 0; i < 4; ++i) L.H[i] = mk(H[2 * i], H[2 * i + 1]);
+  for (int i = 0; i < 3; ++i) L.G[i] = mk(G[2 * i], G[2 * i + 1]);
+}
+
+template <int NL>
+static void ext_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, int64_t ns) {
+  constexpr int D = NL == 1 ? 2 : NL * NL + 1;
+  constexpr int NLS = NL == 1 ? 2 : NL;   // solver instantiation (unused for the single lens)
+  static EASmem<NLS * NLS + 1, false, 1> sm0;
+  static EASmem<NLS * NLS + 1, true, 1> sm1;
+  for (int64_t s = 0; s < ns; ++s) {
+    if (NL == 1) limb_walk_single_body(cfg, b, L, s); else limb_walk_body<NLS, 1>(cfg, b, L, sm0, 0, s);
+  }
+  for (int r = 0; r < NITER; ++r) {
+    for (int64_t s = 0; s < ns; ++s) refine_select_body<D>(cfg, b, r, s);
+    for (int64_t g = 0; g < (int64_t)cfg.nadd * cfg.S; ++g) {
+      if (NL == 1) refine_solve_single_body(cfg, b, L, r, g);
+      else if (cfg.comp) refine_solve_body<NLS, true, 1>(cfg, b, L, r, sm1, 0, g);
+      else refine_solve_body<NLS, false, 1>(cfg, b, L, r, sm0, 0, g);
+    }
+  }
+  for (int64_t s = 0; s < ns; ++s) tracks_body<D>(cfg, b, s);
+  for (int64_t s = 0; s < ns; ++s) contours_body<D>(cfg, b, L, s);
+  if (cfg.ld) {
+    for (int64_t g = 0; g < (int64_t)cfg.VMAX * cfg.S; ++g) ld_pq_body<NL>(cfg, b, L, g);
+    for (int64_t s = 0; s < ns; ++s) ld_sum_body(cfg, b, s);
+  }
+}
+
+extern "C" int hostsim_mag_extended(const double* w, double* mag, uint8_t* test_out, int64_t n, double rho, int nlenses,
+                                    const double* eps, const double* r, const double* H, const double* G, double x_cm,
+                                    double q, int gate, int npts_limb, int ld, double u1, int npts_ld, int itmax, int comp,
+                                    double* tracks_out /* optional (NP, D, 2) of source 0 */, uint8_t* flags_out) {
+  ExtCfg cfg;
+  int rc = make_cfg(n, rho, nlenses, npts_limb, ld, u1, npts_ld, itmax, comp, &cfg);
+  if (rc) return rc;
+  Layout lay = make_layout(cfg);
+  std::vector<char> ws(lay.total + 256, 0);
+  LensConst L;
+  fill_lens(L, nlenses, eps, r, H, G, x_cm);
+  if (nlenses == 1) { L.eps[0] = 1.0; L.x_cm = 0.0; }
+  ExtBuf b = bind(cfg, lay, ws.data());
+  b.w = (const cb200_d2*)w;
+  b.mag = mag;
+  int32_t* list = (int32_t*)(ws.data() + lay.list);
+  int32_t* count = (int32_t*)(ws.data() + lay.count);
+  if (cfg.ld) {
+    const int nn = cfg.n1 + cfg.n2;
+    double* tab = (double*)(ws.data() + lay.gl);
+    leggauss(cfg.n1, tab, tab + nn);
+    leggauss(cfg.n2, tab + cfg.n1, tab + nn + cfg.n1);
+  }
+  int64_t ns = n;
+  if (gate && nlenses == 2) {
+    *count = 0;
+    static EASmem<5, false, 1> g0;
+    static EASmem<5, true, 1> g1;
+    for (int64_t i = 0; i < n; ++i) {
+      if (comp) gate_body<true, 1>((const cb200_d2*)w, mag, test_out, list, count, n, L, rho, q, itmax, g1, 0, i);
+      else gate_body<false, 1>((const cb200_d2*)w, mag, test_out, list, count, n, L, rho, q, itmax, g0, 0, i);
+    }
+    b.list = list; b.count = count; ns = *count;
+  }
+  switch (nlenses) {
+    case 1: ext_pipeline<1>(cfg, b, L, ns); break;
+    case 2: ext_pipeline<2>(cfg, b, L, ns); break;
+    default: ext_pipeline<3>(cfg, b, L, ns); break;
+  }
+  if (tracks_out)
+    for (int p = 0; p < cfg.NP; ++p)
+      for (int j = 0; j < cfg.D; ++j) {
+        tracks_out[2 * (p * cfg.D + j)] = b.sre[((int64_t)p * cfg.D + j) * cfg.S];
+        tracks_out[2 * (p * cfg.D + j) + 1] = b.sim[((int64_t)p * cfg.D + j) * cfg.S];
+        if (flags_out) flags_out[p * cfg.D + j] = b.sflg[((int64_t)p * cfg.D + j) * cfg.S];
+      }
+  return 0;
+}

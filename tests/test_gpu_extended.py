@@ -1,0 +1,155 @@
+"""GPU tier: kernel family 3 (contour-integration extended-source magnification, limb darkening,
+hexadecapole gate) through the C ABI vs the oracle and the golden vectors from the reference.
+
+Tolerance: rtol 1e-4 against the CPU restatement of the reference algorithm.
+The kernels run the same Gauss-Seidel solver path as the reference, so agreement is normally
+~1e-10; the 1e-4 bar leaves room for a limb point whose warm start lands on another root after a
+last-bit difference (which changes which intervals get refined)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, c1_w
+from oracle import extended, lens
+
+pytestmark = pytest.mark.gpu
+HP2 = dict(s=0.9, q=0.2)
+HP3 = dict(s=0.9, q=0.2, q3=0.1, r3=0.8, psi=1.0)
+
+
+@pytest.fixture(scope="module")
+def cb(built_lib):
+    import caustics_b200
+    assert torch.cuda.is_available()
+    return caustics_b200
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(ROOT, "tests", "golden", "ext_golden.npz"))
+
+
+def _oracle(w, rho, nl, hp, **kw):
+    return np.array([extended.mag_extended_source(x, rho, nl, **kw, **hp) for x in w])
+
+
+@pytest.mark.parametrize("rho", [1e-1, 1e-2, 1e-3])
+def test_binary_uniform_near_caustics(cb, g, rho):
+    """tests/test_extended_source.py:259-274 setting (points within 2 rho of the caustic)"""
+    w = g[f"b_w_{rho}"]
+    got = cb.mag_extended_source(w, rho, nlenses=2, npts_limb=200, **HP2)
+    want = _oracle(w, rho, 2, HP2, npts_limb=200)
+    assert np.allclose(got, want, rtol=1e-4, atol=0)
+    assert (np.abs(got / want - 1) < 1e-8).mean() > 0.9
+    assert np.abs(got / g[f"b_unif_{rho}"] - 1).max() < 1e-3           # the reference's own numbers
+
+
+def test_binary_limb_darkened(cb, g):
+    """tests/test_extended_source.py:277-291 setting, u1 = 0.7"""
+    w = g["b_w_0.01"][:16]
+    got = cb.mag_extended_source(torch.from_numpy(w).cuda(), 1e-2, nlenses=2, npts_limb=200,
+                                 limb_darkening=True, u1=0.7, npts_ld=100, **HP2)
+    assert got.is_cuda and got.shape == (16,)
+    want = _oracle(w, 1e-2, 2, HP2, npts_limb=200, limb_darkening=True, u1=0.7, npts_ld=100)
+    assert np.allclose(got.cpu().numpy(), want, rtol=1e-4, atol=0)
+    assert np.abs(got.cpu().numpy() / g["b_ld_0.01"] - 1).max() < 1e-3
+    # u1 = 0 limb darkening == uniform disk (tests/test_extended_source.py:150-163, rtol 1e-3)
+    u0 = cb.mag_extended_source(w, 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.0, **HP2)
+    un = cb.mag_extended_source(w, 1e-2, nlenses=2, npts_limb=200, **HP2)
+    assert np.allclose(u0, un, rtol=1e-3)
+
+
+@pytest.mark.parametrize("npts", [150, 400, 500])
+def test_binary_other_sampling(cb, g, npts):
+    w = g["b_w_0.01"][:12]
+    got = cb.mag_extended_source(w, 1e-2, nlenses=2, npts_limb=npts, **HP2)
+    assert np.allclose(got, _oracle(w, 1e-2, 2, HP2, npts_limb=npts), rtol=1e-4, atol=0)
+
+
+@pytest.mark.parametrize("rho", [1e-1, 1e-2])
+def test_triple_uniform_near_caustics(cb, g, rho):
+    w = g[f"t_w_{rho}"]
+    got = cb.mag_extended_source(w, rho, nlenses=3, npts_limb=200, **HP3)
+    assert np.allclose(got, _oracle(w, rho, 3, HP3, npts_limb=200), rtol=1e-4, atol=0)
+    assert np.abs(got / g[f"t_unif_{rho}"] - 1).max() < 1e-3
+
+
+def test_triple_limb_darkened_and_compensated(cb, g):
+    w = g["t_w_0.01"][:6]
+    got = cb.mag_extended_source(w, 1e-2, nlenses=3, npts_limb=200, limb_darkening=True, u1=0.3, npts_ld=60, **HP3)
+    assert np.allclose(got, g["t_ld_0.01"], rtol=1e-3)
+    want = _oracle(w, 1e-2, 3, HP3, npts_limb=200, roots_compensated=True)
+    got = cb.mag_extended_source(w, 1e-2, nlenses=3, npts_limb=200, roots_compensated=True, **HP3)
+    assert np.allclose(got, want, rtol=1e-4, atol=0)
+
+
+def test_single_lens(cb, g):
+    """tests/test_extended_source.py:134-183; closed form for a source centred on the lens"""
+    for rho in (1.0, 1e-1, 1e-2):
+        w = g[f"s_w_{rho}"] + 1e-9
+        got = cb.mag_extended_source(w, rho, nlenses=1, npts_limb=150)
+        assert np.allclose(got, g[f"s_unif_{rho}"], rtol=1e-6)
+        assert abs(got[0] / np.sqrt(1 + 4 / rho**2) - 1) < 1e-3
+    got = cb.mag_extended_source(g["s_w_0.1"] + 1e-9, 0.1, nlenses=1, npts_limb=300, limb_darkening=True, u1=0.7)
+    assert np.allclose(got, g["s_ld_0.1"], rtol=1e-3)
+    assert isinstance(cb.mag_extended_source(0.05 + 0.1j, 1e-2, nlenses=2, **HP2), float)   # scalar in, scalar out
+
+
+def test_light_curve_gate(cb, g):
+    """`mag` (lightcurve.py:99-254): same gate decisions as the reference restatement, hexadecapole
+    values to 1e-10, full-integration values to 1e-4, and the reference's own light curve"""
+    w = g["lc_w"]
+    got, used = cb.mag(w, 1e-2, nlenses=2, npts_limb=200, return_test=True, **HP2)
+    want, t_want = extended.mag(w, 1e-2, 2, 200, return_test=True, **HP2)
+    assert (used == t_want).all()
+    assert np.allclose(got[t_want], want[t_want], rtol=1e-10, atol=0)
+    assert np.allclose(got[~t_want], want[~t_want], rtol=1e-4, atol=0)
+    assert np.allclose(got, g["lc_unif"], rtol=1e-4)
+    ld = cb.mag(w[40:120], 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7, **HP2)
+    assert np.allclose(ld, g["lc_ld"], rtol=1e-3)
+
+
+def test_c3_light_curve_subset(cb):
+    """config 3: the C1 trajectory with rho = 1e-2, u1 = 0.7 -- every 25th point against the oracle,
+    and structural checks on all 10^4 points"""
+    w = c1_w()
+    got, used = cb.mag(torch.from_numpy(w).cuda(), 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7,
+                       npts_ld=100, return_test=True, **HP2)
+    got, used = got.cpu().numpy(), used.cpu().numpy()
+    assert np.isfinite(got).all() and (got >= 1.0).all()
+    assert 0.02 < (~used).mean() < 0.3
+    sub = slice(0, None, 25)
+    want, t_want = extended.mag(w[sub], 1e-2, 2, 200, True, 0.7, 100, return_test=True, **HP2)
+    assert (used[sub] == t_want).all()
+    assert np.allclose(got[sub], want, rtol=1e-4, atol=0)
+    # far from the caustic the finite-source and point-source magnifications agree to O(rho^2)
+    ps = cb.mag_point_source(w, nlenses=2, **HP2)
+    far = np.abs(w.real) > 1.5
+    assert np.allclose(got[far], ps[far], rtol=1e-3)
+
+
+def test_triple_mag_runs_and_matches_full(cb, g):
+    """nlenses = 3 through `mag`: full integration everywhere (the reference cannot run this branch)"""
+    w = g["t_w_0.01"][:8]
+    got, used = cb.mag(w, 1e-2, nlenses=3, npts_limb=200, return_test=True, **HP3)
+    assert not used.any()
+    assert np.allclose(got, cb.mag_extended_source(w, 1e-2, nlenses=3, npts_limb=200, **HP3), rtol=1e-12)
+
+
+def test_batch_independence_and_chunking(cb, g):
+    """each source is an independent unit: a batch equals its elements; chunked == unchunked"""
+    w = np.concatenate([g["b_w_0.01"], g["b_w_0.1"]])
+    full = cb.mag_extended_source(w, 1e-2, nlenses=2, npts_limb=200, **HP2)
+    one = np.array([cb.mag_extended_source(complex(x), 1e-2, nlenses=2, npts_limb=200, **HP2) for x in w[:5]])
+    assert np.array_equal(full[:5], one)
+    from caustics_b200 import extended_source as es
+    old = es._MAX_WS_BYTES
+    try:
+        es._MAX_WS_BYTES = 2 << 20
+        assert np.array_equal(cb.mag_extended_source(w, 1e-2, nlenses=2, npts_limb=200, **HP2), full)
+    finally:
+        es._MAX_WS_BYTES = old
+    with pytest.raises(ValueError):
+        cb.mag_extended_source(w, 1e-2, nlenses=2, npts_limb=4000, **HP2)

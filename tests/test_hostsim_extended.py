@@ -1,0 +1,95 @@
+"""CPU tier: the DEVICE code of kernel family 3 (csrc/extended_core.cuh and friends) compiled for the
+host (tests/hostsim, one-lane warps) against the oracle.  Checks the kernels' algorithmic logic --
+limb walk, refinement, track matching, segment splitting, stitching, Green integrals, limb darkening,
+hexadecapole gate -- where no GPU exists.  Test scaffolding only; the product has no CPU path."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import extended, lens
+from test_hostsim import hs  # noqa: F401  (fixture: builds tests/hostsim/libhostsim.so)
+
+vp, D_ = ctypes.c_void_p, ctypes.c_double
+HP2 = dict(s=0.9, q=0.2)
+HP3 = dict(s=0.9, q=0.2, q3=0.1, r3=0.8, psi=1.0)
+
+
+def lens_const(nl, **p):
+    r, eps = lens._lenses(nl, **p)
+    r = np.concatenate([r, np.zeros(3 - len(r))]).astype(complex)
+    eps = np.concatenate([eps, np.zeros(3 - len(eps))])
+    one = lambda root: np.array([-root, 1.0 + 0j])
+    H = np.array([1.0 + 0j])
+    for ri in r[:nl]:
+        H = lens._pmul(H, one(ri))
+    G = np.zeros(1, complex)
+    for j in range(nl):
+        t = np.array([eps[j] + 0j])
+        for i in range(nl):
+            if i != j:
+                t = lens._pmul(t, one(r[i]))
+        G = lens._padd(G, t)
+    Hp, Gp = np.zeros(4, complex), np.zeros(3, complex)
+    Hp[:len(H)], Gp[:len(G)] = H, G
+    return eps, r, Hp, Gp
+
+
+def hs_ext(lib, w, rho, nl, hp, npts=200, ld=False, u1=0.0, npts_ld=100, gate=False, comp=False):
+    p, xcm = lens.lens_params(nl, **hp)
+    if nl == 1:
+        eps, r, H, G = np.zeros(3), np.zeros(3, complex), np.zeros(4, complex), np.zeros(3, complex)
+    else:
+        eps, r, H, G = lens_const(nl, **p)
+    w = np.ascontiguousarray(np.atleast_1d(w), dtype=complex)
+    n = len(w)
+    mag, test = np.zeros(n), np.zeros(n, np.uint8)
+    rc = lib.hostsim_mag_extended(w.ctypes.data_as(vp), mag.ctypes.data_as(vp), test.ctypes.data_as(vp),
+                                  ctypes.c_int64(n), D_(rho), nl, eps.ctypes.data_as(vp), r.ctypes.data_as(vp),
+                                  H.ctypes.data_as(vp), G.ctypes.data_as(vp), D_(xcm), D_(hp.get("q", 1.0)),
+                                  int(gate), npts, int(ld), D_(u1), npts_ld, 2500, int(comp), None, None)
+    assert rc == 0
+    return (mag, test.astype(bool)) if gate else mag
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(ROOT, "tests", "golden", "ext_golden.npz"))
+
+
+@pytest.mark.parametrize("rho", [1e-1, 1e-2, 1e-3])
+def test_binary_uniform(hs, g, rho):
+    w = g[f"b_w_{rho}"][:16]
+    want = np.array([extended.mag_extended_source(x, rho, 2, 200, **HP2) for x in w])
+    got = hs_ext(hs, w, rho, 2, HP2)
+    assert np.allclose(got, want, rtol=1e-8)
+    assert np.abs(got / g[f"b_unif_{rho}"][:16] - 1).max() < 1e-3      # and the reference itself
+
+
+def test_binary_limb_darkened(hs, g):
+    w = g["b_w_0.01"][:6]
+    want = np.array([extended.mag_extended_source(x, 1e-2, 2, 200, True, 0.7, 100, **HP2) for x in w])
+    assert np.allclose(hs_ext(hs, w, 1e-2, 2, HP2, ld=True, u1=0.7), want, rtol=1e-8)
+
+
+def test_triple(hs, g):
+    w = g["t_w_0.01"][:8]
+    want = np.array([extended.mag_extended_source(x, 1e-2, 3, 200, **HP3) for x in w])
+    assert np.allclose(hs_ext(hs, w, 1e-2, 3, HP3), want, rtol=1e-8)
+    want = np.array([extended.mag_extended_source(x, 1e-2, 3, 200, True, 0.3, 60, **HP3) for x in w[:3]])
+    assert np.allclose(hs_ext(hs, w[:3], 1e-2, 3, HP3, ld=True, u1=0.3, npts_ld=60), want, rtol=1e-8)
+
+
+def test_single_and_gate(hs, g):
+    w = g["s_w_0.1"] + 1e-9
+    want = np.array([extended.mag_extended_source(x, 0.1, 1, 150) for x in w])
+    assert np.allclose(hs_ext(hs, w, 0.1, 1, {}, npts=150), want, rtol=1e-10)
+    wl = g["lc_w"]
+    want, t_want = extended.mag(wl, 1e-2, 2, 200, return_test=True, **HP2)
+    got, t_got = hs_ext(hs, wl, 1e-2, 2, HP2, gate=True)
+    assert (t_got == t_want).all()
+    assert np.allclose(got[t_want], want[t_want], rtol=1e-10)          # hexadecapole: pure arithmetic
+    assert np.allclose(got[~t_want], want[~t_want], rtol=1e-8)
+    assert np.allclose(got, g["lc_unif"], rtol=1e-4)
