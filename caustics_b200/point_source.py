@@ -155,7 +155,7 @@ def _images_point_source(w, nlenses=2, roots_itmax=2500, roots_compensated=False
         w_abs_sq = w.real**2 + w.imag**2
         sq = xp.sqrt(1 + 4 / w_abs_sq)
         z = xp.stack([0.5 * w * (1.0 + sq), 0.5 * w * (1.0 - sq)])
-        return z, (xp.ones(z.shape, dtype=xp.bool) if xp is torch else np.ones(z.shape, dtype=bool))
+        return z, (torch.ones_like(z, dtype=torch.bool) if xp is torch else np.ones(z.shape, dtype=bool))
     if nlenses not in (2, 3):
         raise ValueError("`nlenses` has to be set to be <= 3.")
     deg = nlenses**2 + 1
