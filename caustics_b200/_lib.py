@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcaustics_b200.so")
+LIB_PATH = os.environ.get("CAUSTICS_B200_LIB", os.path.join(_HERE, "libcaustics_b200.so"))
 
 FLAG_INIT_BINI = 1
 FLAG_COEFFS_HIGH_FIRST = 2

@@ -31,6 +31,24 @@ __host__ __device__ constexpr double ea_gamma(int n) {
 }
 
 enum : int { EA_INIT_REFERENCE = 0, EA_INIT_BINI = 1 };
+
+// Reciprocal used inside the Aberth sum  S = sum_i 1/(z_j - z_i).  S only steers the iteration: the
+// fixed point of z <- z - h/(hd - h S) is h(z) = 0 whatever S is, and the stopping test looks at
+// h alone, so S needs far less than double accuracy (CB200_ABERTH_MODE >= 1: one Newton step on the
+// 20-bit hardware seed, ~1e-12 relative).
+#ifndef CB200_ABERTH_MODE
+#define CB200_ABERTH_MODE 1
+#endif
+__device__ __forceinline__ double rcp_aberth(double x) {
+#if CB200_ABERTH_MODE >= 1 && !defined(CB200_HOSTSIM)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+#else
+  return rcp_fast(x);
+#endif
+}
 constexpr unsigned EA_COMP_CAP = 12;  // see ea_solve_thread
 
 // Power-of-two normalisation of the coefficients: p_i *= 2^-e with e = exponent of max |component|.
@@ -294,11 +312,32 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
         if (upd) {
           // Aberth sum over the other roots (:31-40) and the (reversed) correction (:41,:56-57)
           cd s = mk(0, 0);
+#if CB200_ABERTH_MODE == 2
+          // two terms per reciprocal: 1/a + 1/b = (a + b) conj(ab) / |ab|^2
+#pragma unroll
+          for (int i = 0; i + 1 < DEG - 1; i += 2) {
+            const int i0 = i + (i >= j ? 1 : 0), i1 = i + 1 + (i + 1 >= j ? 1 : 0);
+            const cd a = z - mk(zre[i0 * NT], zim[i0 * NT]);
+            const cd b = z - mk(zre[i1 * NT], zim[i1 * NT]);
+            const cd ab = a * b, apb = a + b;
+            const double inv = rcp_aberth(norm2(ab));
+            s = s + mk((apb.re * ab.re + apb.im * ab.im) * inv, (apb.im * ab.re - apb.re * ab.im) * inv);
+          }
+          if ((DEG - 1) & 1) {
+            const int ii = DEG - 2 + (DEG - 2 >= j ? 1 : 0);
+            const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
+            const double inv = rcp_aberth(norm2(a));
+            s = s + mk(a.re * inv, -a.im * inv);
+          }
+#else
 #pragma unroll
           for (int i = 0; i < DEG - 1; ++i) {
             const int ii = i + (i >= j ? 1 : 0);  // skip root j without a branch
-            s = s + crecip(z - mk(zre[ii * NT], zim[ii * NT]));
+            const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
+            const double inv = rcp_aberth(norm2(a));
+            s = s + mk(a.re * inv, -a.im * inv);
           }
+#endif
           cd num = h, den = hd;
           if (rev) {
             const cd z2 = z * z;

@@ -20,8 +20,11 @@ constexpr int NT = 128;  // threads per CTA (4 warps): 20 KB (deg 10) of root pl
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUSTICS_ERR_CUDA_BASE + (int)e; }
 
 // ------------------------------------------------------------------------------------------
+#ifndef CB200_EA_MINBLOCKS
+#define CB200_EA_MINBLOCKS 1
+#endif
 template <int DEG, bool COMP>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, CB200_EA_MINBLOCKS)
 ea_kernel(const double2* __restrict__ coeffs, const double2* __restrict__ roots_init,
           double2* __restrict__ roots, int32_t* __restrict__ sweeps, int64_t size, int itmax,
           int custom_init, int flags) {
