@@ -186,6 +186,46 @@ int caustics_mag_extended_source(const void* w, double* mag, int64_t n, double r
                     compensated, workspace, workspace_bytes, stream);
 }
 
+int caustics_ext_contour_capacity(int nlenses, int npts_limb, int* vmax, int* cmax) {
+  ExtCfg c;
+  const int rc = make_cfg(1, 1.0, nlenses, npts_limb, 0, 0.0, 100, 1, 0, &c);
+  if (rc) return rc;
+  if (vmax) *vmax = c.VMAX;
+  if (cmax) *cmax = c.CMAX;
+  return CAUSTICS_OK;
+}
+
+int caustics_ext_contours(const void* w, double* mag, int64_t n, double rho, const caustics_lens* lens,
+                          int npts_limb, int itmax, int compensated, void* workspace, size_t workspace_bytes,
+                          void* vz, double* vtheta, uint8_t* vcid, int32_t* vcount, double* cpar,
+                          int32_t* cstart, int32_t* ncont, void* stream) {
+  if (!lens || n < 0) return CAUSTICS_ERR_BAD_ARG;
+  ExtCfg cfg;
+  int rc = make_cfg(n, rho, lens->nlenses, npts_limb, 0, 0.0, 100, itmax, compensated, &cfg);
+  if (rc) return rc;
+  if (n == 0) return CAUSTICS_OK;
+  if (n > 0x7fffffffLL / cfg.VMAX) return CAUSTICS_ERR_BAD_ARG;
+  if (!w || !workspace || !vz || !vtheta || !vcid || !vcount || !cpar || !cstart || !ncont) return CAUSTICS_ERR_BAD_ARG;
+  const Layout lay = make_layout(cfg);
+  if (workspace_bytes < lay.total) return CAUSTICS_ERR_BAD_ARG;
+  LensConst L;
+  memset(&L, 0, sizeof(L));
+  if (lens->nlenses == 1) { L.nlenses = 1; L.eps[0] = 1.0; }
+  else if ((rc = caustics_internal_lens_const(lens, &L))) return rc;
+  cfg.emit = 1;
+  ExtBuf b = bind(cfg, lay, workspace);
+  b.w = (const double2*)w;
+  b.mag = mag;
+  b.vz = (double2*)vz; b.vth = vtheta; b.vcid = vcid; b.vcount = vcount;
+  b.cpar = cpar; b.cstart = cstart; b.ncont = ncont; b.cz0 = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (lens->nlenses) {
+    case 1: return run_pipeline<1>(cfg, b, L, st);
+    case 2: return run_pipeline<2>(cfg, b, L, st);
+    default: return run_pipeline<3>(cfg, b, L, st);
+  }
+}
+
 int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t n, double rho,
                  const caustics_lens* lens, double q, int npts_limb, int limb_darkening, double u1, int npts_ld,
                  int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream) {

@@ -35,6 +35,7 @@ struct ExtCfg {
   int nl, D, N0, nadd, NP;
   double rho;
   int itmax, comp, ld, n1, n2, VMAX, CMAX;
+  int emit;         // 1: k_contours also writes the contour vertex lists (z, theta, contour id) for the host
   double u1;
   int64_t S;        // capacity (stride) of the source axis
 };
@@ -47,8 +48,10 @@ struct ExtBuf {
   double* zre; double* zim; uint8_t* flg;   // [NP][D][S] by arrival slot; flg bit0 real, bit1 det>0
   uint16_t* order;         // [NP][S]   arrival slot of the p-th point in theta order
   uint16_t* left;          // [NADD][S] warm-start slot of each new point of the current round
+  uint16_t* right;         // [NADD][S] slot of the right end of the interval each new point splits
+  double* dval;            // [NP][S]   by arrival slot: squared width of the interval that STARTS at this slot
   double* sre; double* sim; uint8_t* sflg;  // [NP][D][S] theta-ordered, rows = image tracks
-  cb200_d2* vz; double* vP; double* vQ; uint8_t* vcid;   // [VMAX][S] limb-darkening vertex lists
+  cb200_d2* vz; double* vP; double* vQ; uint8_t* vcid; double* vth;   // vth: optional theta per vertex   // [VMAX][S] limb-darkening vertex lists
   int32_t* vcount;         // [S]
   int32_t* ncont;          // [S] number of contours emitted
   cb200_d2* cz0; double* cpar; int32_t* cstart;   // [CMAX(+1)][S] per contour: centroid, parity, first vertex
@@ -149,6 +152,26 @@ __device__ void limb_walk_single_body(const ExtCfg& cfg, const ExtBuf& b, const 
   }
 }
 
+// squared width of the interval between two stored limb points: the largest image displacement over
+// the tracks where at least one end is a real image (extended_source.py:118-125)
+template <int D>
+__device__ __forceinline__ double interval_width2(const ExtCfg& cfg, const ExtBuf& b, int sa, int sb, int64_t s) {
+  double dmax = 0.0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const double dx = b.zre[I3(sb, j, s)] - b.zre[I3(sa, j, s)], dy = b.zim[I3(sb, j, s)] - b.zim[I3(sa, j, s)];
+    const double d2 = ((b.flg[I3(sa, j, s)] | b.flg[I3(sb, j, s)]) & 1) ? dx * dx + dy * dy : 0.0;
+    dmax = fmax(dmax, d2);
+  }
+  return dmax;
+}
+template <int D>
+__device__ __forceinline__ void update_widths(const ExtCfg& cfg, const ExtBuf& b, int r, int slot, int64_t s) {
+  const int lf = b.left[I2(r, s)], rt = b.right[I2(r, s)];
+  b.dval[I2(lf, s)] = interval_width2<D>(cfg, b, lf, slot, s);
+  b.dval[I2(slot, s)] = interval_width2<D>(cfg, b, slot, rt, s);
+}
+
 // ---------------------------------------------------------------------------------------------
 // One refinement round, selection part: rank the intervals of the current theta order by the largest
 // image displacement across them (only tracks where at least one end is a real image), take the
@@ -161,24 +184,32 @@ __device__ void refine_select_body(const ExtCfg& cfg, const ExtBuf& b, int round
   double val[NADD_MAX];
   int idx[NADD_MAX];
   int cnt = 0;
+  // Interval widths are kept per interval (dval, indexed by the slot that starts it): round 0 measures
+  // all of them, later rounds only read them -- a new point changes exactly two (refine_solve_body).
   double pre[D], pim[D];
   uint8_t pf[D];
-  {
-    const int slot = b.order[I2(0, s)];
+  int pslot = b.order[I2(0, s)];
+  if (round == 0) {
 #pragma unroll
-    for (int j = 0; j < D; ++j) { pre[j] = b.zre[I3(slot, j, s)]; pim[j] = b.zim[I3(slot, j, s)]; pf[j] = b.flg[I3(slot, j, s)]; }
+    for (int j = 0; j < D; ++j) { pre[j] = b.zre[I3(pslot, j, s)]; pim[j] = b.zim[I3(pslot, j, s)]; pf[j] = b.flg[I3(pslot, j, s)]; }
   }
   for (int i = 0; i + 1 < cur; ++i) {
-    const int slot = b.order[I2(i + 1, s)];
     double dmax = 0.0;
+    if (round == 0) {
+      const int slot = b.order[I2(i + 1, s)];
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-      const double re = b.zre[I3(slot, j, s)], im = b.zim[I3(slot, j, s)];
-      const uint8_t f = b.flg[I3(slot, j, s)];
-      const double dx = re - pre[j], dy = im - pim[j];
-      const double d2 = ((f | pf[j]) & 1) ? dx * dx + dy * dy : 0.0;
-      dmax = fmax(dmax, d2);
-      pre[j] = re; pim[j] = im; pf[j] = f;
+      for (int j = 0; j < D; ++j) {
+        const double re = b.zre[I3(slot, j, s)], im = b.zim[I3(slot, j, s)];
+        const uint8_t f = b.flg[I3(slot, j, s)];
+        const double dx = re - pre[j], dy = im - pim[j];
+        const double d2 = ((f | pf[j]) & 1) ? dx * dx + dy * dy : 0.0;
+        dmax = fmax(dmax, d2);
+        pre[j] = re; pim[j] = im; pf[j] = f;
+      }
+      b.dval[I2(pslot, s)] = dmax;
+      pslot = slot;
+    } else {
+      dmax = b.dval[I2(b.order[I2(i, s)], s)];
     }
     // descending list; a later interval with an equal value ranks BEFORE earlier ones
     if (cnt < n || dmax >= val[cnt - 1]) {
@@ -194,6 +225,7 @@ __device__ void refine_select_body(const ExtCfg& cfg, const ExtBuf& b, int round
     const int sl = b.order[I2(i, s)], sr = b.order[I2(i + 1, s)];
     b.theta[I2(cur + r, s)] = 0.5 * (b.theta[I2(sl, s)] + b.theta[I2(sr, s)]);
     b.left[I2(r, s)] = (uint16_t)sl;
+    b.right[I2(r, s)] = (uint16_t)sr;
   }
   // splice: jnp.insert(x, idcs + 1, new) -- element for interval i lands right after position i.
   // Work from the back so nothing is overwritten before it is moved.  rk[] = ranks sorted by interval.
@@ -236,6 +268,7 @@ __device__ void refine_solve_body(const ExtCfg& cfg, const ExtBuf& b, const Lens
     }
   }
   solve_and_store<NL, COMP, NT>(cfg, b, L, sm, tid, active, w, true, slot, s);
+  if (active) update_widths<D>(cfg, b, r, slot, s);
 }
 
 __device__ void refine_solve_single_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int round, int64_t g) {
@@ -244,6 +277,7 @@ __device__ void refine_solve_single_body(const ExtCfg& cfg, const ExtBuf& b, con
   if (r >= cfg.nadd || s >= nsrc(cfg, b)) return;
   const int slot = cfg.N0 + round * cfg.nadd + r;
   store_single(cfg, b, limb_point(source_centre(cfg, b, L, s), cfg.rho, b.theta[I2(slot, s)]), slot, s);
+  update_widths<2>(cfg, b, r, slot, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -312,6 +346,9 @@ struct Tracks {
   const ExtCfg& cfg; const ExtBuf& b; int64_t s;
   __device__ __forceinline__ cd pt(int track, int p) const {
     return mk(b.sre[(((int64_t)p * cfg.D + track) * cfg.S + s)], b.sim[(((int64_t)p * cfg.D + track) * cfg.S + s)]);
+  }
+  __device__ __forceinline__ double th(int p) const {
+    return b.vth ? b.theta[(int64_t)b.order[(int64_t)p * cfg.S + s] * cfg.S + s] : 0.0;
   }
   __device__ __forceinline__ uint8_t fl(int track, int p) const {
     return b.sflg[(((int64_t)p * cfg.D + track) * cfg.S + s)];
@@ -392,19 +429,23 @@ struct GreenAcc {
 
 // limb-darkening vertex emitter: appends the vertices of one closed contour (closing point included)
 struct LdEmit {
-  const ExtCfg& cfg; const ExtBuf& b; int64_t s; int nv, nc; cd first, csum; int cnt0; bool any;
+  const ExtCfg& cfg; const ExtBuf& b; int64_t s; int nv, nc; cd first, csum; int cnt0; bool any; double first_th;
   __device__ void start() { any = false; csum = mk(0, 0); cnt0 = nv; }
-  __device__ void put(cd z) {
-    if (nv < cfg.VMAX) { b.vz[(int64_t)nv * cfg.S + s] = make_cb200_d2(z.re, z.im); b.vcid[(int64_t)nv * cfg.S + s] = (uint8_t)nc; }
+  __device__ void put(cd z, double th) {
+    if (nv < cfg.VMAX) {
+      b.vz[(int64_t)nv * cfg.S + s] = make_cb200_d2(z.re, z.im);
+      b.vcid[(int64_t)nv * cfg.S + s] = (uint8_t)nc;
+      if (b.vth) b.vth[(int64_t)nv * cfg.S + s] = th;
+    }
     ++nv; csum = csum + z;
   }
-  __device__ void add(cd z) { if (!any) { first = z; any = true; } put(z); }
+  __device__ void add(cd z, double th) { if (!any) { first = z; first_th = th; any = true; } put(z, th); }
   __device__ void close(double parity) {
     if (!any) return;
-    put(first);
+    put(first, first_th);
     if (nc < cfg.CMAX) {
       const double inv = 1.0 / (double)(nv - cnt0);      // centroid incl. the closing point (integrate.py:112)
-      b.cz0[(int64_t)nc * cfg.S + s] = make_cb200_d2(csum.re * inv, csum.im * inv);
+      if (b.cz0) b.cz0[(int64_t)nc * cfg.S + s] = make_cb200_d2(csum.re * inv, csum.im * inv);
       b.cpar[(int64_t)nc * cfg.S + s] = parity;
       b.cstart[(int64_t)nc * cfg.S + s] = cnt0;
     }
@@ -420,6 +461,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
   const double norm = 1.0 / (3.14159265358979323846 * cfg.rho * cfg.rho);
   const int64_t out_idx = b.list ? (int64_t)b.list[s] : s;
   double total = 0.0;
+  const bool emit = cfg.ld || cfg.emit;
   LdEmit E{cfg, b, s, 0, 0};
   GreenAcc G;
 
@@ -433,11 +475,12 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
     closed |= 1u << i;
     const uint8_t f0 = T.fl(i, 0);
     const double par = (f0 & 4) ? 0.0 : ((f0 & 2) ? 1.0 : -1.0);
-    if (cfg.ld) {
+    if (emit) {
       E.start();
-      for (int p = 0; p < NP; ++p) E.add(T.pt(i, p));
+      for (int p = 0; p < NP; ++p) E.add(T.pt(i, p), T.th(p));
       E.close(par);
-    } else {
+    }
+    if (!cfg.ld) {
       G.start();
       for (int p = 0; p < NP; ++p) G.add(T.pt(i, p));
       total += par * G.close();
@@ -550,25 +593,28 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
       }
       // close the contour (:724-725) and integrate
       const double par = chain_parity(parts, act);
-      if (cfg.ld) E.start(); else G.start();
+      if (emit) E.start();
+      G.start();
       for (int q = act.head; q < act.tail; ++q) {
         const Seg& g = parts[act.seg[q]];
         const int n = seg_n(g);
         for (int k = 0; k < n; ++k) {
-          const cd z = seg_pt(T, g, k, act.rev[q]);
-          if (cfg.ld) E.add(z); else G.add(z);
+          const int pidx = act.rev[q] ? g.hi - 1 - k : g.lo + k;
+          const cd z = T.pt(g.track, pidx);
+          if (emit) E.add(z, T.th(pidx));
+          G.add(z);
         }
       }
-      if (cfg.ld) E.close(par); else total += par * G.close();
+      if (emit) E.close(par);
+      total += par * G.close();
     }
   }
-  if (cfg.ld) {
+  if (emit) {
     b.vcount[s] = E.nv < cfg.VMAX ? E.nv : cfg.VMAX;
     b.cstart[(int64_t)(E.nc < cfg.CMAX ? E.nc : cfg.CMAX) * cfg.S + s] = E.nv < cfg.VMAX ? E.nv : cfg.VMAX;
     b.ncont[s] = E.nc < cfg.CMAX ? E.nc : cfg.CMAX;
-  } else {
-    b.mag[out_idx] = fabs(total) * norm;
   }
+  if (!cfg.ld && b.mag) b.mag[out_idx] = fabs(total) * norm;
 }
 
 // ---------------------------------------------------------------------------------------------

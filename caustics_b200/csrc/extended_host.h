@@ -33,7 +33,7 @@ inline void leggauss(int n, double* x, double* w) {
 }
 
 struct Layout {
-  size_t theta, zre, zim, flg, order, left, sre, sim, sflg, vz, vP, vQ, vcid, vcount, ncont, cz0, cpar, cstart, gl, list, count, total;
+  size_t theta, zre, zim, flg, order, left, right, dval, sre, sim, sflg, vz, vP, vQ, vcid, vcount, ncont, cz0, cpar, cstart, gl, list, count, total;
 };
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -43,7 +43,7 @@ inline Layout make_layout(const ExtCfg& c) {
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
   l.theta = take(NP * S * 8);
   l.zre = take(NP * D * S * 8); l.zim = take(NP * D * S * 8); l.flg = take(NP * D * S);
-  l.order = take(NP * S * 2); l.left = take((size_t)NADD_MAX * S * 2);
+  l.order = take(NP * S * 2); l.left = take((size_t)NADD_MAX * S * 2); l.right = take((size_t)NADD_MAX * S * 2); l.dval = take(NP * S * 8);
   l.sre = take(NP * D * S * 8); l.sim = take(NP * D * S * 8); l.sflg = take(NP * D * S);
   if (c.ld) {
     l.vz = take((size_t)c.VMAX * S * 16); l.vP = take((size_t)c.VMAX * S * 8); l.vQ = take((size_t)c.VMAX * S * 8);
@@ -81,7 +81,7 @@ inline ExtBuf bind(const ExtCfg& c, const Layout& l, void* ws) {
   ExtBuf b; memset(&b, 0, sizeof(b));
   b.theta = (double*)(base + l.theta);
   b.zre = (double*)(base + l.zre); b.zim = (double*)(base + l.zim); b.flg = (uint8_t*)(base + l.flg);
-  b.order = (uint16_t*)(base + l.order); b.left = (uint16_t*)(base + l.left);
+  b.order = (uint16_t*)(base + l.order); b.left = (uint16_t*)(base + l.left); b.right = (uint16_t*)(base + l.right); b.dval = (double*)(base + l.dval);
   b.sre = (double*)(base + l.sre); b.sim = (double*)(base + l.sim); b.sflg = (uint8_t*)(base + l.sflg);
   if (c.ld) {
     b.vz = (cb200_d2*)(base + l.vz); b.vP = (double*)(base + l.vP); b.vQ = (double*)(base + l.vQ);

@@ -219,6 +219,37 @@ int launch_ps(const double2* w, GridSpec g, const double2* z_init, double2* z, u
 
 thread_local int g_last_xla_error = 0;
 
+
+// Greedy nearest-neighbour track matching along the first axis (utils.match_points, utils.py:15-40,
+// as used by critical_and_caustic_curves, point_source.py:1637-1641): one thread per curve set.
+// z (B, npts, D) complex128 -> out (B, npts, D) with column k ordered so that entry i continues
+// entry i of column k-1 (for each i in order: the nearest not-yet-taken root, ties to the lowest).
+__global__ void match_tracks_kernel(const double2* __restrict__ z, double2* __restrict__ out, int64_t B, int npts, int D) {
+  const int64_t bidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bidx >= B) return;
+  const double2* zi = z + bidx * npts * D;
+  double2* zo = out + bidx * npts * D;
+  double cre[16], cim[16];
+  for (int i = 0; i < D; ++i) { cre[i] = zi[i].x; cim[i] = zi[i].y; zo[i] = zi[i]; }
+  for (int k = 1; k < npts; ++k) {
+    unsigned used = 0;
+    double nre[16], nim[16];
+    for (int i = 0; i < D; ++i) {
+      double bd = 1e300; int best = -1;
+      for (int m = 0; m < D; ++m) {
+        const double dx = zi[k * D + m].x - cre[i], dy = zi[k * D + m].y - cim[i];
+        const double d2 = dx * dx + dy * dy;
+        if (!((used >> m) & 1u) && d2 < bd) { bd = d2; best = m; }
+      }
+      if (best < 0) for (int m = D - 1; m >= 0; --m) if (!((used >> m) & 1u)) best = m;
+      used |= 1u << best;
+      nre[i] = zi[k * D + best].x; nim[i] = zi[k * D + best].y;
+      zo[k * D + i] = zi[k * D + best];
+    }
+    for (int i = 0; i < D; ++i) { cre[i] = nre[i]; cim[i] = nim[i]; }
+  }
+}
+
 // DFMA-saturating microbenchmark: 8 independent FMA chains per thread.  Used by bench.py to measure
 // the FP64 (non-tensor) roofline denominator on the device the numbers are taken on.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double seed) {
@@ -242,6 +273,14 @@ extern "C" __attribute__((visibility("hidden"))) int caustics_internal_lens_cons
 }
 
 extern "C" {
+
+int caustics_match_tracks(const void* z, void* out, int64_t nsets, int npts, int deg, void* stream) {
+  if (nsets < 0 || npts < 0 || deg < 1 || deg > 16) return CAUSTICS_ERR_BAD_ARG;
+  if (nsets == 0 || npts == 0) return CAUSTICS_OK;
+  if (!z || !out) return CAUSTICS_ERR_BAD_ARG;
+  match_tracks_kernel<<<(unsigned)((nsets + 63) / 64), 64, 0, (cudaStream_t)stream>>>((const double2*)z, (double2*)out, nsets, npts, deg);
+  return cuda_rc(cudaGetLastError());
+}
 
 int caustics_bench_fp64_peak(double* sink, int blocks, int iters, void* stream) {
   if (!sink || blocks <= 0 || iters <= 0) return CAUSTICS_ERR_BAD_ARG;

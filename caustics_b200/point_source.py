@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from .primitive import poly_roots
 
-__all__ = ["mag_point_source", "lens_eq", "lens_eq_det_jac", "lens_params"]
+__all__ = ["mag_point_source", "lens_eq", "lens_eq_det_jac", "lens_params", "critical_and_caustic_curves"]
 
 
 def lens_params(nlenses, **params):
@@ -232,3 +232,40 @@ def mag_point_source(w, nlenses=2, roots_itmax=2500, roots_compensated=False, fl
                                                 int(flags)))
     mag = mag.reshape(shape)
     return torch.from_numpy(mag) if is_t else mag
+
+
+def critical_and_caustic_curves(npts=200, nlenses=2, **params):
+    """Critical curves and caustics (point_source.py:1582-1649): the 2N roots of the critical-curve
+    polynomial at `npts` phases phi in [-pi, pi] (kernel 1, degree 4 / 6), ordered into continuous
+    curves by greedy track matching on the device, and mapped through the lens equation.  Returns
+    (z_cr, z_ca), CUDA tensors of shape (2 * nlenses, npts), shifted by the centre of mass like the
+    reference."""
+    _lib.require_cuda()
+    dev = torch.device("cuda")
+    phi = torch.linspace(-math.pi, math.pi, npts, dtype=torch.float64, device=dev)
+    if nlenses == 1:
+        return torch.exp(-1j * phi), torch.zeros(npts, dtype=torch.complex128, device=dev)
+    p, x_cm = lens_params(nlenses, **params)
+    x = torch.exp(-1j * phi)
+    one, zero = torch.ones_like(x), torch.zeros_like(x)
+    a, e1 = p["a"], p["e1"]
+    if nlenses == 2:                       # point_source.py:1482-1495
+        coeffs = [x, zero, -2 * a**2 * x - 1.0, (-4 * a * e1 + 2 * a) * one, a**4 * x - a**2]
+    elif nlenses == 3:                     # point_source.py:1498-1534
+        e2, r3 = p["e2"], complex(p["r3"])
+        coeffs = [x, -2 * x * r3, -2 * a**2 * x - 1 + x * r3**2,
+                  4 * a**2 * x * r3 - 2 * a * e1 + 2 * a * e2 + 2 * e1 * r3 + 2 * e2 * r3,
+                  a**4 * x - 3 * a**2 * e1 - 3 * a**2 * e2 + 2 * a**2 - 2 * a**2 * x * r3**2
+                  + 4 * a * e1 * r3 - 4 * a * e2 * r3 - e1 * r3**2 - e2 * r3**2,
+                  -2 * a**4 * x * r3 + 2 * a**2 * e1 * r3 + 2 * a**2 * e2 * r3 - 2 * a * e1 * r3**2 + 2 * a * e2 * r3**2,
+                  a**4 * e1 + a**4 * e2 - a**4 + a**4 * x * r3**2 - a**2 * e1 * r3**2 - a**2 * e2 * r3**2]
+    else:
+        raise ValueError("`nlenses` has to be set to be <= 3.")
+    c = torch.stack([torch.as_tensor(v, dtype=torch.complex128, device=dev) * one for v in coeffs], dim=-1)
+    z = poly_roots(c)                                            # (npts, 2N), default itmax like the reference
+    out = torch.empty_like(z)
+    _lib.check(_lib.lib().caustics_match_tracks(z.data_ptr(), out.data_ptr(), 1, npts, z.shape[1],
+                                                torch.cuda.current_stream().cuda_stream))
+    z_cr = out.T.contiguous()
+    z_ca = lens_eq(z_cr, nlenses, **p)
+    return z_cr - x_cm, z_ca - x_cm

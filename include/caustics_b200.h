@@ -139,6 +139,23 @@ int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t
                  const caustics_lens* lens, double q, int npts_limb, int limb_darkening, double u1, int npts_ld,
                  int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Contours of the images of the source limb, for differentiating the uniform-disk magnification on
+ * the host side (the implicit-function rule stays in Python, north_star): per source, the vertices
+ * of every closed contour in integration order, closing vertex included.  vz (VMAX, n) complex128,
+ * vtheta (VMAX, n) limb angle of each vertex, vcid (VMAX, n) contour id, vcount (n), cpar (CMAX, n)
+ * contour parity, cstart (CMAX + 1, n) first vertex of each contour, ncont (n); source index fastest.
+ * mag (n), optional, receives the uniform-disk magnification.  VMAX, CMAX from _capacity. */
+int caustics_ext_contour_capacity(int nlenses, int npts_limb, int* vmax, int* cmax);
+int caustics_ext_contours(const void* w, double* mag, int64_t n, double rho, const caustics_lens* lens,
+                          int npts_limb, int itmax, int compensated, void* workspace, size_t workspace_bytes,
+                          void* vz, double* vtheta, uint8_t* vcid, int32_t* vcount, double* cpar,
+                          int32_t* cstart, int32_t* ncont, void* stream);
+
+/* ---- track matching (critical / caustic curves, point_source.py:1582-1649) -------------------
+ * z (nsets, npts, deg) complex128 -> out, same shape: every row re-ordered so that entry i continues
+ * entry i of the previous row (greedy nearest neighbour without reuse, utils.py:15-40). deg <= 16. */
+int caustics_match_tracks(const void* z, void* out, int64_t nsets, int npts, int deg, void* stream);
+
 /* ---- measurement aid -----------------------------------------------------------------------
  * Launches blocks x 256 threads, each running 8 independent chains of `iters` double-precision
  * FMAs (2 * 8 * 256 * blocks * iters flop).  bench.py times it to get the FP64 roofline peak. */

@@ -82,6 +82,10 @@ def ps_golden():
         out[f"gate_{rho}"], out[f"planet_{rho}"] = N(t1), N(t2)
     mu, dmu = mp._mag_hexadecapole(z, zm, 0.05, u1=0.4, nlenses=2, a=a, e1=e1)
     out["hex_mu_ld"], out["hex_dmu_ld"] = N(mu), N(dmu)
+    # critical curves and caustics, point_source.py:1582-1649
+    for nl, hp in ((2, dict(s=0.9, q=0.2)), (3, hp3)):
+        zcr, zca = C.critical_and_caustic_curves(npts=50, nlenses=nl, **hp)
+        out[f"crit{nl}_cr"], out[f"crit{nl}_ca"] = N(zcr), N(zca)
     np.savez_compressed(os.path.join(HERE, "ps_golden.npz"), **out)
 
 

@@ -153,3 +153,58 @@ def test_batch_independence_and_chunking(cb, g):
         es._MAX_WS_BYTES = old
     with pytest.raises(ValueError):
         cb.mag_extended_source(w, 1e-2, nlenses=2, npts_limb=4000, **HP2)
+
+
+def test_uniform_gradients_vs_finite_differences(cb, g):
+    """config 4's gradient check: d mag / d (s, q, q3, r3, psi, rho) through the implicit-function
+    rule vs central finite differences (tests/test_extended_source.py:294-331, rtol 1e-3), on triple-
+    and binary-lens points near caustics"""
+    w = torch.from_numpy(g["t_w_0.01"][:6]).cuda()
+    names = ["s", "q", "q3", "r3", "psi", "rho"]
+    base = dict(s=0.9, q=0.2, q3=0.1, r3=0.8, psi=1.0, rho=1e-2)
+    t = {k: torch.tensor(v, dtype=torch.float64, device="cuda", requires_grad=True) for k, v in base.items()}
+    m = cb.mag_extended_source(w, t["rho"], nlenses=3, npts_limb=200, **{k: t[k] for k in names[:5]})
+    plain = cb.mag_extended_source(w, 1e-2, nlenses=3, npts_limb=200, **{k: base[k] for k in names[:5]})
+    assert torch.allclose(m.detach(), plain, rtol=1e-9)          # same value as the plain path
+    m.sum().backward()
+
+    def f(**over):
+        v = dict(base, **over)
+        return cb.mag_extended_source(w, v["rho"], nlenses=3, npts_limb=200, **{k: v[k] for k in names[:5]}).sum().item()
+
+    for k in names:
+        h = 1e-6 * max(1.0, abs(base[k])) if k != "rho" else 1e-7
+        fd = (f(**{k: base[k] + h}) - f(**{k: base[k] - h})) / (2 * h)
+        an = t[k].grad.item()
+        assert abs(an - fd) <= 2e-3 * max(abs(fd), 1.0), (k, an, fd)
+    # binary lens: gradient w.r.t. the source position (both components) and s
+    wb = torch.from_numpy(g["b_w_0.01"][:5]).cuda().requires_grad_()
+    s = torch.tensor(0.9, dtype=torch.float64, device="cuda", requires_grad=True)
+    cb.mag_extended_source(wb, 1e-2, nlenses=2, npts_limb=200, s=s, q=0.2).sum().backward()
+    h = 1e-6
+    w0 = wb.detach()
+    for d, pick in ((h, lambda gr: gr.real), (1j * h, lambda gr: gr.imag)):
+        for i in range(2):
+            e = torch.zeros_like(w0); e[i] = d
+            fd = (cb.mag_extended_source(w0 + e, 1e-2, nlenses=2, npts_limb=200, s=0.9, q=0.2)[i] -
+                  cb.mag_extended_source(w0 - e, 1e-2, nlenses=2, npts_limb=200, s=0.9, q=0.2)[i]).item() / (2 * h)
+            an = pick(wb.grad[i]).item()
+            assert abs(an - fd) <= 2e-3 * max(abs(fd), 1.0), (i, an, fd)
+    with pytest.raises(NotImplementedError):
+        cb.mag_extended_source(wb, 1e-2, nlenses=2, limb_darkening=True, u1=0.3, s=s, q=0.2)
+
+
+def test_critical_and_caustic_curves(cb, ps_golden):
+    """point_source.py:1582-1649 against the reference's own curves (as point sets per phase, and as
+    continuous tracks)"""
+    for nl, hp in ((2, HP2), (3, HP3)):
+        z_cr, z_ca = cb.critical_and_caustic_curves(npts=50, nlenses=nl, **hp)
+        assert z_cr.shape == (2 * nl, 50)
+        ref_cr, ref_ca = ps_golden[f"crit{nl}_cr"], ps_golden[f"crit{nl}_ca"]
+        a = np.sort_complex(z_cr.cpu().numpy().T.copy())
+        b = np.sort_complex(ref_cr.T.copy())
+        assert np.abs(a - b).max() < 1e-9
+        assert np.abs(np.sort_complex(z_ca.cpu().numpy().T.copy()) - np.sort_complex(ref_ca.T.copy())).max() < 1e-8
+        # rows are continuous curves: no jumps larger than the typical step
+        step = torch.abs(z_cr[:, 1:] - z_cr[:, :-1])
+        assert step.max().item() < 0.5
