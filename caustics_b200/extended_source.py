@@ -90,29 +90,21 @@ def _detached(v):
     return v.detach() if isinstance(v, torch.Tensor) else v
 
 
-def _mag_uniform_differentiable(w0, rho, nlenses, npts_limb, roots_itmax, roots_compensated, params):
-    """Uniform-disk magnification with gradients w.r.t. w0, rho and the lens parameters.
-
-    The kernels produce the closed image contours (vertex z, limb angle theta, contour id, parity);
-    the gradient then follows the reference's route (jax.grad through the implicit-function JVP of
-    the roots, ehrlich_aberth_primitive.py:254-324, and the trapezoid sums of integrate.py:23-27;
-    sampling, masks and contour topology are constants there too): every vertex is an image of the
-    limb point w = w0 + rho e^{i theta}, i.e. a zero of F(z) = lens_eq(z; params) - w, so
-    z(params) = z0 - J^{-1} F(z0; params) with J = dF/d(z, zbar) frozen at z0 carries the exact
-    first-order dependence (one implicit Newton step; the value is unchanged since F(z0) = 0)."""
-    from .point_source import lens_eq, _lenses
+def _get_contours(w0, rho, nlenses, npts_limb, roots_itmax, roots_compensated, params):
+    """Closed image contours of every source (caustics_ext_contours): dict of device tensors
+    vz, vth, vcid (nv, n), valid (nv, n), cpar (CMAX, n), plus the flattened centres `wf`."""
+    import ctypes
     _lib.require_cuda()
     L = _lib.lib()
     dev = w0.device if isinstance(w0, torch.Tensor) and w0.is_cuda else torch.device("cuda")
-    w0t = torch.as_tensor(w0, dtype=torch.complex128, device=dev) if not isinstance(w0, torch.Tensor) else w0.to(dev, torch.complex128)
-    shape = tuple(w0t.shape)
+    w0t = (w0.to(dev, torch.complex128) if isinstance(w0, torch.Tensor)
+           else torch.as_tensor(w0, dtype=torch.complex128, device=dev))
     wf = w0t.reshape(-1)
     n = wf.numel()
     p, x_cm = lens_params(nlenses, **params) if nlenses > 1 else ({}, 0.0)
     p0 = {k: _detached(v) for k, v in p.items()}
     lens = _c_lens(nlenses, _detached(x_cm), **p0)
-    rho0 = float(_detached(rho))
-    vmax, cmax = ctypes_int(), ctypes_int()
+    vmax, cmax = ctypes.c_int(0), ctypes.c_int(0)
     _lib.check(L.caustics_ext_contour_capacity(nlenses, int(npts_limb), vmax, cmax))
     VM, CM = vmax.value, cmax.value
     vz = torch.empty((VM, n), dtype=torch.complex128, device=dev)
@@ -126,40 +118,59 @@ def _mag_uniform_differentiable(w0, rho, nlenses, npts_limb, roots_itmax, roots_
     with torch.cuda.device(dev):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         wd = wf.detach().contiguous()
-        _lib.check(L.caustics_ext_contours(wd.data_ptr(), None, n, rho0, lens, int(npts_limb), int(roots_itmax),
-                                           int(bool(roots_compensated)), ws.data_ptr(), nbytes, vz.data_ptr(),
-                                           vth.data_ptr(), vcid.data_ptr(), vcount.data_ptr(), cpar.data_ptr(),
-                                           cstart.data_ptr(), ncont.data_ptr(),
+        _lib.check(L.caustics_ext_contours(wd.data_ptr(), None, n, float(_detached(rho)), lens, int(npts_limb),
+                                           int(roots_itmax), int(bool(roots_compensated)), ws.data_ptr(), nbytes,
+                                           vz.data_ptr(), vth.data_ptr(), vcid.data_ptr(), vcount.data_ptr(),
+                                           cpar.data_ptr(), cstart.data_ptr(), ncont.data_ptr(),
                                            torch.cuda.current_stream().cuda_stream))
     nv = int(vcount.max().item())
-    vz, vth, vcid = vz[:nv], vth[:nv], vcid[:nv].long()
     valid = torch.arange(nv, device=dev)[:, None] < vcount[None, :]
-    z0 = torch.where(valid, vz, torch.ones_like(vz))              # keep padding away from the lenses
+    return {"vz": vz[:nv], "vth": vth[:nv], "vcid": vcid[:nv].long(), "valid": valid, "cpar": cpar,
+            "wf": wf, "shape": tuple(w0t.shape)}
+
+
+def _mag_from_contours(cont, wf, rho, nlenses, params, newton_steps=1):
+    """Uniform-disk magnification from a fixed set of contour vertices (fixed limb angles, fixed
+    topology) as a differentiable function of the source centres `wf`, `rho` and the lens parameters.
+    Every vertex is an image of w = wf + x_cm + rho e^{i theta}, a zero of F(z) = lens_eq(z) - w.
+    One Newton step z0 - J^{-1} F(z0; params), with J = dF/d(z, zbar) frozen at the kernel's z0,
+    leaves the value unchanged (F(z0) = 0) and carries the exact first-order dependence -- the
+    implicit-function rule of ehrlich_aberth_primitive.py:254-324 written on the lens equation.
+    `newton_steps` > 1 re-polishes the vertices (used to evaluate nearby parameters)."""
+    from .point_source import lens_eq, _lenses
+    vz, vth, vcid, valid, cpar = cont["vz"], cont["vth"], cont["vcid"], cont["valid"], cont["cpar"]
+    dev = vz.device
+    p, x_cm = lens_params(nlenses, **params) if nlenses > 1 else ({}, 0.0)
     rho_t = torch.as_tensor(rho, dtype=torch.float64, device=dev)
     w = (wf + x_cm)[None, :] + rho_t * torch.exp(1j * vth)
-    if nlenses == 1:
-        F = z0 - 1.0 / torch.conj(z0) - w
-        g = 1.0 / torch.conj(z0) ** 2
-    else:
-        F = lens_eq(z0, nlenses, **p) - w
-        r0, e0 = _lenses(nlenses, **p0)
-        g = sum(ej / (torch.conj(z0) - (torch.conj(rj) if isinstance(rj, torch.Tensor) else np.conj(rj))) ** 2
-                for rj, ej in zip(r0, e0))
-    g = g.detach() if isinstance(g, torch.Tensor) else g
-    delta = (-F + g * torch.conj(F)) / (1.0 - torch.abs(g) ** 2)
-    z = z0 + delta
+    z = torch.where(valid, vz, torch.ones_like(vz))              # keep padding away from the lenses
+    for _ in range(newton_steps):
+        zd = z.detach()
+        if nlenses == 1:
+            F = z - 1.0 / torch.conj(z) - w
+            g = 1.0 / torch.conj(zd) ** 2
+        else:
+            F = lens_eq(z, nlenses, **p) - w
+            r0, e0 = _lenses(nlenses, **{k: _detached(v) for k, v in p.items()})
+            g = sum(ej / (torch.conj(zd) - (torch.conj(rj) if isinstance(rj, torch.Tensor) else np.conj(rj))) ** 2
+                    for rj, ej in zip(r0, e0))
+        g = g.detach()
+        z = z + (-F + g * torch.conj(F)) / (1.0 - torch.abs(g) ** 2)
     x, y = z.real, z.imag
     cross = x[:-1] * y[1:] - x[1:] * y[:-1]
     edge = (vcid[:-1] == vcid[1:]) & valid[1:]
-    par = torch.gather(cpar, 0, vcid.clamp(max=CM - 1))
+    par = torch.gather(cpar, 0, vcid.clamp(max=cpar.shape[0] - 1))
     total = 0.5 * (torch.where(edge, cross, torch.zeros_like(cross)) * par[:-1]).sum(0)
-    mag = torch.abs(total) / (np.pi * rho_t**2)
-    return mag.reshape(shape)
+    return (torch.abs(total) / (np.pi * rho_t**2)).reshape(cont["shape"])
 
 
-def ctypes_int():
-    import ctypes
-    return ctypes.c_int(0)
+def _mag_uniform_differentiable(w0, rho, nlenses, npts_limb, roots_itmax, roots_compensated, params):
+    """Uniform-disk magnification with gradients w.r.t. w0, rho and the lens parameters: contours from
+    the kernels, gradient by the implicit-function rule (sampling, masks and contour topology are
+    constants, exactly as in the reference's jax.grad)."""
+    cont = _get_contours(w0, rho, nlenses, npts_limb, roots_itmax, roots_compensated, params)
+    wf = cont["wf"] if isinstance(w0, torch.Tensor) else cont["wf"]
+    return _mag_from_contours(cont, wf, rho, nlenses, params)
 
 
 def mag_extended_source(w0, rho, nlenses=2, npts_limb=150, limb_darkening=False, u1=0.0, npts_ld=100,
