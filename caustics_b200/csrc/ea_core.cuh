@@ -36,6 +36,9 @@ enum : int { EA_INIT_REFERENCE = 0, EA_INIT_BINI = 1 };
 // fixed point of z <- z - h/(hd - h S) is h(z) = 0 whatever S is, and the stopping test looks at
 // h alone, so S needs far less than double accuracy (CB200_ABERTH_MODE >= 1: one Newton step on the
 // 20-bit hardware seed, ~1e-12 relative).
+#ifndef CB200_STRAIGHT_LINE
+#define CB200_STRAIGHT_LINE 1
+#endif
 #ifndef CB200_ABERTH_MODE
 #define CB200_ABERTH_MODE 1
 #endif
@@ -70,13 +73,12 @@ __device__ __forceinline__ void ea_normalise(cd (&p)[DEG + 1]) {
 // mode EA_INIT_REFERENCE reproduces the reference's purely real guesses r*sin(.) (the comma
 // expression at init_est.h:95), so sweep counts and root order match the reference; EA_INIT_BINI
 // uses the intended r*(cos, sin) which converges in 10-30 % fewer updates.
-template <int DEG, int NT>
-__device__ __noinline__ void ea_init_est(const double (&al)[DEG + 1], double* zre, double* zim,
-                                         int mode) {
+template <int DEG, int NT, class ALPHA>
+__device__ __noinline__ void ea_init_est(const ALPHA& al, double* zre, double* zim, int mode) {
   double ly[DEG + 1];
   int hx[DEG + 1];
 #pragma unroll
-  for (int i = 0; i <= DEG; ++i) ly[i] = al[i] > 0 ? log(al[i]) : -1e30;
+  for (int i = 0; i <= DEG; ++i) { const double a = al.get(i); ly[i] = a > 0 ? log(a) : -1e30; }
   int k = 0;
   for (int i = DEG; i >= 0; --i) {
     while (k >= 2) {
@@ -163,15 +165,40 @@ __device__ __forceinline__ cd comp_step(cd acc, cd x, cd add, cd& err, double (&
   return mk(vr, vi);
 }
 
+// |coefficient| holders: registers (static indices) or a shared-memory plane per thread.  The shared
+// variant frees 2*(DEG+1) registers per thread, which buys another resident CTA per SM.
+#ifndef CB200_ALPHA_SMEM
+#define CB200_ALPHA_SMEM 1
+#endif
+template <int DEG, int NT>
+struct AlphaRegs {
+  double v[DEG + 1];
+  __device__ __forceinline__ double get(int k) const { return v[k]; }
+  __device__ __forceinline__ double get2(int k, bool rev) const { return rev ? v[k] : v[DEG - k]; }
+  __device__ __forceinline__ void set(int k, double x) { v[k] = x; }
+};
+template <int DEG, int NT>
+struct AlphaSmem {
+  double* base;
+  __device__ __forceinline__ double get(int k) const { return base[k * NT]; }
+  __device__ __forceinline__ double get2(int k, bool rev) const { return base[(rev ? k : DEG - k) * NT]; }
+  __device__ __forceinline__ void set(int k, double x) { base[k * NT] = x; }
+};
+
+template <int DEG, int NT, bool SMEM> struct AlphaPick { typedef AlphaRegs<DEG, NT> type; };
+template <int DEG, int NT> struct AlphaPick<DEG, NT, true> { typedef AlphaSmem<DEG, NT> type; };
+template <int DEG, int NT> __device__ __forceinline__ void alpha_bind(AlphaRegs<DEG, NT>&, double*) {}
+template <int DEG, int NT> __device__ __forceinline__ void alpha_bind(AlphaSmem<DEG, NT>& a, double* base) { a.base = base; }
+
 // Value, derivative and the real bound polynomial in one unrolled Horner pass (horner.h:219-267).
 // MODE 0: every lane evaluates p at x (coefficients high->low); MODE 1: every lane evaluates the
 // reversed polynomial (coefficients from index 0, reference's rhorner_*); MODE 2: per-lane select.
 // MODE 0/1 are taken when a warp vote finds the lanes agree, which saves the 6 selects per step.
-template <int DEG, int MODE>
-__device__ __forceinline__ void horner_plain(const cd (&p)[DEG + 1], const double (&al)[DEG + 1], cd x,
+template <int DEG, int MODE, class ALPHA>
+__device__ __forceinline__ void horner_plain(const cd (&p)[DEG + 1], const ALPHA& al, cd x,
                                              double ax, bool rev, cd& h, cd& hd, double& b) {
 #define CB200_COEF(k) (MODE == 0 ? p[DEG - (k)] : MODE == 1 ? p[k] : csel(rev, p[k], p[DEG - (k)]))
-#define CB200_ALPH(k) (MODE == 0 ? al[DEG - (k)] : MODE == 1 ? al[k] : (rev ? al[k] : al[DEG - (k)]))
+#define CB200_ALPH(k) (MODE == 0 ? al.get(DEG - (k)) : MODE == 1 ? al.get(k) : al.get2(k, rev))
   h = CB200_COEF(0);
   b = CB200_ALPH(0);
   hd = h;
@@ -187,11 +214,67 @@ __device__ __forceinline__ void horner_plain(const cd (&p)[DEG + 1], const doubl
 #undef CB200_ALPH
 }
 
+// One plain (non-compensated) root step as ONE straight-line block: prologue, Horner pass, Aberth sum,
+// correction and a predicated store, with no data-dependent branch in between.  The Aberth sum does
+// not depend on the Horner result, so inside one basic block the scheduler overlaps the
+// latency-bound Horner chains with the throughput-bound reciprocals (in the branchy formulation the
+// convergence test separated them).  Lanes that do not need the root (already converged) execute the
+// arithmetic on their converged value and commit nothing; so does the one evaluation per root that
+// only confirms convergence.  MODE as in horner_plain.
+template <int DEG, int MODE, int NT, class ALPHA>
+__device__ __forceinline__ void ea_step_plain(const cd (&p)[DEG + 1], const ALPHA& al,
+                                              double* zre, double* zim, int j, bool need, unsigned& c1) {
+  const cd z = mk(zre[j * NT], zim[j * NT]);
+  const double az2 = norm2(z);
+  const bool rev = MODE == 2 ? az2 > 1.0 : MODE == 1;
+  double rs = rsqrt_fast(az2);
+  rs = az2 > 0.0 ? rs : 0.0;
+  const double absz = az2 * rs;
+  cd x = z;
+  double ax = absz;
+  if (MODE != 0) {
+    const double inv = rs * rs;
+    const cd xr = mk(z.re * inv, -z.im * inv);
+    x = MODE == 1 ? xr : csel(rev, xr, z);
+    ax = MODE == 1 ? rs : (rev ? rs : absz);
+  }
+  cd h, hd;
+  double b;
+  horner_plain<DEG, MODE, ALPHA>(p, al, x, ax, rev, h, hd, b);
+  cd s = mk(0, 0);
+#pragma unroll
+  for (int i = 0; i < DEG - 1; ++i) {
+    const int ii = i + (i >= j ? 1 : 0);  // skip root j without a branch
+    const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
+    const double inv = rcp_aberth(norm2(a));
+    s = s + mk(a.re * inv, -a.im * inv);
+  }
+  cd num = h, den = hd;
+  if (MODE != 0) {
+    const cd z2 = z * z;
+    const cd numr = z2 * h;
+    const cd denr = ((double)DEG * z) * h - hd;
+    num = MODE == 1 ? numr : csel(rev, numr, h);
+    den = MODE == 1 ? denr : csel(rev, denr, hd);
+  }
+  den = den - num * s;
+  const cd corr = cdiv(num, den);
+  const double thr = EA_EPS * b;
+  const bool big = norm2(h) > thr * thr;  // |h| > EPS*b, ehrlich_aberth.h:109/:122
+  if (need && big) {
+    zre[j * NT] = z.re - corr.re;
+    zim[j * NT] = z.im - corr.im;
+  }
+  if (need && !big) c1 |= (1u << j);
+}
+
 // Shared-memory planes owned by one CTA of NT threads.
 template <int DEG, bool COMP, int NT>
 struct EASmem {
   double zre[DEG][NT];
   double zim[DEG][NT];
+  // (plain kernels only: the compensated ones already use 43 KB for the coefficient planes)
+  double al[(CB200_ALPHA_SMEM && !COMP) ? DEG + 1 : 1][(CB200_ALPHA_SMEM && !COMP) ? NT : 1];
   // compensated phase only: coefficient planes for the rolled compensated Horner loop
   double cre[COMP ? DEG + 1 : 1][COMP ? NT : 1];
   double cim[COMP ? DEG + 1 : 1][COMP ? NT : 1];
@@ -213,9 +296,11 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
   double* zre = &sm.zre[0][tid];
   double* zim = &sm.zim[0][tid];
 
-  double al[DEG + 1];
+  typedef typename AlphaPick<DEG, NT, (CB200_ALPHA_SMEM && !COMP)>::type ALPHA;
+  ALPHA al;
+  alpha_bind(al, &sm.al[0][tid]);
 #pragma unroll
-  for (int i = 0; i <= DEG; ++i) al[i] = cabs_fast(p[i]);  // ehrlich_aberth.h:77-82
+  for (int i = 0; i <= DEG; ++i) al.set(i, cabs_fast(p[i]));  // ehrlich_aberth.h:77-82
   if (active && !custom_init) {
     // A polynomial whose coefficients are all exactly real keeps the reference's real-axis guesses
     // on the real axis in exact arithmetic; the reference only escapes through rounding noise in
@@ -224,10 +309,10 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
     double imsum = 0.0;
 #pragma unroll
     for (int i = 0; i <= DEG; ++i) imsum += fabs(p[i].im);
-    ea_init_est<DEG, NT>(al, zre, zim, imsum == 0.0 ? (int)EA_INIT_BINI : init_mode);
+    ea_init_est<DEG, NT, ALPHA>(al, zre, zim, imsum == 0.0 ? (int)EA_INIT_BINI : init_mode);
   }
 #pragma unroll
-  for (int i = 0; i <= DEG; ++i) al[i] *= fma(3.8284271247461900976, (double)i, 1.0);  // :96-99
+  for (int i = 0; i <= DEG; ++i) al.set(i, al.get(i) * fma(3.8284271247461900976, (double)i, 1.0));  // :96-99
   if (COMP) {
 #pragma unroll
     for (int i = 0; i <= DEG; ++i) { sm.cre[i][tid] = p[i].re; sm.cim[i][tid] = p[i].im; }
@@ -254,6 +339,18 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
       const bool need1 = !((c1 >> j) & 1u);
       const bool need2 = COMP && !need1 && !((c2 >> j) & 1u);
       if (!__any_sync(0xffffffffu, need1 || need2)) continue;
+#if CB200_STRAIGHT_LINE
+      if (!COMP) {
+        // warp-uniform choice of the evaluation variant, then one straight-line step
+        const bool rv = zre[j * NT] * zre[j * NT] + zim[j * NT] * zim[j * NT] > 1.0;
+        const bool all_std = __all_sync(0xffffffffu, !need1 || !rv);
+        const bool all_rev = __all_sync(0xffffffffu, !need1 || rv);
+        if (all_std) ea_step_plain<DEG, 0, NT, ALPHA>(p, al, zre, zim, j, need1, c1);
+        else if (all_rev) ea_step_plain<DEG, 1, NT, ALPHA>(p, al, zre, zim, j, need1, c1);
+        else ea_step_plain<DEG, 2, NT, ALPHA>(p, al, zre, zim, j, need1, c1);
+        continue;
+      }
+#endif
 
       const cd z = mk(zre[j * NT], zim[j * NT]);
       const double az2 = norm2(z);
@@ -275,9 +372,9 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
       const bool all_rev = __all_sync(0xffffffffu, !need1 || rev);
       if (need1) {
         double b;
-        if (all_std) horner_plain<DEG, 0>(p, al, x, ax, rev, h, hd, b);
-        else if (all_rev) horner_plain<DEG, 1>(p, al, x, ax, rev, h, hd, b);
-        else horner_plain<DEG, 2>(p, al, x, ax, rev, h, hd, b);
+        if (all_std) horner_plain<DEG, 0, ALPHA>(p, al, x, ax, rev, h, hd, b);
+        else if (all_rev) horner_plain<DEG, 1, ALPHA>(p, al, x, ax, rev, h, hd, b);
+        else horner_plain<DEG, 2, ALPHA>(p, al, x, ax, rev, h, hd, b);
         const double thr = EA_EPS * b;
         if (norm2(h) > thr * thr) upd = true;  // |h| > EPS*b, :109/:122
         else c1 |= (1u << j);

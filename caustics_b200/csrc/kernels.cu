@@ -21,7 +21,7 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUS
 
 // ------------------------------------------------------------------------------------------
 #ifndef CB200_EA_MINBLOCKS
-#define CB200_EA_MINBLOCKS 1
+#define CB200_EA_MINBLOCKS 5
 #endif
 template <int DEG, bool COMP>
 __global__ void __launch_bounds__(NT, CB200_EA_MINBLOCKS)
