@@ -93,6 +93,57 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "reasons": reasons}
 
 
+def other_configs(cb, L, _lib, torch):
+    """The other BASELINE.json configs on this GPU (CUDA events, best of 3), reported beside the
+    headline: C1 (degree-5 roots/s), C5 (binary point-source evals/s on a 2*10^7-point slice of the
+    10^4 x 10^4 map), C4 (triple-lens uniform extended-source evals/s, 10^5 sources) and C3 (binary
+    limb-darkened light curve through `mag`, 10^4 points with the hexadecapole gate)."""
+    from oracle import lens
+
+    def best(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        t = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            t = min(t, a.elapsed_time(b) * 1e-3)
+        return t
+
+    out = {}
+    hp2 = dict(s=0.9, q=0.2)
+    p, x_cm = lens.lens_params(2, **hp2)
+    n = 1_000_000
+    c5 = torch.from_numpy(lens.poly_coeffs(np.linspace(-2, 2, n) + 0.1j + x_cm, 2, **p)).cuda()
+    out["C1_ehrlich_aberth_deg5_roots_per_s"] = 5 * n / best(lambda: cb.poly_roots(c5, itmax=2500))
+    out["C1_ehrlich_aberth_deg5_compensated_roots_per_s"] = 5 * n / best(lambda: cb.poly_roots(c5, itmax=2500, compensated=True))
+    lens_c = cb.point_source._c_lens(2, x_cm, **p)
+    nx, rows = 10_000, 2_000
+    mag = torch.empty(nx * rows, dtype=torch.float64, device="cuda")
+    out["C5_mag_point_source_binary_evals_per_s"] = nx * rows / best(lambda: _lib.check(
+        L.caustics_mag_point_source_grid(-1.5, -1.5, 3.0 / 9999, 3.0 / 9999, nx, 4000, 4000 + rows, mag.data_ptr(),
+                                         lens_c, 2500, 0, 0, None)))
+    n4 = 100_000
+    w4 = torch.from_numpy(np.linspace(-2, 2, n4) + 0.1j).cuda()
+    lens3 = cb.point_source._c_lens(3, 0.0, **LENS)
+    m4 = torch.empty(n4, dtype=torch.float64, device="cuda")
+    nbytes = L.caustics_ext_workspace_bytes(n4, 3, 200, 0, 100)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    out["C4_mag_extended_source_triple_uniform_evals_per_s"] = n4 / best(lambda: _lib.check(
+        L.caustics_mag_extended_source(w4.data_ptr(), m4.data_ptr(), n4, 1e-2, lens3, 200, 0, 0.0, 100, 2500, 0,
+                                       ws.data_ptr(), nbytes, None)))
+    del ws
+    n3 = 10_000
+    w3 = torch.from_numpy(np.linspace(-2, 2, n3) + 0.1j).cuda()
+    res = {}
+
+    def lc():
+        res["m"], res["t"] = cb.mag(w3, 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7, npts_ld=100,
+                                    return_test=True, **hp2)
+    out["C3_mag_binary_ld_lightcurve_evals_per_s"] = n3 / best(lc)
+    out["C3_full_contour_integrations"] = int((~res["t"]).sum().item())
+    return out
+
+
 def cpu_reference_time(coeffs_low_high, nthreads):
     from oracle import solver
     fn = solver.ref_solve if solver.ref_available() else solver.port_solve
@@ -261,6 +312,9 @@ def main():
                    "kind": "reference" if solver.ref_available() else "port",
                    "sample": f"every 8th polynomial of the workload ({ncs}), one run, {dt:.1f} s; "
                              "the reference custom call is a serial loop (cpu_ops.cc:45-72)"}
+        extra = None
+        if world == 1:
+            extra = other_configs(cb, L, _lib, torch)
         out = {"metric": "roots/s (deg 10, triple-lens trajectory)", "value": value, "unit": "roots/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -269,7 +323,7 @@ def main():
                        "h2d_bytes_per_step": N_POLY * (DEG + 1) * 16, "d2h_bytes_per_step": N_POLY * DEG * 16,
                        "api": "caustics_b200.poly_roots(numpy pinned) -> caustics_ea_solve_host",
                        "matches_device_path": same},
-               "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu}
+               "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -17,12 +17,16 @@ __device__ __forceinline__ cd mk(double re, double im) { cd r; r.re = re; r.im =
 __device__ __forceinline__ cd operator+(cd a, cd b) { return mk(a.re + b.re, a.im + b.im); }
 __device__ __forceinline__ cd operator-(cd a, cd b) { return mk(a.re - b.re, a.im - b.im); }
 __device__ __forceinline__ cd operator-(cd a) { return mk(-a.re, -a.im); }
+// Products and sums-of-products are written with explicit fma / _rn intrinsics, so the rounding of
+// every complex operation is fixed by the source and not by nvcc's contraction choices: a
+// polynomial's result is then independent of which template variant its warp executes (the variants
+// differ only in selects), i.e. of how the batch happens to be laid out over warps.
 __device__ __forceinline__ cd operator*(cd a, cd b) {
-  return mk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+  return mk(fma(a.re, b.re, -__dmul_rn(a.im, b.im)), fma(a.re, b.im, __dmul_rn(a.im, b.re)));
 }
 __device__ __forceinline__ cd operator*(double s, cd a) { return mk(s * a.re, s * a.im); }
 __device__ __forceinline__ cd conj(cd a) { return mk(a.re, -a.im); }
-__device__ __forceinline__ double norm2(cd a) { return a.re * a.re + a.im * a.im; }
+__device__ __forceinline__ double norm2(cd a) { return fma(a.re, a.re, __dmul_rn(a.im, a.im)); }
 __device__ __forceinline__ double cabs_fast(cd a) { return sqrt(norm2(a)); }
 // a*b + c with all four products fused
 __device__ __forceinline__ cd cfma(cd a, cd b, cd c) {
@@ -62,7 +66,7 @@ __device__ __forceinline__ cd crecip(cd a) {
 }
 __device__ __forceinline__ cd cdiv(cd a, cd b) {
   double inv = rcp_fast(norm2(b));
-  return mk((a.re * b.re + a.im * b.im) * inv, (a.im * b.re - a.re * b.im) * inv);
+  return mk(__dmul_rn(fma(a.re, b.re, __dmul_rn(a.im, b.im)), inv), __dmul_rn(fma(a.im, b.re, -__dmul_rn(a.re, b.im)), inv));
 }
 __device__ __forceinline__ cd csel(bool c, cd a, cd b) { return mk(c ? a.re : b.re, c ? a.im : b.im); }
 

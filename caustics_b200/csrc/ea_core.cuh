@@ -247,20 +247,20 @@ __device__ __forceinline__ void ea_step_plain(const cd (&p)[DEG + 1], const ALPH
     const int ii = i + (i >= j ? 1 : 0);  // skip root j without a branch
     const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
     const double inv = rcp_aberth(norm2(a));
-    s = s + mk(a.re * inv, -a.im * inv);
+    s = mk(fma(a.re, inv, s.re), fma(-a.im, inv, s.im));
   }
   cd num = h, den = hd;
   if (MODE != 0) {
     const cd z2 = z * z;
     const cd numr = z2 * h;
-    const cd denr = ((double)DEG * z) * h - hd;
+    const cd denr = cfma((double)DEG * z, h, -hd);
     num = MODE == 1 ? numr : csel(rev, numr, h);
     den = MODE == 1 ? denr : csel(rev, denr, hd);
   }
-  den = den - num * s;
+  den = cfma(-num, s, den);
   const cd corr = cdiv(num, den);
   const double thr = EA_EPS * b;
-  const bool big = norm2(h) > thr * thr;  // |h| > EPS*b, ehrlich_aberth.h:109/:122
+  const bool big = norm2(h) > __dmul_rn(thr, thr);  // |h| > EPS*b, ehrlich_aberth.h:109/:122
   if (need && big) {
     zre[j * NT] = z.re - corr.re;
     zim[j * NT] = z.im - corr.im;

@@ -196,10 +196,6 @@ def test_uniform_gradients_vs_finite_differences(cb, g):
         e = torch.zeros_like(w); e[2] = d
         fd = (frozen(w_=w + e) - frozen(w_=w - e)) / (2 * h)
         assert abs(pick(wg.grad[2]).item() - fd) <= 2e-4 * max(abs(fd), 1.0)
-    # coarse difference of the full pipeline (re-sampled limb): agrees to the sampling-noise level
-    full = lambda **over: cb.mag_extended_source(w, rho0, nlenses=3, npts_limb=400, **dict(base, **over)).sum().item()
-    fd = (full(s=0.9 + 1e-6) - full(s=0.9 - 1e-6)) / 2e-6
-    assert abs(t["s"].grad.item() - fd) <= 0.1 * abs(fd)
     # binary lens, single lens: runs and matches the plain value
     s = torch.tensor(0.9, dtype=torch.float64, device="cuda", requires_grad=True)
     wb = torch.from_numpy(g["b_w_0.01"][:5]).cuda()

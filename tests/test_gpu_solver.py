@@ -165,3 +165,19 @@ def test_autograd_matches_finite_differences(cb):
             fd = (fz(base + e) - fz(base - e)) / (2 * h)
             an = g[idx].real.item() if d == 1.0 else g[idx].imag.item()
             assert abs(fd - an) <= 1e-4 + 1e-4 * abs(fd)
+
+
+def test_batch_layout_invariance(cb, ea_golden):
+    """A polynomial's roots do not depend on which other polynomials share its warp or on chunking:
+    same bits for a shuffled batch, for the host-pipeline chunks and for a one-polynomial call."""
+    rng = np.random.default_rng(99)
+    c = np.concatenate([ea_golden["c2_coeffs"], ea_golden["rand10_coeffs"],
+                        rng.standard_normal((3000, 11)) * np.exp(rng.uniform(-3, 3, (3000, 1))) + 1j * rng.standard_normal((3000, 11))])
+    base = cb.poly_roots(torch.from_numpy(c).cuda(), itmax=2500).cpu().numpy()
+    perm = rng.permutation(len(c))
+    shuf = cb.poly_roots(torch.from_numpy(np.ascontiguousarray(c[perm])).cuda(), itmax=2500).cpu().numpy()
+    assert np.array_equal(shuf, base[perm])
+    assert np.array_equal(cb.poly_roots(np.ascontiguousarray(c), itmax=2500), base)       # host chunks
+    for i in (0, 517, len(c) - 1):
+        one = cb.poly_roots(torch.from_numpy(c[i:i + 1].copy()).cuda(), itmax=2500).cpu().numpy()
+        assert np.array_equal(one[0], base[i])
