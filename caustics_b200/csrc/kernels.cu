@@ -220,6 +220,26 @@ int launch_ps(const double2* w, GridSpec g, const double2* z_init, double2* z, u
 thread_local int g_last_xla_error = 0;
 
 
+// Same, but every DFMA reads three DISTINCT, changing register pairs (no constant or repeated
+// operand): the register-file-limited rate that real Horner / Aberth code sees.
+__global__ void __launch_bounds__(256) fp64_peak3_kernel(double* sink, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  double b0 = 1.0000001, b1 = 0.9999999, b2 = 1.0000002, b3 = 0.9999998, b4 = 1.0000003, b5 = 0.9999997, b6 = 1.0000004, b7 = 0.9999996;
+  double c0 = 1e-9 * threadIdx.x, c1 = c0 + 1e-9, c2 = c0 + 2e-9, c3 = c0 + 3e-9, c4 = c0 + 4e-9, c5 = c0 + 5e-9, c6 = c0 + 6e-9, c7 = c0 + 7e-9;
+#pragma unroll 2
+  for (int i = 0; i < iters; i += 3) {
+    // rotate roles so no operand is loop-invariant: a = a*b+c ; b = b*c+a ; c = c*a+b
+    a0 = fma(a0, b0, c0); a1 = fma(a1, b1, c1); a2 = fma(a2, b2, c2); a3 = fma(a3, b3, c3);
+    a4 = fma(a4, b4, c4); a5 = fma(a5, b5, c5); a6 = fma(a6, b6, c6); a7 = fma(a7, b7, c7);
+    b0 = fma(b0, c0, a0); b1 = fma(b1, c1, a1); b2 = fma(b2, c2, a2); b3 = fma(b3, c3, a3);
+    b4 = fma(b4, c4, a4); b5 = fma(b5, c5, a5); b6 = fma(b6, c6, a6); b7 = fma(b7, c7, a7);
+    c0 = fma(c0, a0, b0); c1 = fma(c1, a1, b1); c2 = fma(c2, a2, b2); c3 = fma(c3, a3, b3);
+    c4 = fma(c4, a4, b4); c5 = fma(c5, a5, b5); c6 = fma(c6, a6, b6); c7 = fma(c7, a7, b7);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) + ((b0 + b1) + (b2 + b3)) + ((c4 + c5) + (c6 + c7));
+  if (r == 123.456) sink[0] = r;
+}
+
 // Greedy nearest-neighbour track matching along the first axis (utils.match_points, utils.py:15-40,
 // as used by critical_and_caustic_curves, point_source.py:1637-1641): one thread per curve set.
 // z (B, npts, D) complex128 -> out (B, npts, D) with column k ordered so that entry i continues
@@ -273,6 +293,12 @@ extern "C" __attribute__((visibility("hidden"))) int caustics_internal_lens_cons
 }
 
 extern "C" {
+
+int caustics_bench_fp64_peak3(double* sink, int blocks, int iters, void* stream) {
+  if (!sink || blocks <= 0 || iters <= 0) return CAUSTICS_ERR_BAD_ARG;
+  fp64_peak3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters, 0.5);
+  return cuda_rc(cudaGetLastError());
+}
 
 int caustics_match_tracks(const void* z, void* out, int64_t nsets, int npts, int deg, void* stream) {
   if (nsets < 0 || npts < 0 || deg < 1 || deg > 16) return CAUSTICS_ERR_BAD_ARG;

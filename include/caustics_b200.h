@@ -160,6 +160,9 @@ int caustics_match_tracks(const void* z, void* out, int64_t nsets, int npts, int
  * Launches blocks x 256 threads, each running 8 independent chains of `iters` double-precision
  * FMAs (2 * 8 * 256 * blocks * iters flop).  bench.py times it to get the FP64 roofline peak. */
 int caustics_bench_fp64_peak(double* sink, int blocks, int iters, void* stream);
+/* same flop count (iters rounded up to a multiple of 3), but every DFMA reads three distinct,
+ * changing register pairs: the register-file-limited DFMA rate */
+int caustics_bench_fp64_peak3(double* sink, int blocks, int iters, void* stream);
 
 #ifdef __cplusplus
 }
