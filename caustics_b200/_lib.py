@@ -40,6 +40,8 @@ SIGNATURES = {
     "caustics_ea_degree_supported": (_i, [_i]),
     "caustics_error_string": (ctypes.c_char_p, [_i]),
     "caustics_ea_solve": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "caustics_ea_jvp": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "caustics_ea_vjp": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "caustics_ea_solve_host": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i]),
     "caustics_release_workspace": (None, []),
     "caustics_ea_xla": (None, [_vp, ctypes.POINTER(_vp), ctypes.c_char_p, ctypes.c_size_t]),

@@ -23,14 +23,16 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUS
 #ifndef CB200_EA_MINBLOCKS
 #define CB200_EA_MINBLOCKS 5
 #endif
-template <int DEG, bool COMP>
-__global__ void __launch_bounds__(NT, CB200_EA_MINBLOCKS)
+// degrees <= 10 (the lens polynomials): 128-thread CTAs, 5 CTAs/SM (96 registers);
+// degrees 11..16: 64-thread CTAs (the shared planes stay below 48 KB), no register cap
+template <int DEG, bool COMP, int NTK>
+__global__ void __launch_bounds__(NTK, DEG <= 10 ? CB200_EA_MINBLOCKS : 1)
 ea_kernel(const double2* __restrict__ coeffs, const double2* __restrict__ roots_init,
           double2* __restrict__ roots, int32_t* __restrict__ sweeps, int64_t size, int itmax,
           int custom_init, int flags) {
-  __shared__ EASmem<DEG, COMP, NT> sm;
+  __shared__ EASmem<DEG, COMP, NTK> sm;
   const int tid = threadIdx.x;
-  const int64_t idx = (int64_t)blockIdx.x * NT + tid;
+  const int64_t idx = (int64_t)blockIdx.x * NTK + tid;
   const bool active = idx < size;
   const int init_mode = flags & CAUSTICS_FLAG_INIT_BINI ? EA_INIT_BINI : EA_INIT_REFERENCE;
   const bool high_first = (flags & CAUSTICS_FLAG_COEFFS_HIGH_FIRST) != 0;
@@ -56,7 +58,7 @@ ea_kernel(const double2* __restrict__ coeffs, const double2* __restrict__ roots_
 #pragma unroll
     for (int k = 0; k <= DEG; ++k) p[k] = mk(k == 0 ? -1.0 : (k == DEG ? 1.0 : 0.0), 0.0);
   }
-  const EAResult r = ea_solve_thread<DEG, COMP, NT>(p, sm, tid, active, custom_init != 0, init_mode, itmax);
+  const EAResult r = ea_solve_thread<DEG, COMP, NTK>(p, sm, tid, active, custom_init != 0, init_mode, itmax);
   if (active) {
     double2* dst = roots + idx * DEG;
 #pragma unroll
@@ -68,16 +70,59 @@ ea_kernel(const double2* __restrict__ coeffs, const double2* __restrict__ roots_
 template <int DEG>
 int launch_ea(const void* coeffs, const void* roots_init, void* roots, int32_t* sweeps, int64_t size,
               int itmax, int compensated, int custom_init, int flags, cudaStream_t st) {
-  const int64_t nblk = (size + NT - 1) / NT;
+  constexpr int NTK = DEG <= 10 ? NT : 64;
+  const int64_t nblk = (size + NTK - 1) / NTK;
   if (nblk > 0x7fffffffLL) return CAUSTICS_ERR_BAD_ARG;
-  dim3 grid((unsigned)nblk), block(NT);
+  dim3 grid((unsigned)nblk), block(NTK);
   if (compensated)
-    ea_kernel<DEG, true><<<grid, block, 0, st>>>((const double2*)coeffs, (const double2*)roots_init,
-                                                 (double2*)roots, sweeps, size, itmax, custom_init, flags);
+    ea_kernel<DEG, true, NTK><<<grid, block, 0, st>>>((const double2*)coeffs, (const double2*)roots_init,
+                                                      (double2*)roots, sweeps, size, itmax, custom_init, flags);
   else
-    ea_kernel<DEG, false><<<grid, block, 0, st>>>((const double2*)coeffs, (const double2*)roots_init,
-                                                  (double2*)roots, sweeps, size, itmax, custom_init, flags);
+    ea_kernel<DEG, false, NTK><<<grid, block, 0, st>>>((const double2*)coeffs, (const double2*)roots_init,
+                                                       (double2*)roots, sweeps, size, itmax, custom_init, flags);
   return cuda_rc(cudaGetLastError());
+}
+
+// Implicit-function tangent and cotangent of the roots (ehrlich_aberth_primitive.py:254-324):
+//   JVP  dz_j = -(sum_k dp_k z_j^k) / p'(z_j)
+//   VJP  gp_k = sum_j conj(-z_j^k / p'(z_j)) gz_j      (the transpose JAX derives from the JVP)
+// One thread per polynomial, Horner in registers; memory-bound (no (size, deg, deg+1) temporary).
+__global__ void ea_jvp_kernel(const double2* __restrict__ coeffs, const double2* __restrict__ roots,
+                              const double2* __restrict__ dcoeffs, double2* __restrict__ droots, int64_t size, int deg) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= size) return;
+  const double2* p = coeffs + n * (deg + 1);
+  const double2* dp = dcoeffs + n * (deg + 1);
+  for (int j = 0; j < deg; ++j) {
+    const double2 zz = roots[n * deg + j];
+    const cd z = mk(zz.x, zz.y);
+    cd num = mk(0, 0), der = mk(0, 0);
+    for (int k = deg; k >= 0; --k) {
+      num = cfma(num, z, mk(dp[k].x, dp[k].y));
+      if (k >= 1) der = cfma(der, z, (double)k * mk(p[k].x, p[k].y));
+    }
+    const cd r = cdiv(-num, der);
+    droots[n * deg + j] = make_double2(r.re, r.im);
+  }
+}
+__global__ void ea_vjp_kernel(const double2* __restrict__ coeffs, const double2* __restrict__ roots,
+                              const double2* __restrict__ groots, double2* __restrict__ gcoeffs, int64_t size, int deg) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= size) return;
+  const double2* p = coeffs + n * (deg + 1);
+  cd acc[33];
+  for (int k = 0; k <= deg; ++k) acc[k] = mk(0, 0);
+  for (int j = 0; j < deg; ++j) {
+    const double2 zz = roots[n * deg + j], gg = groots[n * deg + j];
+    const cd z = mk(zz.x, zz.y);
+    cd der = mk(0, 0);
+    for (int k = deg; k >= 1; --k) der = cfma(der, z, (double)k * mk(p[k].x, p[k].y));
+    const cd g = cdiv(mk(gg.x, gg.y), conj(-der));
+    const cd zc = conj(z);
+    cd zk = mk(1, 0);
+    for (int k = 0; k <= deg; ++k) { acc[k] = cfma(g, zk, acc[k]); zk = zk * zc; }
+  }
+  for (int k = 0; k <= deg; ++k) gcoeffs[n * (deg + 1) + k] = make_double2(acc[k].re, acc[k].im);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -294,6 +339,26 @@ extern "C" __attribute__((visibility("hidden"))) int caustics_internal_lens_cons
 
 extern "C" {
 
+int caustics_ea_jvp(const void* coeffs, const void* roots, const void* dcoeffs, void* droots, int64_t size, int deg,
+                    void* stream) {
+  if (size < 0 || deg < 1 || deg > 32) return CAUSTICS_ERR_BAD_ARG;
+  if (size == 0) return CAUSTICS_OK;
+  if (!coeffs || !roots || !dcoeffs || !droots) return CAUSTICS_ERR_BAD_ARG;
+  ea_jvp_kernel<<<(unsigned)((size + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      (const double2*)coeffs, (const double2*)roots, (const double2*)dcoeffs, (double2*)droots, size, deg);
+  return cuda_rc(cudaGetLastError());
+}
+
+int caustics_ea_vjp(const void* coeffs, const void* roots, const void* groots, void* gcoeffs, int64_t size, int deg,
+                    void* stream) {
+  if (size < 0 || deg < 1 || deg > 32) return CAUSTICS_ERR_BAD_ARG;
+  if (size == 0) return CAUSTICS_OK;
+  if (!coeffs || !roots || !groots || !gcoeffs) return CAUSTICS_ERR_BAD_ARG;
+  ea_vjp_kernel<<<(unsigned)((size + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      (const double2*)coeffs, (const double2*)roots, (const double2*)groots, (double2*)gcoeffs, size, deg);
+  return cuda_rc(cudaGetLastError());
+}
+
 int caustics_bench_fp64_peak3(double* sink, int blocks, int iters, void* stream) {
   if (!sink || blocks <= 0 || iters <= 0) return CAUSTICS_ERR_BAD_ARG;
   fp64_peak3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters, 0.5);
@@ -322,13 +387,13 @@ int caustics_device_count(void) {
   return n;
 }
 
-int caustics_ea_degree_supported(int deg) { return deg >= 2 && deg <= 10; }
+int caustics_ea_degree_supported(int deg) { return deg >= 2 && deg <= 16; }
 
 const char* caustics_error_string(int code) {
   switch (code) {
     case CAUSTICS_OK: return "ok";
     case CAUSTICS_ERR_BAD_ARG: return "bad argument";
-    case CAUSTICS_ERR_UNSUPPORTED_DEGREE: return "polynomial degree has no instantiated kernel (supported: 2..10)";
+    case CAUSTICS_ERR_UNSUPPORTED_DEGREE: return "polynomial degree has no instantiated kernel (supported: 2..16)";
     case CAUSTICS_ERR_BAD_DESCRIPTOR: return "opaque descriptor has the wrong size";
     default:
       if (code >= CAUSTICS_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(code - CAUSTICS_ERR_CUDA_BASE));
@@ -348,7 +413,8 @@ int caustics_ea_solve(const void* coeffs, const void* roots_init, void* roots, i
   case D: return launch_ea<D>(coeffs, roots_init, roots, sweeps, size, itmax, compensated, custom_init, flags, st);
   switch (deg) {
     CB200_CASE(2) CB200_CASE(3) CB200_CASE(4) CB200_CASE(5) CB200_CASE(6)
-    CB200_CASE(7) CB200_CASE(8) CB200_CASE(9) CB200_CASE(10)
+    CB200_CASE(7) CB200_CASE(8) CB200_CASE(9) CB200_CASE(10) CB200_CASE(11) CB200_CASE(12)
+    CB200_CASE(13) CB200_CASE(14) CB200_CASE(15) CB200_CASE(16)
   }
 #undef CB200_CASE
   return CAUSTICS_ERR_UNSUPPORTED_DEGREE;

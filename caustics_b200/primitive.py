@@ -87,6 +87,14 @@ def roots_jvp(coeffs_low_high, roots, dcoeffs):
     """Tangent of the roots for a coefficient tangent (ehrlich_aberth_primitive.py:304-319):
     dz = -(sum_k dp_k z^k) / p'(z).  Works on numpy arrays or torch tensors; coeffs/dcoeffs
     (size, deg+1) low->high, roots (size, deg)."""
+    if isinstance(roots, torch.Tensor) and roots.is_cuda and roots.dim() == 2:
+        p = coeffs_low_high.to(torch.complex128).contiguous()
+        z, dp = roots.contiguous(), dcoeffs.to(torch.complex128).contiguous()
+        out = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            _lib.check(_lib.lib().caustics_ea_jvp(p.data_ptr(), z.data_ptr(), dp.data_ptr(), out.data_ptr(),
+                                                  z.shape[0], z.shape[1], torch.cuda.current_stream().cuda_stream))
+        return out
     xp = torch if isinstance(roots, torch.Tensor) else np
     deg = coeffs_low_high.shape[-1] - 1
     # Horner for sum_k dp_k z^k and for p'(z) (no (size, deg, deg+1) temporary, cf. SURVEY 8-a9)
@@ -109,10 +117,18 @@ class _PolyRoots(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_roots):
         p, z = ctx.saved_tensors
-        deg = p.shape[1] - 1
         # z_j = h_j(p) is holomorphic in p: dz_j/dp_k = -z_j^k / p'(z_j); torch's convention for a
         # holomorphic map is grad_p = conj(dz/dp) * grad_z (the tangent w.r.t. roots_init is zero,
-        # ehrlich_aberth_primitive.py:299-302).
+        # ehrlich_aberth_primitive.py:299-302).  On the device this is one memory-bound kernel.
+        if p.is_cuda:
+            g = grad_roots.to(torch.complex128).contiguous()
+            out = torch.empty_like(p)
+            with torch.cuda.device(p.device):
+                _lib.check(_lib.lib().caustics_ea_vjp(p.data_ptr(), z.data_ptr(), g.data_ptr(), out.data_ptr(),
+                                                      p.shape[0], p.shape[1] - 1,
+                                                      torch.cuda.current_stream().cuda_stream))
+            return out, None, None, None, None, None
+        deg = p.shape[1] - 1
         der = torch.zeros_like(z)
         for k in range(deg, 0, -1):
             der = der * z + k * p[:, k:k + 1]

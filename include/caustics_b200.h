@@ -74,7 +74,7 @@ typedef struct caustics_ea_descriptor {
 /* library / device queries (no compute) */
 const char* caustics_version(void);
 int caustics_device_count(void);
-/* degrees for which a kernel is instantiated: 1 if supported */
+/* degrees for which a kernel is instantiated (2..16): 1 if supported */
 int caustics_ea_degree_supported(int deg);
 const char* caustics_error_string(int code);
 
@@ -85,6 +85,15 @@ const char* caustics_error_string(int code);
 int caustics_ea_solve(const void* coeffs, const void* roots_init, void* roots, int32_t* sweeps,
                       int64_t size, int deg, int itmax, int compensated, int custom_init,
                       int flags, void* stream);
+
+/* Implicit-function tangent / cotangent of the roots (ehrlich_aberth_primitive.py:254-324), device
+ * pointers, coeffs LOW->HIGH (size, deg+1), roots (size, deg), deg <= 32:
+ *   jvp: dcoeffs (size, deg+1) -> droots (size, deg),  dz_j = -(sum_k dp_k z_j^k) / p'(z_j)
+ *   vjp: groots (size, deg) -> gcoeffs (size, deg+1),  gp_k = sum_j conj(-z_j^k / p'(z_j)) gz_j */
+int caustics_ea_jvp(const void* coeffs, const void* roots, const void* dcoeffs, void* droots, int64_t size,
+                    int deg, void* stream);
+int caustics_ea_vjp(const void* coeffs, const void* roots, const void* groots, void* gcoeffs, int64_t size,
+                    int deg, void* stream);
 
 /* Same contract with HOST pointers: chunked H2D -> kernel -> D2H pipeline over an internal pinned +
  * device workspace on the current device (grows on demand, freed by caustics_release_workspace).

@@ -46,7 +46,7 @@ int hostsim_ea_solve(const double* coeffs, const double* ri, double* roots, int3
                      int itmax, int comp, int custom_init, int init_mode) {
 #define C(D) case D: if (comp) solve_all<D, true>(coeffs, ri, roots, sweeps, size, itmax, custom_init, init_mode); \
                      else solve_all<D, false>(coeffs, ri, roots, sweeps, size, itmax, custom_init, init_mode); return 0;
-  switch (deg) { C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) }
+  switch (deg) { C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(13) C(16) }
 #undef C
   return 2;
 }

@@ -38,13 +38,13 @@ def test_struct_layouts(built_lib):
 def test_argument_errors_without_compute(built_lib):
     from caustics_b200 import _lib
     L = built_lib
-    assert L.caustics_ea_solve(None, None, None, None, 10, 11, 100, 0, 0, 0, None) == 2  # unsupported degree
+    assert L.caustics_ea_solve(None, None, None, None, 10, 17, 100, 0, 0, 0, None) == 2  # unsupported degree
     assert L.caustics_ea_solve(None, None, None, None, -1, 5, 100, 0, 0, 0, None) == 1
     assert L.caustics_ea_solve(None, None, None, None, 0, 5, 100, 0, 0, 0, None) == 0    # empty batch: no launch
     assert L.caustics_ea_solve(None, None, None, None, 4, 5, 100, 0, 0, 0, None) == 1    # null buffers
-    for deg in range(2, 11):
+    for deg in range(2, 17):
         assert L.caustics_ea_degree_supported(deg) == 1
-    assert L.caustics_ea_degree_supported(11) == 0
+    assert L.caustics_ea_degree_supported(17) == 0 and L.caustics_ea_degree_supported(1) == 0
     bad = _lib.Lens(); bad.nlenses = 4
     assert L.caustics_mag_point_source(None, None, None, 0, ctypes.byref(bad), 10, 0, 0, None) == 1
     # bad opaque descriptor: nothing launched, sticky error instead of the reference's C++ throw

@@ -58,7 +58,7 @@ def test_roots_vs_reference_golden(cb, ea_golden, name, comp):
     assert (sweeps == psw).mean() > (0.8 if comp else 0.95)
 
 
-@pytest.mark.parametrize("deg", [2, 3, 4, 5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("deg", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 16])
 def test_all_degrees_random(cb, deg):
     rng = np.random.default_rng(deg)
     n = 4099  # ragged tail: not a multiple of the CTA size
@@ -110,7 +110,7 @@ def test_itmax_and_empty_and_dtype(cb):
         cb.poly_roots(torch.ones((4, 6), dtype=torch.complex64, device="cuda"))
     from caustics_b200._lib import CausticsError
     with pytest.raises(CausticsError):
-        cb.poly_roots(torch.ones((4, 13), dtype=torch.complex128, device="cuda"))
+        cb.poly_roots(torch.ones((4, 19), dtype=torch.complex128, device="cuda"))
 
 
 def test_real_coefficients_and_scaling(cb):
@@ -181,3 +181,23 @@ def test_batch_layout_invariance(cb, ea_golden):
     for i in (0, 517, len(c) - 1):
         one = cb.poly_roots(torch.from_numpy(c[i:i + 1].copy()).cuda(), itmax=2500).cpu().numpy()
         assert np.array_equal(one[0], base[i])
+
+
+def test_jvp_vjp_kernels(cb):
+    """on-device tangent / cotangent vs the Python rule of the reference"""
+    rng = np.random.default_rng(21)
+    for deg in (5, 10):
+        c = rng.standard_normal((300, deg + 1)) + 1j * rng.standard_normal((300, deg + 1))
+        dc = rng.standard_normal((300, deg + 1)) + 1j * rng.standard_normal((300, deg + 1))
+        z = solver.solve(c, compensated=True)
+        want = lens.jvp_roots(c, z, dc)
+        got = cb.roots_jvp(torch.from_numpy(c).cuda(), torch.from_numpy(z).cuda(), torch.from_numpy(dc).cuda())
+        assert np.allclose(got.cpu().numpy(), want, rtol=1e-10, atol=1e-12)
+        # VJP is the conjugate transpose of the JVP: Re<g, J dp> == Re<J^H g, dp>
+        g = rng.standard_normal((300, deg)) + 1j * rng.standard_normal((300, deg))
+        ct = torch.from_numpy(c).cuda().requires_grad_()
+        zz = cb.primitive._PolyRoots.apply(ct, None, 2500, True, False, 0)
+        (zz * torch.from_numpy(np.conj(g)).cuda()).real.sum().backward()
+        lhs = np.real(np.sum(np.conj(g) * want))
+        rhs = np.real(np.sum(np.conj(ct.grad.cpu().numpy()) * dc))
+        assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs))
