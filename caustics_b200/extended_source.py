@@ -23,7 +23,7 @@ def _to_device(w):
     """-> (flat complex128 CUDA tensor, restore function)"""
     if isinstance(w, torch.Tensor):
         shape, dev = tuple(w.shape), w.device
-        flat = w.detach().to(device="cuda" if not w.is_cuda else dev, dtype=torch.complex128).reshape(-1).contiguous()
+        flat = w.detach().to(device="cuda" if not w.is_cuda else dev, dtype=torch.complex128).reshape(-1).resolve_conj().resolve_neg().contiguous()
         if w.is_cuda:
             return flat, lambda m: m.reshape(shape)
         return flat, lambda m: m.cpu().reshape(shape)
@@ -117,7 +117,7 @@ def _get_contours(w0, rho, nlenses, npts_limb, roots_itmax, roots_compensated, p
     nbytes = L.caustics_ext_workspace_bytes(n, nlenses, int(npts_limb), 0, 100)
     with torch.cuda.device(dev):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        wd = wf.detach().contiguous()
+        wd = wf.detach().resolve_conj().resolve_neg().contiguous()
         _lib.check(L.caustics_ext_contours(wd.data_ptr(), None, n, float(_detached(rho)), lens, int(npts_limb),
                                            int(roots_itmax), int(bool(roots_compensated)), ws.data_ptr(), nbytes,
                                            vz.data_ptr(), vth.data_ptr(), vcid.data_ptr(), vcount.data_ptr(),

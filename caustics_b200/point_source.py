@@ -170,13 +170,13 @@ def _images_point_source(w, nlenses=2, roots_itmax=2500, roots_compensated=False
     lens = _c_lens(nlenses, 0.0, **params)
     shape = tuple(w.shape)
     if isinstance(w, torch.Tensor) and w.is_cuda:
-        wf = w.to(torch.complex128).contiguous().reshape(-1)
+        wf = w.to(torch.complex128).resolve_conj().resolve_neg().contiguous().reshape(-1)
         n = wf.numel()
         z = torch.empty((deg, n), dtype=torch.complex128, device=w.device)
         mask = torch.empty((deg, n), dtype=torch.uint8, device=w.device)
         zi = None
         if custom_init:
-            zi = z_init.to(device=w.device, dtype=torch.complex128).contiguous().reshape(n, deg)
+            zi = z_init.to(device=w.device, dtype=torch.complex128).resolve_conj().resolve_neg().contiguous().reshape(n, deg)
         with torch.cuda.device(w.device):
             st = torch.cuda.current_stream().cuda_stream
             _lib.check(L.caustics_images_point_source(
@@ -215,7 +215,7 @@ def mag_point_source(w, nlenses=2, roots_itmax=2500, roots_compensated=False, fl
     lens = _c_lens(nlenses, x_cm, **p)
     shape = tuple(w.shape)
     if isinstance(w, torch.Tensor) and w.is_cuda:
-        wf = w.to(torch.complex128).contiguous().reshape(-1)
+        wf = w.to(torch.complex128).resolve_conj().resolve_neg().contiguous().reshape(-1)
         mag = torch.empty(wf.numel(), dtype=torch.float64, device=w.device)
         with torch.cuda.device(w.device):
             st = torch.cuda.current_stream().cuda_stream

@@ -27,11 +27,11 @@ def _solve_flat(coeffs, roots_init, itmax, compensated, custom_init, flags, retu
     if isinstance(coeffs, torch.Tensor) and coeffs.is_cuda:
         if coeffs.dtype != torch.complex128:
             raise NotImplementedError(f"Unsupported dtype {coeffs.dtype}")
-        c = coeffs.contiguous()
+        c = coeffs.resolve_conj().resolve_neg().contiguous()   # data_ptr ignores lazy conj/neg bits
         size, deg = c.shape[0], c.shape[1] - 1
         ri_ptr = None
         if custom_init:
-            ri = roots_init.to(device=c.device, dtype=torch.complex128).contiguous()
+            ri = roots_init.to(device=c.device, dtype=torch.complex128).resolve_conj().resolve_neg().contiguous()
             if ri.shape != (size, deg):
                 raise ValueError("roots_init must have shape (size, deg)")
             ri_ptr = ri.data_ptr()
@@ -88,8 +88,9 @@ def roots_jvp(coeffs_low_high, roots, dcoeffs):
     dz = -(sum_k dp_k z^k) / p'(z).  Works on numpy arrays or torch tensors; coeffs/dcoeffs
     (size, deg+1) low->high, roots (size, deg)."""
     if isinstance(roots, torch.Tensor) and roots.is_cuda and roots.dim() == 2:
-        p = coeffs_low_high.to(torch.complex128).contiguous()
-        z, dp = roots.contiguous(), dcoeffs.to(torch.complex128).contiguous()
+        p = coeffs_low_high.to(torch.complex128).resolve_conj().resolve_neg().contiguous()
+        z = roots.resolve_conj().resolve_neg().contiguous()
+        dp = dcoeffs.to(torch.complex128).resolve_conj().resolve_neg().contiguous()
         out = torch.empty_like(z)
         with torch.cuda.device(z.device):
             _lib.check(_lib.lib().caustics_ea_jvp(p.data_ptr(), z.data_ptr(), dp.data_ptr(), out.data_ptr(),
@@ -121,7 +122,7 @@ class _PolyRoots(torch.autograd.Function):
         # holomorphic map is grad_p = conj(dz/dp) * grad_z (the tangent w.r.t. roots_init is zero,
         # ehrlich_aberth_primitive.py:299-302).  On the device this is one memory-bound kernel.
         if p.is_cuda:
-            g = grad_roots.to(torch.complex128).contiguous()
+            g = grad_roots.to(torch.complex128).resolve_conj().resolve_neg().contiguous()
             out = torch.empty_like(p)
             with torch.cuda.device(p.device):
                 _lib.check(_lib.lib().caustics_ea_vjp(p.data_ptr(), z.data_ptr(), g.data_ptr(), out.data_ptr(),

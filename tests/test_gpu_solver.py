@@ -201,3 +201,15 @@ def test_jvp_vjp_kernels(cb):
         lhs = np.real(np.sum(np.conj(g) * want))
         rhs = np.real(np.sum(np.conj(ct.grad.cpu().numpy()) * dc))
         assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs))
+
+
+def test_lazy_conj_inputs(cb):
+    """torch marks conj()/neg as lazy bits; the ABI must see the materialised values"""
+    rng = np.random.default_rng(5)
+    c = torch.from_numpy(rng.standard_normal((64, 6)) + 1j * rng.standard_normal((64, 6))).cuda()
+    a = cb.poly_roots(torch.conj(c), compensated=True)
+    b = cb.poly_roots(torch.conj(c).clone(), compensated=True)
+    assert torch.equal(a, b)
+    w = torch.from_numpy(rng.uniform(-1, 1, 50) + 1j * rng.uniform(-1, 1, 50)).cuda()
+    assert torch.equal(cb.mag_point_source(torch.conj(w), nlenses=2, s=0.9, q=0.2),
+                       cb.mag_point_source(torch.conj(w).clone(), nlenses=2, s=0.9, q=0.2))
