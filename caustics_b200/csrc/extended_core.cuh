@@ -193,9 +193,18 @@ __device__ void refine_select_body(const ExtCfg& cfg, const ExtBuf& b, int round
 #pragma unroll
     for (int j = 0; j < D; ++j) { pre[j] = b.zre[I3(pslot, j, s)]; pim[j] = b.zim[I3(pslot, j, s)]; pf[j] = b.flg[I3(pslot, j, s)]; }
   }
-  for (int i = 0; i + 1 < cur; ++i) {
-    double dmax = 0.0;
-    if (round == 0) {
+  // descending list; a later interval with an equal value ranks BEFORE earlier ones
+  auto consider = [&](double dmax, int i) {
+    if (cnt < n || dmax >= val[cnt - 1]) {
+      int pos = cnt < n ? cnt : n - 1;
+      while (pos > 0 && val[pos - 1] <= dmax) { val[pos] = val[pos - 1]; idx[pos] = idx[pos - 1]; --pos; }
+      val[pos] = dmax; idx[pos] = i;
+      if (cnt < n) ++cnt;
+    }
+  };
+  if (round == 0) {
+    for (int i = 0; i + 1 < cur; ++i) {
+      double dmax = 0.0;
       const int slot = b.order[I2(i + 1, s)];
 #pragma unroll
       for (int j = 0; j < D; ++j) {
@@ -208,15 +217,22 @@ __device__ void refine_select_body(const ExtCfg& cfg, const ExtBuf& b, int round
       }
       b.dval[I2(pslot, s)] = dmax;
       pslot = slot;
-    } else {
-      dmax = b.dval[I2(b.order[I2(i, s)], s)];
+      consider(dmax, i);
     }
-    // descending list; a later interval with an equal value ranks BEFORE earlier ones
-    if (cnt < n || dmax >= val[cnt - 1]) {
-      int pos = cnt < n ? cnt : n - 1;
-      while (pos > 0 && val[pos - 1] <= dmax) { val[pos] = val[pos - 1]; idx[pos] = idx[pos - 1]; --pos; }
-      val[pos] = dmax; idx[pos] = i;
-      if (cnt < n) ++cnt;
+  } else {
+    // the two loads per interval (order -> width) are issued eight intervals at a time, so a small
+    // batch of sources is not serialised on global-memory latency
+    constexpr int BATCH = 8;
+    for (int i0 = 0; i0 + 1 < cur; i0 += BATCH) {
+      int sl[BATCH];
+      double dv[BATCH];
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) sl[k] = (i0 + k + 1 < cur) ? (int)b.order[I2(i0 + k, s)] : 0;
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) dv[k] = b.dval[I2(sl[k], s)];
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k)
+        if (i0 + k + 1 < cur) consider(dv[k], i0 + k);
     }
   }
   // new points: rank r -> arrival slot cur + r; theta at the interval midpoint, warm start from the left end
@@ -236,14 +252,23 @@ __device__ void refine_select_body(const ExtCfg& cfg, const ExtBuf& b, int round
     rk[pos] = r;   // descending by interval index
   }
   int shift = n, q = 0;   // q walks rk[] (largest interval first)
-  for (int pth = cur - 1; pth >= 0; --pth) {
-    // every selected interval i >= pth has its new element after position i >= pth
-    while (q < n && idx[rk[q]] >= pth) {
-      b.order[I2(idx[rk[q]] + shift, s)] = (uint16_t)(cur + rk[q]);
-      --shift; ++q;
+  constexpr int SB = 8;
+  for (int p0 = cur - 1; p0 >= 0 && shift > 0; p0 -= SB) {
+    uint16_t ov[SB];
+#pragma unroll
+    for (int k = 0; k < SB; ++k) ov[k] = (p0 - k >= 0) ? b.order[I2(p0 - k, s)] : (uint16_t)0;   // loads first
+#pragma unroll
+    for (int k = 0; k < SB; ++k) {
+      const int pth = p0 - k;
+      if (pth < 0 || shift == 0) break;
+      // every selected interval i >= pth has its new element after position i >= pth
+      while (q < n && idx[rk[q]] >= pth) {
+        b.order[I2(idx[rk[q]] + shift, s)] = (uint16_t)(cur + rk[q]);
+        --shift; ++q;
+      }
+      if (shift == 0) break;
+      b.order[I2(pth + shift, s)] = ov[k];
     }
-    if (shift == 0) break;
-    b.order[I2(pth + shift, s)] = b.order[I2(pth, s)];
   }
 }
 
@@ -287,12 +312,24 @@ template <int D>
 __device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
   if (s >= nsrc(cfg, b)) return;
   double cre[D], cim[D];   // carry: previous column in track order
+  // the raw column of the NEXT limb point is fetched while the current one is matched
+  double nzr[D], nzi[D];
+  uint8_t nf[D];
+  {
+    const int slot0 = b.order[I2(0, s)];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { nzr[j] = b.zre[I3(slot0, j, s)]; nzi[j] = b.zim[I3(slot0, j, s)]; nf[j] = b.flg[I3(slot0, j, s)]; }
+  }
   for (int p = 0; p < cfg.NP; ++p) {
-    const int slot = b.order[I2(p, s)];
     double zr[D], zi[D];
     uint8_t f[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) { zr[j] = b.zre[I3(slot, j, s)]; zi[j] = b.zim[I3(slot, j, s)]; f[j] = b.flg[I3(slot, j, s)]; }
+    for (int j = 0; j < D; ++j) { zr[j] = nzr[j]; zi[j] = nzi[j]; f[j] = nf[j]; }
+    if (p + 1 < cfg.NP) {
+      const int slotn = b.order[I2(p + 1, s)];
+#pragma unroll
+      for (int j = 0; j < D; ++j) { nzr[j] = b.zre[I3(slotn, j, s)]; nzi[j] = b.zim[I3(slotn, j, s)]; nf[j] = b.flg[I3(slotn, j, s)]; }
+    }
     // exact duplicates (inside the column, or an unchanged warm start) get a tiny real offset
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -469,6 +506,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
   unsigned closed = 0;
   for (int i = 0; i < D; ++i) {
     bool all_real = true;
+#pragma unroll 8
     for (int p = 0; p < NP; ++p) all_real = all_real && (T.fl(i, p) & 1);
     const bool cl = cfg.nl == 1 || (all_real && norm2(T.pt(i, 0) - T.pt(i, NP - 1)) < 1e-10);
     if (!cl) continue;
@@ -482,6 +520,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
     }
     if (!cfg.ld) {
       G.start();
+#pragma unroll 8
       for (int p = 0; p < NP; ++p) G.add(T.pt(i, p));
       total += par * G.close();
     }
@@ -500,12 +539,16 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
       int np_ = 0, nend = 0;
       // boundaries in increasing order; the first MAXPARTS starts and ends are kept (:202-203)
       bool prev_real = false; double prev_par = 0.0; cd prev_z = mk(0, 0);
+#pragma unroll 4
       for (int p = 0; p <= NP; ++p) {
         bool real = false; double par = 0.0; cd z = mk(0, 0);
-        if (p < NP) {
-          const uint8_t f = T.fl(i, p);
-          real = f & 1;
-          if (real) { par = (f & 4) ? 0.0 : ((f & 2) ? 1.0 : -1.0); z = T.pt(i, p); }
+        {
+          // unconditional loads (clamped index) so that unrolled iterations overlap their latency
+          const int pc = p < NP ? p : NP - 1;
+          const uint8_t f = T.fl(i, pc);
+          const cd zz = T.pt(i, pc);
+          real = (p < NP) && (f & 1);
+          if (real) { par = (f & 4) ? 0.0 : ((f & 2) ? 1.0 : -1.0); z = zz; }
         }
         bool start = false, end = false;
         if (p == 0) start = real;
