@@ -725,11 +725,16 @@ __device__ void ld_sum_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
   for (int c = 0; c < nc; ++c) {
     const int v0 = b.cstart[(int64_t)c * cfg.S + s], v1 = b.cstart[(int64_t)(c + 1) * cfg.S + s];
     double acc = 0.0;
-    for (int v = v0; v + 1 < v1; ++v) {
-      const cb200_d2 za = b.vz[(int64_t)v * cfg.S + s], zb = b.vz[(int64_t)(v + 1) * cfg.S + s];
-      const double Pa = b.vP[(int64_t)v * cfg.S + s], Pb = b.vP[(int64_t)(v + 1) * cfg.S + s];
-      const double Qa = b.vQ[(int64_t)v * cfg.S + s], Qb = b.vQ[(int64_t)(v + 1) * cfg.S + s];
-      acc += 0.5 * (Pa + Pb) * (zb.x - za.x) + 0.5 * (Qa + Qb) * (zb.y - za.y);
+    if (v1 > v0) {
+      cb200_d2 za = b.vz[(int64_t)v0 * cfg.S + s];
+      double Pa = b.vP[(int64_t)v0 * cfg.S + s], Qa = b.vQ[(int64_t)v0 * cfg.S + s];
+#pragma unroll 8
+      for (int v = v0 + 1; v < v1; ++v) {
+        const cb200_d2 zb = b.vz[(int64_t)v * cfg.S + s];
+        const double Pb = b.vP[(int64_t)v * cfg.S + s], Qb = b.vQ[(int64_t)v * cfg.S + s];
+        acc += 0.5 * (Pa + Pb) * (zb.x - za.x) + 0.5 * (Qa + Qb) * (zb.y - za.y);
+        za = zb; Pa = Pb; Qa = Qb;
+      }
     }
     total += acc * b.cpar[(int64_t)c * cfg.S + s];
   }
