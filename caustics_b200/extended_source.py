@@ -198,5 +198,58 @@ def mag(w_points, rho, nlenses=2, npts_limb=200, limb_darkening=False, u1=0.0, n
     if nlenses not in (1, 2, 3):
         raise ValueError("nlenses must be <= 3")
     q = params.get("q", 1.0) if nlenses == 2 else 1.0
+    if _requires_grad(w_points, rho, u1, *params.values()):
+        if limb_darkening:
+            raise NotImplementedError("gradients of the limb-darkened magnification are not implemented; "
+                                      "the uniform disk is differentiable")
+        return _mag_differentiable(w_points, rho, nlenses, npts_limb, roots_itmax, roots_compensated,
+                                   params, return_test)
     return _run(w_points, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax,
-                roots_compensated, True, q, params, return_test=return_test)
+                roots_compensated, True, _detached(q), params, return_test=return_test)
+
+
+def _implicit_images(z0, w, nlenses, p):
+    """Images as differentiable functions of (w, lens parameters): one Newton step on the lens equation
+    from the kernel's images z0 with the Jacobian frozen there (see _mag_from_contours)."""
+    from .point_source import lens_eq, _lenses
+    F = lens_eq(z0, nlenses, **p) - w
+    r0, e0 = _lenses(nlenses, **{k: _detached(v) for k, v in p.items()})
+    g = sum(ej / (torch.conj(z0) - (torch.conj(rj) if isinstance(rj, torch.Tensor) else np.conj(rj))) ** 2
+            for rj, ej in zip(r0, e0)).detach()
+    return z0 + (-F + g * torch.conj(F)) / (1.0 - torch.abs(g) ** 2)
+
+
+def _mag_differentiable(w_points, rho, nlenses, npts_limb, roots_itmax, roots_compensated, params, return_test):
+    """`mag` with gradients (uniform disk): the gate decision comes from the kernels and is a constant,
+    as in the reference where lax.cond predicates carry no gradient; hexadecapole points go through
+    the torch form of the Cassan expansion evaluated at implicitly-differentiated images, the others
+    through the differentiable contour integration."""
+    from .multipole import hexadecapole_terms
+    from .point_source import _images_point_source, _lenses
+    dev = w_points.device if isinstance(w_points, torch.Tensor) and w_points.is_cuda else torch.device("cuda")
+    w = (w_points.to(dev, torch.complex128) if isinstance(w_points, torch.Tensor)
+         else torch.as_tensor(w_points, dtype=torch.complex128, device=dev))
+    shape = tuple(w.shape)
+    wf = w.reshape(-1)
+    detp = {k: _detached(v) for k, v in params.items()}
+    q = detp.get("q", 1.0) if nlenses == 2 else 1.0
+    _, used = _run(wf.detach(), float(_detached(rho)), nlenses, npts_limb, False, 0.0, 100, roots_itmax,
+                   roots_compensated, True, q, detp, return_test=True)
+    out = torch.zeros(wf.numel(), dtype=torch.float64, device=dev)
+    hx = torch.nonzero(used).reshape(-1)
+    fl = torch.nonzero(~used).reshape(-1)
+    if hx.numel():
+        p, x_cm = lens_params(nlenses, **params)
+        ws = wf[hx] + x_cm
+        p0 = {k: _detached(v) for k, v in p.items()}
+        z0, mask = _images_point_source(ws.detach(), nlenses, roots_itmax, roots_compensated, **p0)
+        z = _implicit_images(torch.where(mask, z0, torch.ones_like(z0)), ws[None, :], nlenses, p)
+        r, eps = _lenses(nlenses, **p)
+        mu0, dq, dh = hexadecapole_terms(z, torch.as_tensor(rho, dtype=torch.float64, device=dev), 0.0, r, eps)
+        val = torch.where(mask, torch.abs(mu0 + dq + dh), torch.zeros_like(mu0)).sum(0)
+        out = out.index_put((hx,), val)
+    if fl.numel():
+        val = _mag_uniform_differentiable(wf[fl], rho, nlenses, npts_limb, roots_itmax, roots_compensated, params)
+        out = out.index_put((fl,), val)
+    out = out.reshape(shape)
+    return (out, used.reshape(shape)) if return_test else out

@@ -225,3 +225,23 @@ def test_critical_and_caustic_curves(cb, ps_golden):
         # rows are continuous curves: no jumps larger than the typical step
         step = torch.abs(z_cr[:, 1:] - z_cr[:, :-1])
         assert step.max().item() < 0.5
+
+
+def test_mag_gradient(cb, g):
+    """jax.grad through `mag` in the reference == torch autograd here: same values as the plain path,
+    gradient w.r.t. s and rho against differences at fixed gate decisions"""
+    w = torch.from_numpy(g["lc_w"][::4]).cuda()
+    s = torch.tensor(0.9, dtype=torch.float64, device="cuda", requires_grad=True)
+    rho = torch.tensor(1e-2, dtype=torch.float64, device="cuda", requires_grad=True)
+    m, used = cb.mag(w, rho, nlenses=2, npts_limb=200, return_test=True, s=s, q=0.2)
+    plain, used0 = cb.mag(w, 1e-2, nlenses=2, npts_limb=200, return_test=True, s=0.9, q=0.2)
+    assert torch.equal(used, used0) and used.any() and (~used).any()
+    assert torch.allclose(m.detach(), plain, rtol=1e-9)
+    # hexadecapole points only: smooth, so plain central differences are a clean check
+    (m * used).sum().backward()
+    h = 1e-6
+    f = lambda ss, rr: (cb.mag(w, rr, nlenses=2, npts_limb=200, s=ss, q=0.2) * used).sum().item()
+    fd_s = (f(0.9 + h, 1e-2) - f(0.9 - h, 1e-2)) / (2 * h)
+    fd_r = (f(0.9, 1e-2 + 1e-7) - f(0.9, 1e-2 - 1e-7)) / 2e-7
+    assert abs(s.grad.item() - fd_s) <= 1e-5 * max(1.0, abs(fd_s))
+    assert abs(rho.grad.item() - fd_r) <= 1e-4 * max(1.0, abs(fd_r))
