@@ -40,6 +40,8 @@ DEG = 10
 LENS = dict(a=0.698, e1=0.02809, e2=0.9687, r3=-0.0197 - 0.95087j)
 F_UPDATE = 28 * DEG + 21          # flop per plain root update, SURVEY 8(d)
 INIT_FLOP = 600                   # initial estimates + |coefficients| per polynomial
+UPDATES_PER_POLY = 95.2           # plain root updates per polynomial on this workload
+NCU_DRAM_BYTES_PER_LAUNCH = 3.05e8  # 176 MB read + 129 MB written, profiles/r01_ncu_ea_kernel_deg10.csv
 CONFIG = {"workload": "C2: ehrlich_aberth on 10^6 degree-10 triple-lens polynomials per GPU "
                       "(w=linspace(-2,2,N*10^6)+0.1i sliced per rank), plain mode, itmax=2500, "
                       "reference-compatible initial estimates",
@@ -47,12 +49,20 @@ CONFIG = {"workload": "C2: ehrlich_aberth on 10^6 degree-10 triple-lens polynomi
           "l2": "inputs+outputs 336 MB per step > 126 MB L2 (no explicit flush needed)"}
 
 
-def make_coeffs(rank, world, n=N_POLY):
-    """HIGH -> LOW coefficients (the poly_roots convention) of this rank's slice, float64 NumPy."""
-    from oracle import lens
+def make_coeffs(rank, world, n=N_POLY, impl="ours"):
+    """HIGH -> LOW coefficients (the poly_roots convention) of this rank's slice, complex128 NumPy.
+    Our arm builds them with the product's own coefficient code on the GPU; the reference arm (no
+    GPU needed) with the oracle's NumPy restatement -- the same polynomial to rounding."""
     w = np.linspace(-2, 2, world * n)[rank * n:(rank + 1) * n] + 0.1j
     out = np.empty((n, DEG + 1), dtype=np.complex128)
     step = 100000
+    if impl == "ours":
+        import torch
+        from caustics_b200.point_source import _poly_coeffs_torch
+        for i in range(0, n, step):
+            out[i:i + step] = _poly_coeffs_torch(torch.from_numpy(w[i:i + step]).cuda(), 3, **LENS).cpu().numpy()
+        return out
+    from oracle import lens
     for i in range(0, n, step):
         out[i:i + step] = lens.poly_coeffs(w[i:i + step], 3, **LENS)
     return out
@@ -98,7 +108,7 @@ def other_configs(cb, L, _lib, torch):
     headline: C1 (degree-5 roots/s), C5 (binary point-source evals/s on a 2*10^7-point slice of the
     10^4 x 10^4 map), C4 (triple-lens uniform extended-source evals/s, 10^5 sources) and C3 (binary
     limb-darkened light curve through `mag`, 10^4 points with the hexadecapole gate)."""
-    from oracle import lens
+    from caustics_b200.point_source import _poly_coeffs_torch, lens_params
 
     def best(fn, reps=3):
         fn(); torch.cuda.synchronize()
@@ -111,9 +121,9 @@ def other_configs(cb, L, _lib, torch):
 
     out = {}
     hp2 = dict(s=0.9, q=0.2)
-    p, x_cm = lens.lens_params(2, **hp2)
+    p, x_cm = lens_params(2, **hp2)
     n = 1_000_000
-    c5 = torch.from_numpy(lens.poly_coeffs(np.linspace(-2, 2, n) + 0.1j + x_cm, 2, **p)).cuda()
+    c5 = _poly_coeffs_torch(torch.from_numpy(np.linspace(-2, 2, n) + 0.1j + x_cm).cuda(), 2, **p)
     out["C1_ehrlich_aberth_deg5_roots_per_s"] = 5 * n / best(lambda: cb.poly_roots(c5, itmax=2500))
     out["C1_ehrlich_aberth_deg5_compensated_roots_per_s"] = 5 * n / best(lambda: cb.poly_roots(c5, itmax=2500, compensated=True))
     lens_c = cb.point_source._c_lens(2, x_cm, **p)
@@ -162,7 +172,7 @@ def run_reference(args, rank, world):
     from oracle import solver
     ncpu = os.cpu_count() or 1
     sample = 100_000
-    c = np.ascontiguousarray(make_coeffs(0, 1, sample * 10)[::10][:, ::-1])
+    c = np.ascontiguousarray(make_coeffs(0, 1, sample * 10, impl="reference")[::10][:, ::-1])
     for _ in range(args.warmup):
         cpu_reference_time(c[:20000], ncpu)
     t0 = time.perf_counter()
@@ -287,11 +297,10 @@ def main():
         fp64_peak = dfma_peak(L.caustics_bench_fp64_peak)        # chains with two constant operands
         fp64_peak3 = dfma_peak(L.caustics_bench_fp64_peak3)      # three distinct register operands
 
-        # ---- algorithmic work: update counts from the CPU port on a sample --------------------
-        from oracle import solver
-        sample = np.ascontiguousarray(coeffs[::50][:, ::-1])
-        _, sweeps, stats = solver.port_solve(sample, itmax=2500, return_stats=True)
-        upd_per_poly = stats[0] / len(sample)
+        # ---- algorithmic work per polynomial: the fixed constants of DESIGN.md section 4 ----------
+        # (95.2 root updates per polynomial of this workload, counted by the CPU port of the
+        # reference algorithm and pinned by tests/test_oracle.py::test_c2_update_count)
+        upd_per_poly = UPDATES_PER_POLY
         flop_per_poly = upd_per_poly * F_UPDATE + INIT_FLOP
         achieved = N_POLY * flop_per_poly / (ms * 1e-3) / 1e12
         peaks = {}
@@ -302,7 +311,9 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_bytes = N_POLY * ((DEG + 1) * 16 + DEG * 16)
         roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp64_peak, "traffic": None,
+                    "frac": achieved / fp64_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                    "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of "
+                                      "ea_kernel<10,false> (profiles/); algorithmic bytes per launch = 3.36e8",
                     "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure)",
                     "peak_3operand_dfma": fp64_peak3, "frac_of_3operand_peak": achieved / fp64_peak3,
                     "note": "a DFMA reading three distinct register pairs issues at ~69 % of the constant-operand "
@@ -313,6 +324,7 @@ def main():
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         cpu = None
         if not args.no_cpu_baseline:
+            from oracle import solver
             ncs = 1_000_000 // 8
             cs = np.ascontiguousarray(coeffs[::8][:, ::-1])
             dt = cpu_reference_time(cs, 1)

@@ -53,13 +53,13 @@ def main():
         print(json.dumps(rec), flush=True)
 
     want = lambda k: not args.only or k in args.only.split(",")
-    from oracle import lens, extended, solver
+    from caustics_b200.point_source import _poly_coeffs_torch, lens_params
 
     if want("C1"):
         # C1: 10^4 degree-5 polynomials (binary trajectory); too small to fill a B200 -> also 10^6
         for n in (10_000, 1_000_000):
-            p, x_cm = lens.lens_params(2, **HP2)
-            c = torch.from_numpy(lens.poly_coeffs(np.linspace(-2, 2, n) + 0.1j + x_cm, 2, **p)).cuda()
+            p, x_cm = lens_params(2, **HP2)
+            c = _poly_coeffs_torch(torch.from_numpy(np.linspace(-2, 2, n) + 0.1j + x_cm).cuda(), 2, **p)
             for comp in (False, True):
                 t = timeit(lambda: cb.poly_roots(c, itmax=2500, compensated=comp))
                 emit(f"C1 ehrlich_aberth deg5 n={n} compensated={comp}", "roots/s", 5 * n, t)
@@ -74,7 +74,7 @@ def main():
         for flags in (0, 1):
             t = timeit(lambda: _lib.check(L.caustics_mag_point_source(w.data_ptr(), mag.data_ptr(), None, n, lens_c, 2500, 0, flags, None)))
             emit(f"C2 fused mag_point_source triple n={n} flags={flags}", "evals/s", n, t)
-        c = torch.from_numpy(lens.poly_coeffs(np.linspace(-2, 2, n) + 0.1j, 3, **C2P)).cuda()
+        c = _poly_coeffs_torch(torch.from_numpy(np.linspace(-2, 2, n) + 0.1j).cuda(), 3, **C2P)
         for comp, flags in ((False, 0), (False, 1), (True, 0)):
             t = timeit(lambda: cb.poly_roots(c, itmax=2500, compensated=comp, flags=flags))
             emit(f"C2 ehrlich_aberth deg10 n={n} compensated={comp} flags={flags}", "roots/s", 10 * n, t)
@@ -93,6 +93,7 @@ def main():
         t = timeit(lambda: cb.mag_extended_source(wf, 1e-2, nlenses=2, npts_limb=200, **HP2), reps=3, warm=1)
         emit("C3 same points, uniform disk", "evals/s", nfull, t)
         if args.cpu:
+            from oracle import extended      # CPU baseline leg only
             sub = np.linspace(-2, 2, n)[::100] + 0.1j
             t0 = time.perf_counter(); extended.mag(sub, 1e-2, 2, 200, True, 0.7, 100, **HP2); dt = time.perf_counter() - t0
             emit("C3 CPU oracle (NumPy restatement + reference solver), 1 core, every 100th point", "evals/s", len(sub), dt)
@@ -110,7 +111,7 @@ def main():
              finite=bool(torch.isfinite(mag).all().item()))
     if want("C5"):
         nx, rows = 10_000, 2_000     # 2*10^7 of the 10^8 grid points per timing
-        p, x_cm = lens.lens_params(2, **HP2)
+        p, x_cm = lens_params(2, **HP2)
         lens_c = cb.point_source._c_lens(2, x_cm, **p)
         mag = torch.empty(nx * rows, dtype=torch.float64, device="cuda")
         for flags in (0, 1):

@@ -105,3 +105,13 @@ def test_jvp_rule_vs_finite_differences():
     zm = solver.port_solve(c - h * dc, compensated=True, custom_init=True, roots_init=z)
     fd = (zp - zm) / (2 * h)
     assert np.allclose(lens.jvp_roots(c, z, dc), fd, rtol=1e-4, atol=1e-4)
+
+
+def test_c2_update_count():
+    """the algorithmic-work constant bench.py uses for the roofline: plain root
+    updates per polynomial of the C2 workload, counted by the restatement of the reference algorithm"""
+    w = np.linspace(-2, 2, 1000000)[::500] + 0.1j
+    c = lens.poly_coeffs(w, 3, a=0.698, e1=0.02809, e2=0.9687, r3=-0.0197 - 0.95087j)
+    _, sweeps, stats = solver.port_solve(np.ascontiguousarray(c[:, ::-1]), itmax=2500, return_stats=True)
+    assert abs(stats[0] / len(w) - 95.2) < 1.5
+    assert stats[2] == 0
