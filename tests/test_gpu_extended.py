@@ -208,8 +208,6 @@ def test_uniform_gradients_vs_finite_differences(cb, g):
     m1.sum().backward()
     exact = -4.0 / (0.1**3 * np.sqrt(1 + 4 / 0.1**2))        # d/drho sqrt(1 + 4/rho^2)
     assert abs(r1.grad.item() / exact - 1) < 2e-3
-    with pytest.raises(NotImplementedError):
-        cb.mag_extended_source(wb, 1e-2, nlenses=2, limb_darkening=True, u1=0.3, s=s, q=0.2)
 
 
 def test_critical_and_caustic_curves(cb, ps_golden):
@@ -245,3 +243,35 @@ def test_mag_gradient(cb, g):
     fd_r = (f(0.9, 1e-2 + 1e-7) - f(0.9, 1e-2 - 1e-7)) / 2e-7
     assert abs(s.grad.item() - fd_s) <= 1e-5 * max(1.0, abs(fd_s))
     assert abs(rho.grad.item() - fd_r) <= 1e-4 * max(1.0, abs(fd_r))
+
+
+def test_grad_limb_darkened_binary(cb):
+    """the reference's own gradient test (tests/test_extended_source.py:293-331): jacobian of the
+    limb-darkened binary magnification w.r.t. (s, q, rho, u1) at the first caustic point,
+    npts_limb=300, npts_ld=100, rtol 1e-3 against finite differences"""
+    from caustics_b200 import extended_source as es
+    _, ca = cb.critical_and_caustic_curves(npts=50, nlenses=2, s=0.9, q=0.2)
+    w0 = ca.reshape(-1)[:1].clone()
+    base = dict(s=0.9, q=0.2)
+    rho0, u10 = 1e-2, 0.7
+    t = {k: torch.tensor(v, dtype=torch.float64, device="cuda", requires_grad=True) for k, v in base.items()}
+    rho = torch.tensor(rho0, dtype=torch.float64, device="cuda", requires_grad=True)
+    u1 = torch.tensor(u10, dtype=torch.float64, device="cuda", requires_grad=True)
+    m = cb.mag_extended_source(w0, rho, nlenses=2, npts_limb=300, limb_darkening=True, u1=u1, npts_ld=100, **t)
+    plain = cb.mag_extended_source(w0, rho0, nlenses=2, npts_limb=300, limb_darkening=True, u1=u10, npts_ld=100, **base)
+    assert torch.allclose(m.detach(), plain, rtol=1e-9)     # torch quadrature == CUDA quadrature
+    m.sum().backward()
+    cont = es._get_contours(w0, rho0, 2, 300, 2500, False, base)
+
+    def frozen(rho_=rho0, u1_=u10, **over):
+        with torch.no_grad():
+            return es._mag_from_contours(cont, w0.reshape(-1), rho_, 2, dict(base, **over), newton_steps=5,
+                                         ld=(u1_, 100)).sum().item()
+
+    for k in base:
+        fd = (frozen(**{k: base[k] + 1e-8}) - frozen(**{k: base[k] - 1e-8})) / 2e-8
+        assert abs(t[k].grad.item() - fd) <= 1e-3 * abs(fd), (k, t[k].grad.item(), fd)
+    fd = (frozen(rho_=rho0 + 1e-9) - frozen(rho_=rho0 - 1e-9)) / 2e-9
+    assert abs(rho.grad.item() - fd) <= 1e-3 * abs(fd)
+    fd = (frozen(u1_=u10 + 1e-6) - frozen(u1_=u10 - 1e-6)) / 2e-6
+    assert abs(u1.grad.item() - fd) <= 1e-3 * abs(fd)

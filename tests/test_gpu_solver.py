@@ -213,3 +213,24 @@ def test_lazy_conj_inputs(cb):
     w = torch.from_numpy(rng.uniform(-1, 1, 50) + 1j * rng.uniform(-1, 1, 50)).cuda()
     assert torch.equal(cb.mag_point_source(torch.conj(w), nlenses=2, s=0.9, q=0.2),
                        cb.mag_point_source(torch.conj(w).clone(), nlenses=2, s=0.9, q=0.2))
+
+
+def test_pathological_inputs_terminate(cb):
+    """NaN / Inf / all-zero / zero-leading-coefficient polynomials: bounded by itmax, no hang, the
+    healthy polynomials in the same warps are unaffected"""
+    rng = np.random.default_rng(3)
+    c = rng.standard_normal((256, 6)) + 1j * rng.standard_normal((256, 6))
+    good = c.copy()
+    c[3] = np.nan
+    c[40] = 0.0
+    c[77, 0] = 0.0            # zero leading coefficient (high -> low order)
+    c[100, -1] = 0.0          # zero constant term: a root at the origin
+    c[130, 2] = np.inf
+    out, sw = cb.primitive._solve_flat(torch.from_numpy(c).cuda(), None, 60, False, False,
+                                       cb._lib.FLAG_COEFFS_HIGH_FIRST, return_sweeps=True)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    ref = cb.poly_roots(torch.from_numpy(good).cuda(), itmax=60).cpu().numpy()
+    keep = np.setdiff1d(np.arange(256), [3, 40, 77, 100, 130])
+    assert np.array_equal(out[keep], ref[keep])
+    assert np.abs(out[100]).min() < 1e-300      # the root at the origin
