@@ -184,6 +184,7 @@ __device__ void refine_select_body(const ExtCfg& cfg, const ExtBuf& b, int round
   double val[NADD_MAX];
   int idx[NADD_MAX];
   int cnt = 0;
+  val[0] = 0.0;
   // Interval widths are kept per interval (dval, indexed by the slot that starts it): round 0 measures
   // all of them, later rounds only read them -- a new point changes exactly two (refine_solve_body).
   double pre[D], pim[D];
