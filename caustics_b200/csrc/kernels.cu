@@ -145,7 +145,10 @@ ps_kernel(const double2* __restrict__ w_in, GridSpec g, const double2* __restric
   const int tid = threadIdx.x;
   const int64_t idx = (int64_t)blockIdx.x * NT + tid;
   const bool active = idx < n;
-  const int init_mode = flags & CAUSTICS_FLAG_INIT_BINI ? EA_INIT_BINI : EA_INIT_REFERENCE;
+  // The magnification is a sum over images: the root ORDER is irrelevant, so the fused magnification
+  // always starts from the intended complex Bini estimates (~10 % fewer updates than the reference's
+  // real-axis guesses); the images mode keeps the reference-compatible order unless asked otherwise.
+  const int init_mode = (MODE == PS_MAG || (flags & CAUSTICS_FLAG_INIT_BINI)) ? EA_INIT_BINI : EA_INIT_REFERENCE;
   cd w = mk(0.3, 0.2);
   if (active) {
     if (g.use) {
