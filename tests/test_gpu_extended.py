@@ -275,3 +275,19 @@ def test_grad_limb_darkened_binary(cb):
     assert abs(rho.grad.item() - fd) <= 1e-3 * abs(fd)
     fd = (frozen(u1_=u10 + 1e-6) - frozen(u1_=u10 - 1e-6)) / 2e-6
     assert abs(u1.grad.item() - fd) <= 1e-3 * abs(fd)
+
+
+@pytest.mark.parametrize("hp", [dict(s=1.5, q=0.5), dict(s=0.5, q=1.0), dict(s=1.2, q=1e-3), dict(s=0.8, q=1e-2)])
+def test_other_geometries_and_radii(cb, hp):
+    """wide / close / planetary binaries and source radii from 1e-4 to 1 (the reference's tests span
+    rho = 1 ... 1e-4, tests/test_extended_source.py:209,259) against the oracle"""
+    rng = np.random.default_rng(5)
+    w = rng.uniform(-0.3, 0.3, 8) + 1j * rng.uniform(-0.3, 0.3, 8)
+    for rho in (1.0, 5e-2, 5e-3, 1e-4):
+        got = cb.mag_extended_source(w, rho, nlenses=2, npts_limb=200, **hp)
+        assert np.allclose(got, _oracle(w, rho, 2, hp, npts_limb=200), rtol=1e-4, atol=0)
+    got = cb.mag_extended_source(w[:4], 5e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.5, **hp)
+    assert np.allclose(got, _oracle(w[:4], 5e-2, 2, hp, npts_limb=200, limb_darkening=True, u1=0.5), rtol=1e-4, atol=0)
+    got, used = cb.mag(w, 5e-3, nlenses=2, npts_limb=200, return_test=True, **hp)
+    want, t_want = extended.mag(w, 5e-3, 2, 200, return_test=True, **hp)
+    assert (used == t_want).all() and np.allclose(got, want, rtol=1e-4, atol=0)

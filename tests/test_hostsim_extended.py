@@ -93,3 +93,16 @@ def test_single_and_gate(hs, g):
     assert np.allclose(got[t_want], want[t_want], rtol=1e-10)          # hexadecapole: pure arithmetic
     assert np.allclose(got[~t_want], want[~t_want], rtol=1e-8)
     assert np.allclose(got, g["lc_unif"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("hp", [dict(s=1.5, q=0.5), dict(s=0.5, q=1.0), dict(s=1.2, q=1e-3)])
+def test_other_geometries_and_radii(hs, hp):
+    """wide / close / planetary binaries, source radii from 1e-4 to 1: device logic == oracle"""
+    rng = np.random.default_rng(5)
+    w = rng.uniform(-0.3, 0.3, 6) + 1j * rng.uniform(-0.3, 0.3, 6)
+    for rho in (1.0, 5e-2, 1e-4):
+        want = np.array([extended.mag_extended_source(x, rho, 2, 200, **hp) for x in w])
+        assert np.allclose(hs_ext(hs, w, rho, 2, hp), want, rtol=1e-6)
+    want, t_want = extended.mag(w, 5e-3, 2, 200, return_test=True, **hp)
+    got, t_got = hs_ext(hs, w, 5e-3, 2, hp, gate=True)
+    assert (t_got == t_want).all() and np.allclose(got, want, rtol=1e-7)
