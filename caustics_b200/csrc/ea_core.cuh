@@ -69,6 +69,26 @@ __device__ __forceinline__ void ea_normalise(cd (&p)[DEG + 1]) {
   }
 }
 
+// log for the initial estimates.  CB200_FAST_LOG: exponent * ln 2 + single-precision log2 of the
+// mantissa (~1e-7 absolute), enough for starting values; 0: libm double log.
+#ifndef CB200_FAST_LOG
+#define CB200_FAST_LOG 0
+#endif
+__device__ __forceinline__ double ea_log(double a) {
+#if CB200_FAST_LOG && !defined(CB200_HOSTSIM)
+  const int hi = __double2hiint(a), lo = __double2loint(a);
+  const int e = ((hi >> 20) & 0x7ff) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);   // mantissa in [1, 2)
+  return ((double)e + (double)__log2f((float)m)) * 0.6931471805599453;
+#else
+  return log(a);
+#endif
+}
+
+// cos / sin of 2 pi / n, n = 0..16 (n = 0 unused)
+__device__ const double EA_ROT_COS[17] = {1.0, 1.0, -1.0, -0.4999999999999998, 6.123233995736766e-17, 0.30901699437494745, 0.5000000000000001, 0.6234898018587336, 0.7071067811865476, 0.766044443118978, 0.8090169943749475, 0.8412535328311812, 0.8660254037844387, 0.8854560256532099, 0.9009688679024191, 0.9135454576426009, 0.9238795325112867};
+__device__ const double EA_ROT_SIN[17] = {0.0, -2.4492935982947064e-16, 1.2246467991473532e-16, 0.8660254037844387, 1.0, 0.9510565162951535, 0.8660254037844386, 0.7818314824680298, 0.7071067811865475, 0.6427876096865393, 0.5877852522924731, 0.5406408174555976, 0.49999999999999994, 0.4647231720437685, 0.4338837391175581, 0.40673664307580015, 0.3826834323650898};
+
 // Bini initial estimates from the upper convex hull of (i, log|p_i|) -- init_est.h:57-102.
 // mode EA_INIT_REFERENCE reproduces the reference's purely real guesses r*sin(.) (the comma
 // expression at init_est.h:95), so sweep counts and root order match the reference; EA_INIT_BINI
@@ -78,7 +98,7 @@ __device__ __noinline__ void ea_init_est(const ALPHA& al, double* zre, double* z
   double ly[DEG + 1];
   int hx[DEG + 1];
 #pragma unroll
-  for (int i = 0; i <= DEG; ++i) { const double a = al.get(i); ly[i] = a > 0 ? log(a) : -1e30; }
+  for (int i = 0; i <= DEG; ++i) { const double a = al.get(i); ly[i] = a > 0 ? ea_log(a) : -1e30; }
   int k = 0;
   for (int i = DEG; i >= 0; --i) {
     while (k >= 2) {
@@ -88,19 +108,22 @@ __device__ __noinline__ void ea_init_est(const ALPHA& al, double* zre, double* z
     }
     hx[k++] = i;
   }
-  const double pi2 = 6.28318530717958647693, sigma = 0.7, th = pi2 / DEG;
   int pos = 0;
   for (int i = k - 2; i >= 0; --i) {
     int lo = hx[i + 1], up = hx[i];
     int nz = up - lo;
     // (|p_lo| / |p_up|)^(1/nz), from the logs already at hand
     double r = exp((ly[lo] - ly[up]) / nz);
-    double ang = pi2 / nz;
+    // angles 2 pi j / nz + 2 pi i / DEG + 0.7: one sincospi per hull edge, then exact-table rotations
+    // by 2 pi / nz (instead of one libm sincos per root)
+    double s, c;
+    sincospi(fma((double)i, 2.0 / DEG, 0.22281692032865347), &s, &c);   // 0.7 / pi
+    const double rc = EA_ROT_COS[nz], rs = EA_ROT_SIN[nz];
     for (int j = 0; j < nz; ++j) {
-      double s, c;
-      sincos(ang * j + th * i + sigma, &s, &c);
       zre[(pos + j) * NT] = (mode == EA_INIT_REFERENCE) ? r * s : r * c;
       zim[(pos + j) * NT] = (mode == EA_INIT_REFERENCE) ? 0.0 : r * s;
+      const double cn = fma(c, rc, -s * rs), sn = fma(s, rc, c * rs);
+      c = cn; s = sn;
     }
     pos += nz;
   }

@@ -37,5 +37,6 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int, int = 32
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int, int = 32) { return v; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(unsigned x) { return __builtin_ffs(x); }
+static inline void sincospi(double x, double* s, double* c) { *s = sin(3.14159265358979323846 * x); *c = cos(3.14159265358979323846 * x); }
 using std::max;
 using std::min;
