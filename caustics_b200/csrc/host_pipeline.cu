@@ -6,6 +6,7 @@
 // grown on demand and reused across calls; nothing else in the library allocates.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <mutex>
 
 #include "../../include/caustics_b200.h"
@@ -60,12 +61,16 @@ int get_ws(Workspace** out) {
   return CAUSTICS_OK;
 }
 
-// chunk length: large enough to amortise launch + copy latency, small enough to pipeline
+// chunk length: large enough to amortise launch + copy latency, small enough that the pipeline's
+// fill (first H2D) and drain (last kernel + D2H) stay a small part of the call.
+// CAUSTICS_B200_CHUNK overrides it (experiments).
 int64_t pick_chunk(int64_t n) {
-  int64_t c = (n + 2 * NSLOT - 1) / (2 * NSLOT);
-  const int64_t lo = 1 << 14, hi = 1 << 18;
-  if (c < lo) c = lo;
-  if (c > hi) c = hi;
+  static int64_t forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("CAUSTICS_B200_CHUNK");
+    forced = e ? atoll(e) : 0;
+  }
+  int64_t c = forced > 0 ? forced : (int64_t)1 << 15;
   return c < n ? c : n;
 }
 
