@@ -311,7 +311,10 @@ struct EAResult {
 // Solve one polynomial per thread.  p: coefficients low->high (already normalised) in registers.
 // Roots are read from / left in sm.zre/zim[.][tid] (the caller stores custom initial roots there
 // when custom_init).  All 32 lanes of a warp must call this together; `active` = false lanes idle.
-template <int DEG, bool COMP, int NT>
+// STRAIGHT selects the straight-line plain step (best for cold starts, where ~90 % of the evaluations
+// are followed by an update) or the branchy one that skips the Aberth sum when no lane updates (best
+// for warm starts, where every root's second evaluation only confirms convergence).
+template <int DEG, bool COMP, int NT, bool STRAIGHT = (CB200_STRAIGHT_LINE != 0)>
 __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASmem<DEG, COMP, NT>& sm,
                                                     int tid, bool active, bool custom_init,
                                                     int init_mode, int itmax) {
@@ -362,8 +365,7 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
       const bool need1 = !((c1 >> j) & 1u);
       const bool need2 = COMP && !need1 && !((c2 >> j) & 1u);
       if (!__any_sync(0xffffffffu, need1 || need2)) continue;
-#if CB200_STRAIGHT_LINE
-      if (!COMP) {
+      if (STRAIGHT && !COMP) {
         // warp-uniform choice of the evaluation variant, then one straight-line step
         const bool rv = zre[j * NT] * zre[j * NT] + zim[j * NT] * zim[j * NT] > 1.0;
         const bool all_std = __all_sync(0xffffffffu, !need1 || !rv);
@@ -373,7 +375,6 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
         else ea_step_plain<DEG, 2, NT, ALPHA>(p, al, zre, zim, j, need1, c1);
         continue;
       }
-#endif
 
       const cd z = mk(zre[j * NT], zim[j * NT]);
       const double az2 = norm2(z);

@@ -11,6 +11,10 @@
 #include "lens_core.cuh"
 #include "multipole.cuh"
 
+#ifndef CB200_EXT_STRAIGHT
+#define CB200_EXT_STRAIGHT 0   // warm-started limb solves: the branchy step (see ea_solve_thread)
+#endif
+
 namespace cb200 {
 
 #ifdef CB200_HOSTSIM
@@ -98,7 +102,7 @@ __device__ __forceinline__ void solve_and_store(const ExtCfg& cfg, const ExtBuf&
   cd p[D + 1];
   lens_poly<NL>(L, w, p);
   ea_normalise<D>(p);
-  ea_solve_thread<D, COMP, NT>(p, sm, tid, active, warm, EA_INIT_REFERENCE, cfg.itmax);
+  ea_solve_thread<D, COMP, NT, CB200_EXT_STRAIGHT != 0>(p, sm, tid, active, warm, EA_INIT_REFERENCE, cfg.itmax);
   if (!active) return;
 #pragma unroll
   for (int j = 0; j < D; ++j) {
