@@ -34,6 +34,7 @@ using namespace cb200;
 namespace {
 
 constexpr int NT = 128;
+constexpr int64_t SMALL_BATCH = 16384;   // below this many sources the warp-per-source selection is used
 
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUSTICS_ERR_CUDA_BASE + (int)e; }
 
@@ -49,6 +50,13 @@ __global__ void __launch_bounds__(NT) k_limb_walk_single(ExtCfg cfg, ExtBuf b, L
 template <int D>
 __global__ void __launch_bounds__(NT) k_refine_select(ExtCfg cfg, ExtBuf b, int round) {
   refine_select_body<D>(cfg, b, round, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+// small batches: one warp per source (4 sources per 128-thread CTA)
+template <int D>
+__global__ void __launch_bounds__(NT) k_refine_select_warp(ExtCfg cfg, ExtBuf b, int round) {
+  const int64_t s = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  if (s >= nsrc(cfg, b)) return;   // warp-uniform
+  refine_select_warp_body<D>(cfg, b, round, s, threadIdx.x & 31);
 }
 template <int NL, bool COMP>
 __global__ void __launch_bounds__(NT) k_refine_solve(ExtCfg cfg, ExtBuf b, LensConst L, int round) {
@@ -66,12 +74,62 @@ template <int D>
 __global__ void __launch_bounds__(NT) k_contours(ExtCfg cfg, ExtBuf b, LensConst L) {
   contours_body<D>(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
+// small batches: one warp per source; the lanes copy the source's tracks into shared memory, lane 0
+// runs the (scalar) stitching logic on the copy
+template <int D>
+__global__ void __launch_bounds__(32) k_contours_staged(ExtCfg cfg, ExtBuf b, LensConst L) {
+  extern __shared__ double stage_mem[];
+  const int64_t s = blockIdx.x;
+  if (s >= nsrc(cfg, b)) return;
+  const int n = cfg.NP * D;
+  double* re = stage_mem;
+  double* im = re + n;
+  double* th = im + n;
+  uint8_t* f = (uint8_t*)(th + cfg.NP);
+  for (int k = threadIdx.x; k < n; k += 32) {
+    const int64_t g = (int64_t)k * cfg.S + s;    // k = p * D + track, same order as the global planes
+    re[k] = b.sre[g]; im[k] = b.sim[g]; f[k] = b.sflg[g];
+  }
+  if (b.vth)
+    for (int pth = threadIdx.x; pth < cfg.NP; pth += 32)
+      th[pth] = b.theta[(int64_t)b.order[(int64_t)pth * cfg.S + s] * cfg.S + s];
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    const TrackStage st{re, im, f, th};
+    contours_body<D>(cfg, b, L, s, &st);
+  }
+}
 template <int NL>
 __global__ void __launch_bounds__(NT) k_ld_pq(ExtCfg cfg, ExtBuf b, LensConst L) {
   ld_pq_body<NL>(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
 __global__ void __launch_bounds__(NT) k_ld_sum(ExtCfg cfg, ExtBuf b) {
   ld_sum_body(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+// small batches: one warp per source; lanes share the edges of each contour (trapezoid of P dx + Q dy)
+__global__ void __launch_bounds__(NT) k_ld_sum_warp(ExtCfg cfg, ExtBuf b) {
+  const int64_t s = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  if (s >= nsrc(cfg, b)) return;   // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int nc = b.ncont[s];
+  double total = 0.0;
+  for (int c = 0; c < nc; ++c) {
+    const int v0 = b.cstart[(int64_t)c * cfg.S + s], v1 = b.cstart[(int64_t)(c + 1) * cfg.S + s];
+    double acc = 0.0;
+    for (int v = v0 + lane; v + 1 < v1; v += 32) {
+      const double2 za = b.vz[(int64_t)v * cfg.S + s], zb = b.vz[(int64_t)(v + 1) * cfg.S + s];
+      const double Pa = b.vP[(int64_t)v * cfg.S + s], Pb = b.vP[(int64_t)(v + 1) * cfg.S + s];
+      const double Qa = b.vQ[(int64_t)v * cfg.S + s], Qb = b.vQ[(int64_t)(v + 1) * cfg.S + s];
+      acc += 0.5 * (Pa + Pb) * (zb.x - za.x) + 0.5 * (Qa + Qb) * (zb.y - za.y);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    total += acc * b.cpar[(int64_t)c * cfg.S + s];
+  }
+  if (lane == 0) {
+    const int64_t out_idx = b.list ? (int64_t)b.list[s] : s;
+    b.mag[out_idx] = fabs(total) / (3.14159265358979323846 * cfg.rho * cfg.rho);
+  }
 }
 template <bool COMP>
 __global__ void __launch_bounds__(NT) k_gate(const double2* w_in, double* mag, uint8_t* test_out, int32_t* list,
@@ -96,17 +154,26 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
   if (NL == 1) k_limb_walk_single<<<gs, NT, 0, st>>>(cfg, b, L);
   else k_limb_walk<(NL == 1 ? 2 : NL)><<<gs, NT, 0, st>>>(cfg, b, L);
   for (int r = 0; r < NITER; ++r) {
-    k_refine_select<D><<<gs, NT, 0, st>>>(cfg, b, r);
+    if (cfg.S <= SMALL_BATCH) k_refine_select_warp<D><<<(unsigned)((cfg.S + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, r);
+    else k_refine_select<D><<<gs, NT, 0, st>>>(cfg, b, r);
     if (NL == 1) k_refine_solve_single<<<gr, NT, 0, st>>>(cfg, b, L, r);
     else if (cfg.comp) k_refine_solve<(NL == 1 ? 2 : NL), true><<<gr, NT, 0, st>>>(cfg, b, L, r);
     else k_refine_solve<(NL == 1 ? 2 : NL), false><<<gr, NT, 0, st>>>(cfg, b, L, r);
   }
   k_tracks<D><<<gs, NT, 0, st>>>(cfg, b);
-  k_contours<D><<<gs, NT, 0, st>>>(cfg, b, L);
+  const size_t stage_bytes = (size_t)cfg.NP * D * 17 + (size_t)cfg.NP * 8 + 64;
+  if (cfg.S <= SMALL_BATCH && stage_bytes <= 200 * 1024) {
+    if (stage_bytes > 48 * 1024)
+      cudaFuncSetAttribute(k_contours_staged<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+    k_contours_staged<D><<<(unsigned)cfg.S, 32, stage_bytes, st>>>(cfg, b, L);
+  } else {
+    k_contours<D><<<gs, NT, 0, st>>>(cfg, b, L);
+  }
   if (cfg.ld) {
     const unsigned gv = (unsigned)(((int64_t)cfg.VMAX * cfg.S + NT - 1) / NT);
     k_ld_pq<NL><<<gv, NT, 0, st>>>(cfg, b, L);
-    k_ld_sum<<<gs, NT, 0, st>>>(cfg, b);
+    if (cfg.S <= SMALL_BATCH) k_ld_sum_warp<<<(unsigned)((cfg.S + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b);
+    else k_ld_sum<<<gs, NT, 0, st>>>(cfg, b);
   }
   return cuda_rc(cudaGetLastError());
 }

@@ -277,6 +277,81 @@ __device__ void refine_select_body(const ExtCfg& cfg, const ExtBuf& b, int round
   }
 }
 
+// The same selection for SMALL batches, one WARP per source: the thread-per-source version above is a
+// chain of ~200 dependent global loads per round, which is latency-bound when there are only a few
+// hundred sources (a light curve's full-integration points).  Here the lanes share the intervals, the
+// top-n is n rounds of a warp arg-max with the same ordering (value descending, ties to the higher
+// interval index), and the splice is one parallel scatter.
+#ifdef CB200_HOSTSIM
+constexpr int SEL_LANES = 1;
+constexpr int SEL_PER_LANE = 4000;            // the host logic test runs the "warp" with one lane
+#else
+constexpr int SEL_LANES = 32;
+constexpr int SEL_PER_LANE = 4000 / 32 + 1;   // NP <= 4000
+#endif
+
+template <int D>
+__device__ void refine_select_warp_body(const ExtCfg& cfg, const ExtBuf& b, int round, int64_t s, int lane) {
+  const int cur = cfg.N0 + round * cfg.nadd, n = cfg.nadd;
+  const int nint = cur - 1;
+  // widths of this lane's intervals i = lane, lane + 32, ...
+  double myv[SEL_PER_LANE];
+  int cntl = 0;
+  for (int i = lane; i < nint; i += SEL_LANES, ++cntl) {
+    const int sa = b.order[I2(i, s)];
+    double d;
+    if (round == 0) {
+      d = interval_width2<D>(cfg, b, sa, b.order[I2(i + 1, s)], s);
+      b.dval[I2(sa, s)] = d;
+    } else {
+      d = b.dval[I2(sa, s)];
+    }
+    myv[cntl] = d;
+  }
+  // n rounds of arg-max over (value, interval index), lexicographic, descending
+  int sel[NADD_MAX];
+  for (int r = 0; r < n; ++r) {
+    double bv = -1.0; int bi = -1;
+    for (int k = 0, i = lane; k < cntl; ++k, i += SEL_LANES)
+      if (myv[k] > bv || (myv[k] == bv && i > bi)) { bv = myv[k]; bi = i; }
+#ifndef CB200_HOSTSIM
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+    }
+#endif
+    sel[r] = bi;
+    if (bi >= 0 && (bi % SEL_LANES) == lane) myv[bi / SEL_LANES] = -2.0;   // taken
+  }
+  // new points (rank r -> arrival slot cur + r): lanes share the ranks
+  for (int r = lane; r < n; r += SEL_LANES) {
+    const int i = sel[r];
+    const int sl = b.order[I2(i, s)], sr = b.order[I2(i + 1, s)];
+    b.theta[I2(cur + r, s)] = 0.5 * (b.theta[I2(sl, s)] + b.theta[I2(sr, s)]);
+    b.left[I2(r, s)] = (uint16_t)sl;
+    b.right[I2(r, s)] = (uint16_t)sr;
+  }
+  // splice: the element at position p moves to p + #(selected intervals < p); the new element of
+  // interval i lands at i + 1 + #(selected < i).  Read everything first, then scatter.
+  uint16_t mine[SEL_PER_LANE];
+  int np = 0;
+  for (int pth = lane; pth < cur; pth += SEL_LANES, ++np) mine[np] = b.order[I2(pth, s)];
+  __syncwarp();
+  np = 0;
+  for (int pth = lane; pth < cur; pth += SEL_LANES, ++np) {
+    int c = 0;
+    for (int r = 0; r < n; ++r) c += sel[r] < pth ? 1 : 0;
+    if (c) b.order[I2(pth + c, s)] = mine[np];
+  }
+  for (int r = lane; r < n; r += SEL_LANES) {
+    int c = 0;
+    for (int q = 0; q < n; ++q) c += sel[q] < sel[r] ? 1 : 0;
+    b.order[I2(sel[r] + 1 + c, s)] = (uint16_t)(cur + r);
+  }
+}
+
 template <int NL, bool COMP, int NT>
 __device__ void refine_solve_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int round, EASmem<NL * NL + 1, COMP, NT>& sm, int tid, int64_t g) {
   constexpr int D = NL * NL + 1;
@@ -384,15 +459,23 @@ __device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
 // (segment, reversed) pieces.  Points are read from the theta-ordered arrays on demand.
 struct Seg { int16_t track, lo, hi; int8_t par; double len; };
 
+// Optional shared-memory copy of one source's tracks ([p][track] planes), used for small batches:
+// the stitching logic is a chain of dependent reads, ~20x faster from shared memory than from L2.
+struct TrackStage { const double* re; const double* im; const uint8_t* f; const double* th; };
+
 struct Tracks {
-  const ExtCfg& cfg; const ExtBuf& b; int64_t s;
+  const ExtCfg& cfg; const ExtBuf& b; int64_t s; const TrackStage* st;
   __device__ __forceinline__ cd pt(int track, int p) const {
+    if (st) return mk(st->re[p * cfg.D + track], st->im[p * cfg.D + track]);
     return mk(b.sre[(((int64_t)p * cfg.D + track) * cfg.S + s)], b.sim[(((int64_t)p * cfg.D + track) * cfg.S + s)]);
   }
   __device__ __forceinline__ double th(int p) const {
-    return b.vth ? b.theta[(int64_t)b.order[(int64_t)p * cfg.S + s] * cfg.S + s] : 0.0;
+    if (!b.vth) return 0.0;
+    if (st) return st->th[p];
+    return b.theta[(int64_t)b.order[(int64_t)p * cfg.S + s] * cfg.S + s];
   }
   __device__ __forceinline__ uint8_t fl(int track, int p) const {
+    if (st) return st->f[p * cfg.D + track];
     return b.sflg[(((int64_t)p * cfg.D + track) * cfg.S + s)];
   }
 };
@@ -496,9 +579,10 @@ struct LdEmit {
 };
 
 template <int D>
-__device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s) {
+__device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s,
+                              const TrackStage* stage = nullptr) {
   if (s >= nsrc(cfg, b)) return;
-  const Tracks T{cfg, b, s};
+  const Tracks T{cfg, b, s, stage};
   const int NP = cfg.NP;
   const double norm = 1.0 / (3.14159265358979323846 * cfg.rho * cfg.rho);
   const int64_t out_idx = b.list ? (int64_t)b.list[s] : s;

@@ -88,7 +88,10 @@ static void ext_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, int64_
     if (NL == 1) limb_walk_single_body(cfg, b, L, s); else limb_walk_body<NLS, 1>(cfg, b, L, sm0, 0, s);
   }
   for (int r = 0; r < NITER; ++r) {
-    for (int64_t s = 0; s < ns; ++s) refine_select_body<D>(cfg, b, r, s);
+    for (int64_t s = 0; s < ns; ++s) {
+      if (s & 1) refine_select_warp_body<D>(cfg, b, r, s, 0);   // odd sources: the small-batch variant (same result)
+      else refine_select_body<D>(cfg, b, r, s);
+    }
     for (int64_t g = 0; g < (int64_t)cfg.nadd * cfg.S; ++g) {
       if (NL == 1) refine_solve_single_body(cfg, b, L, r, g);
       else if (cfg.comp) refine_solve_body<NLS, true, 1>(cfg, b, L, r, sm1, 0, g);
