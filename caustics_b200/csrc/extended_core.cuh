@@ -39,6 +39,7 @@ struct ExtCfg {
   int nl, D, N0, nadd, NP;
   double rho;
   int itmax, comp, ld, n1, n2, VMAX, CMAX;
+  int chains;       // limb walk split into this many independently started chains (small batches)
   int emit;         // 1: k_contours also writes the contour vertex lists (z, theta, contour id) for the host
   double u1;
   int64_t S;        // capacity (stride) of the source axis
@@ -141,6 +142,82 @@ __device__ void limb_walk_body(const ExtCfg& cfg, const ExtBuf& b, const LensCon
     if (active) {
       b.theta[I2(k, s)] = th;
       b.order[I2(k, s)] = (uint16_t)k;
+    }
+  }
+}
+
+// Small batches: the limb walk is a chain of N0 dependent solves per source, pure latency when there
+// are only a few hundred sources.  It is cut into cfg.chains chains that start cold and run
+// concurrently (thread per (chain, source)); align_chains_body then relabels each chain's roots so
+// that row i continues row i of the previous chain's last point -- greedy nearest neighbour, the same
+// rule the reference applies along the whole limb (utils.py:15-40) -- which restores the continuity
+// along rows that the sequential warm start provides and the refinement step relies on.
+template <int NL, int NT>
+__device__ void limb_walk_chain_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,
+                                     EASmem<NL * NL + 1, false, NT>& sm, int tid, int64_t g) {
+  const int c = (int)(g / cfg.S);
+  const int64_t s = g - (int64_t)c * cfg.S;
+  const int len = (cfg.N0 + cfg.chains - 1) / cfg.chains;
+  const int k0 = c * len, k1 = (k0 + len < cfg.N0) ? k0 + len : cfg.N0;
+  const bool active = c < cfg.chains && s < nsrc(cfg, b);
+  const cd w0 = active ? source_centre(cfg, b, L, s) : mk(0.3, 0.2);
+  for (int k = k0; k < k0 + len; ++k) {      // uniform trip count across the warp
+    const bool act = active && k < k1;
+    const double th = theta_init(k < cfg.N0 ? k : cfg.N0 - 1, cfg.N0);
+    const cd w = limb_point(w0, cfg.rho, th);
+    solve_and_store<NL, false, NT>(cfg, b, L, sm, tid, act, w, k > k0, k, s);
+    if (act) {
+      b.theta[I2(k, s)] = th;
+      b.order[I2(k, s)] = (uint16_t)k;
+    }
+  }
+}
+
+template <int D>
+__device__ void align_chains_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
+  if (s >= nsrc(cfg, b)) return;
+  const int len = (cfg.N0 + cfg.chains - 1) / cfg.chains;
+  for (int c = 1; c < cfg.chains; ++c) {
+    const int k0 = c * len, k1 = (k0 + len < cfg.N0) ? k0 + len : cfg.N0;
+    if (k0 >= cfg.N0) break;
+    double pr[D], pi_[D], zr[D], zi[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      pr[j] = b.zre[I3(k0 - 1, j, s)]; pi_[j] = b.zim[I3(k0 - 1, j, s)];
+      zr[j] = b.zre[I3(k0, j, s)]; zi[j] = b.zim[I3(k0, j, s)];
+    }
+    int perm[D];
+    unsigned used = 0;
+    bool ident = true;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double bd = 1e300; int best = -1;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double dx = zr[k] - pr[i], dy = zi[k] - pi_[i];
+        const double d2 = dx * dx + dy * dy;
+        if (!((used >> k) & 1u) && d2 < bd) { bd = d2; best = k; }
+      }
+      if (best < 0) {
+#pragma unroll
+        for (int k = D - 1; k >= 0; --k) if (!((used >> k) & 1u)) best = k;
+      }
+      used |= 1u << best;
+      perm[i] = best;
+      ident = ident && best == i;
+    }
+    if (ident) continue;
+    for (int k = k0; k < k1; ++k) {
+      double cr[D], ci[D]; uint8_t cf[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) { cr[j] = b.zre[I3(k, j, s)]; ci[j] = b.zim[I3(k, j, s)]; cf[j] = b.flg[I3(k, j, s)]; }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double vr = 0, vi = 0; uint8_t vf = 0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) if (j == perm[i]) { vr = cr[j]; vi = ci[j]; vf = cf[j]; }
+        b.zre[I3(k, i, s)] = vr; b.zim[I3(k, i, s)] = vi; b.flg[I3(k, i, s)] = vf;
+      }
     }
   }
 }

@@ -72,6 +72,7 @@ inline int make_cfg(int64_t S, double rho, int nlenses, int npts_limb, int limb_
   c.CMAX = c.D + 3;
   c.VMAX = c.D * c.NP + c.CMAX;
   c.S = S > 0 ? S : 1;
+  c.chains = 1;
   *out = c;
   return CAUSTICS_OK;
 }
