@@ -34,20 +34,26 @@ enum : int { EA_INIT_REFERENCE = 0, EA_INIT_BINI = 1 };
 
 // Reciprocal used inside the Aberth sum  S = sum_i 1/(z_j - z_i).  S only steers the iteration: the
 // fixed point of z <- z - h/(hd - h S) is h(z) = 0 whatever S is, and the stopping test looks at
-// h alone, so S needs far less than double accuracy (CB200_ABERTH_MODE >= 1: one Newton step on the
-// 20-bit hardware seed, ~1e-12 relative).
+// h alone, so S needs far less than double accuracy.  CB200_ABERTH_MODE 0: full-accuracy reciprocal;
+// 1: one Newton step on the 20-bit hardware seed (~1e-12 relative); 3 (default): the seed alone
+// (~1e-6 relative in each term of S).  Measured on C2 / random degree-10 batches: converged roots
+// identical to 2e-15, mean sweep count 15.5103 vs 15.5107, 7 % less kernel time than mode 1.
 #ifndef CB200_STRAIGHT_LINE
 #define CB200_STRAIGHT_LINE 1
 #endif
 #ifndef CB200_ABERTH_MODE
-#define CB200_ABERTH_MODE 1
+#define CB200_ABERTH_MODE 3
 #endif
 __device__ __forceinline__ double rcp_aberth(double x) {
 #if CB200_ABERTH_MODE >= 1 && !defined(CB200_HOSTSIM)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if CB200_ABERTH_MODE == 3
+  return y;   // hardware seed only (~1e-6 relative)
+#else
   const double e = fma(-x, y, 1.0);
   return fma(y, e, y);
+#endif
 #else
   return rcp_fast(x);
 #endif
