@@ -34,26 +34,27 @@ enum : int { EA_INIT_REFERENCE = 0, EA_INIT_BINI = 1 };
 
 // Reciprocal used inside the Aberth sum  S = sum_i 1/(z_j - z_i).  S only steers the iteration: the
 // fixed point of z <- z - h/(hd - h S) is h(z) = 0 whatever S is, and the stopping test looks at
-// h alone, so S needs far less than double accuracy.  CB200_ABERTH_MODE 0: full-accuracy reciprocal;
-// 1: one Newton step on the 20-bit hardware seed (~1e-12 relative); 3 (default): the seed alone
-// (~1e-6 relative in each term of S).  Measured on C2 / random degree-10 batches: converged roots
-// identical to 2e-15, mean sweep count 15.5103 vs 15.5107, 7 % less kernel time than mode 1.
+// h alone, so S needs far less than double accuracy: one Newton step on the 20-bit hardware seed
+// (~1e-12 relative) reproduces the reference's path (same sweep counts, same root order).  With the
+// seed alone (~1e-6 relative per term, `fast`) the converged roots are still identical to 2e-15 and
+// the kernel is 7 % faster, but ~5 % of random polynomials take one sweep more or fewer and a root
+// pair occasionally swaps labels -- so `fast` is used only where the caller has already given up the
+// reference's root order (CAUSTICS_FLAG_INIT_BINI, and the order-independent magnification sums).
 #ifndef CB200_STRAIGHT_LINE
 #define CB200_STRAIGHT_LINE 1
 #endif
 #ifndef CB200_ABERTH_MODE
-#define CB200_ABERTH_MODE 3
+#define CB200_ABERTH_MODE 1
 #endif
-__device__ __forceinline__ double rcp_aberth(double x) {
+__device__ __forceinline__ double rcp_aberth(double x, bool fast) {
 #if CB200_ABERTH_MODE >= 1 && !defined(CB200_HOSTSIM)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#if CB200_ABERTH_MODE == 3
-  return y;   // hardware seed only (~1e-6 relative)
-#else
-  const double e = fma(-x, y, 1.0);
-  return fma(y, e, y);
-#endif
+  if (!fast) {   // warp-uniform
+    const double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+  }
+  return y;
 #else
   return rcp_fast(x);
 #endif
@@ -252,7 +253,8 @@ __device__ __forceinline__ void horner_plain(const cd (&p)[DEG + 1], const ALPHA
 // only confirms convergence.  MODE as in horner_plain.
 template <int DEG, int MODE, int NT, class ALPHA>
 __device__ __forceinline__ void ea_step_plain(const cd (&p)[DEG + 1], const ALPHA& al,
-                                              double* zre, double* zim, int j, bool need, unsigned& c1) {
+                                              double* zre, double* zim, int j, bool need, unsigned& c1,
+                                              bool fast) {
   const cd z = mk(zre[j * NT], zim[j * NT]);
   const double az2 = norm2(z);
   const bool rev = MODE == 2 ? az2 > 1.0 : MODE == 1;
@@ -275,7 +277,7 @@ __device__ __forceinline__ void ea_step_plain(const cd (&p)[DEG + 1], const ALPH
   for (int i = 0; i < DEG - 1; ++i) {
     const int ii = i + (i >= j ? 1 : 0);  // skip root j without a branch
     const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
-    const double inv = rcp_aberth(norm2(a));
+    const double inv = rcp_aberth(norm2(a), fast);
     s = mk(fma(a.re, inv, s.re), fma(-a.im, inv, s.im));
   }
   cd num = h, den = hd;
@@ -323,7 +325,7 @@ struct EAResult {
 template <int DEG, bool COMP, int NT, bool STRAIGHT = (CB200_STRAIGHT_LINE != 0)>
 __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASmem<DEG, COMP, NT>& sm,
                                                     int tid, bool active, bool custom_init,
-                                                    int init_mode, int itmax) {
+                                                    int init_mode, int itmax, bool fast = false) {
   constexpr unsigned FULL = (1u << DEG) - 1u;
   double* zre = &sm.zre[0][tid];
   double* zim = &sm.zim[0][tid];
@@ -376,9 +378,9 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
         const bool rv = zre[j * NT] * zre[j * NT] + zim[j * NT] * zim[j * NT] > 1.0;
         const bool all_std = __all_sync(0xffffffffu, !need1 || !rv);
         const bool all_rev = __all_sync(0xffffffffu, !need1 || rv);
-        if (all_std) ea_step_plain<DEG, 0, NT, ALPHA>(p, al, zre, zim, j, need1, c1);
-        else if (all_rev) ea_step_plain<DEG, 1, NT, ALPHA>(p, al, zre, zim, j, need1, c1);
-        else ea_step_plain<DEG, 2, NT, ALPHA>(p, al, zre, zim, j, need1, c1);
+        if (all_std) ea_step_plain<DEG, 0, NT, ALPHA>(p, al, zre, zim, j, need1, c1, fast);
+        else if (all_rev) ea_step_plain<DEG, 1, NT, ALPHA>(p, al, zre, zim, j, need1, c1, fast);
+        else ea_step_plain<DEG, 2, NT, ALPHA>(p, al, zre, zim, j, need1, c1, fast);
         continue;
       }
 
@@ -447,13 +449,13 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
             const cd a = z - mk(zre[i0 * NT], zim[i0 * NT]);
             const cd b = z - mk(zre[i1 * NT], zim[i1 * NT]);
             const cd ab = a * b, apb = a + b;
-            const double inv = rcp_aberth(norm2(ab));
+            const double inv = rcp_aberth(norm2(ab), fast);
             s = s + mk((apb.re * ab.re + apb.im * ab.im) * inv, (apb.im * ab.re - apb.re * ab.im) * inv);
           }
           if ((DEG - 1) & 1) {
             const int ii = DEG - 2 + (DEG - 2 >= j ? 1 : 0);
             const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
-            const double inv = rcp_aberth(norm2(a));
+            const double inv = rcp_aberth(norm2(a), fast);
             s = s + mk(a.re * inv, -a.im * inv);
           }
 #else
@@ -461,7 +463,7 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
           for (int i = 0; i < DEG - 1; ++i) {
             const int ii = i + (i >= j ? 1 : 0);  // skip root j without a branch
             const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
-            const double inv = rcp_aberth(norm2(a));
+            const double inv = rcp_aberth(norm2(a), fast);
             s = s + mk(a.re * inv, -a.im * inv);
           }
 #endif

@@ -924,7 +924,7 @@ __device__ void gate_body(const cb200_d2* __restrict__ w_in, double* __restrict_
   cd p[D + 1];
   lens_poly<2>(L, w, p);
   ea_normalise<D>(p);
-  ea_solve_thread<D, COMP, NT>(p, sm, tid, active, false, EA_INIT_BINI, itmax);   // order-independent sums
+  ea_solve_thread<D, COMP, NT>(p, sm, tid, active, false, EA_INIT_BINI, itmax, true);   // order-independent sums
   if (!active) return;
   const double a = L.r[0].re, e1 = L.eps[0], e2 = L.eps[1];
   const double rr = rho + 1e-3;  // rho + rho_min

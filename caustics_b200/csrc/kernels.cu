@@ -58,7 +58,8 @@ ea_kernel(const double2* __restrict__ coeffs, const double2* __restrict__ roots_
 #pragma unroll
     for (int k = 0; k <= DEG; ++k) p[k] = mk(k == 0 ? -1.0 : (k == DEG ? 1.0 : 0.0), 0.0);
   }
-  const EAResult r = ea_solve_thread<DEG, COMP, NTK>(p, sm, tid, active, custom_init != 0, init_mode, itmax);
+  const EAResult r = ea_solve_thread<DEG, COMP, NTK>(p, sm, tid, active, custom_init != 0, init_mode, itmax,
+                                                     init_mode == EA_INIT_BINI);
   if (active) {
     double2* dst = roots + idx * DEG;
 #pragma unroll
@@ -174,7 +175,8 @@ ps_kernel(const double2* __restrict__ w_in, GridSpec g, const double2* __restric
       }
     }
   }
-  ea_solve_thread<DEG, COMP, NT>(p, sm, tid, active, MODE == PS_IMAGES && custom_init != 0, init_mode, itmax);
+  ea_solve_thread<DEG, COMP, NT>(p, sm, tid, active, MODE == PS_IMAGES && custom_init != 0, init_mode, itmax,
+                                 init_mode == EA_INIT_BINI);
   if (!active) return;
   double mu = 0.0;
   int cnt = 0;
