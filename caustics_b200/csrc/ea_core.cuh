@@ -46,11 +46,12 @@ enum : int { EA_INIT_REFERENCE = 0, EA_INIT_BINI = 1 };
 #ifndef CB200_ABERTH_MODE
 #define CB200_ABERTH_MODE 1
 #endif
-__device__ __forceinline__ double rcp_aberth(double x, bool fast) {
+template <bool FAST>
+__device__ __forceinline__ double rcp_aberth(double x) {
 #if CB200_ABERTH_MODE >= 1 && !defined(CB200_HOSTSIM)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  if (!fast) {   // warp-uniform
+  if (!FAST) {
     const double e = fma(-x, y, 1.0);
     y = fma(y, e, y);
   }
@@ -251,10 +252,9 @@ __device__ __forceinline__ void horner_plain(const cd (&p)[DEG + 1], const ALPHA
 // convergence test separated them).  Lanes that do not need the root (already converged) execute the
 // arithmetic on their converged value and commit nothing; so does the one evaluation per root that
 // only confirms convergence.  MODE as in horner_plain.
-template <int DEG, int MODE, int NT, class ALPHA>
+template <int DEG, int MODE, int NT, class ALPHA, bool FAST>
 __device__ __forceinline__ void ea_step_plain(const cd (&p)[DEG + 1], const ALPHA& al,
-                                              double* zre, double* zim, int j, bool need, unsigned& c1,
-                                              bool fast) {
+                                              double* zre, double* zim, int j, bool need, unsigned& c1) {
   const cd z = mk(zre[j * NT], zim[j * NT]);
   const double az2 = norm2(z);
   const bool rev = MODE == 2 ? az2 > 1.0 : MODE == 1;
@@ -277,7 +277,7 @@ __device__ __forceinline__ void ea_step_plain(const cd (&p)[DEG + 1], const ALPH
   for (int i = 0; i < DEG - 1; ++i) {
     const int ii = i + (i >= j ? 1 : 0);  // skip root j without a branch
     const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
-    const double inv = rcp_aberth(norm2(a), fast);
+    const double inv = rcp_aberth<FAST>(norm2(a));
     s = mk(fma(a.re, inv, s.re), fma(-a.im, inv, s.im));
   }
   cd num = h, den = hd;
@@ -378,9 +378,15 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
         const bool rv = zre[j * NT] * zre[j * NT] + zim[j * NT] * zim[j * NT] > 1.0;
         const bool all_std = __all_sync(0xffffffffu, !need1 || !rv);
         const bool all_rev = __all_sync(0xffffffffu, !need1 || rv);
-        if (all_std) ea_step_plain<DEG, 0, NT, ALPHA>(p, al, zre, zim, j, need1, c1, fast);
-        else if (all_rev) ea_step_plain<DEG, 1, NT, ALPHA>(p, al, zre, zim, j, need1, c1, fast);
-        else ea_step_plain<DEG, 2, NT, ALPHA>(p, al, zre, zim, j, need1, c1, fast);
+        if (fast) {
+          if (all_std) ea_step_plain<DEG, 0, NT, ALPHA, true>(p, al, zre, zim, j, need1, c1);
+          else if (all_rev) ea_step_plain<DEG, 1, NT, ALPHA, true>(p, al, zre, zim, j, need1, c1);
+          else ea_step_plain<DEG, 2, NT, ALPHA, true>(p, al, zre, zim, j, need1, c1);
+        } else {
+          if (all_std) ea_step_plain<DEG, 0, NT, ALPHA, false>(p, al, zre, zim, j, need1, c1);
+          else if (all_rev) ea_step_plain<DEG, 1, NT, ALPHA, false>(p, al, zre, zim, j, need1, c1);
+          else ea_step_plain<DEG, 2, NT, ALPHA, false>(p, al, zre, zim, j, need1, c1);
+        }
         continue;
       }
 
@@ -449,13 +455,13 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
             const cd a = z - mk(zre[i0 * NT], zim[i0 * NT]);
             const cd b = z - mk(zre[i1 * NT], zim[i1 * NT]);
             const cd ab = a * b, apb = a + b;
-            const double inv = rcp_aberth(norm2(ab), fast);
+            const double inv = rcp_aberth<false>(norm2(ab));
             s = s + mk((apb.re * ab.re + apb.im * ab.im) * inv, (apb.im * ab.re - apb.re * ab.im) * inv);
           }
           if ((DEG - 1) & 1) {
             const int ii = DEG - 2 + (DEG - 2 >= j ? 1 : 0);
             const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
-            const double inv = rcp_aberth(norm2(a), fast);
+            const double inv = rcp_aberth<false>(norm2(a));
             s = s + mk(a.re * inv, -a.im * inv);
           }
 #else
@@ -463,7 +469,7 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
           for (int i = 0; i < DEG - 1; ++i) {
             const int ii = i + (i >= j ? 1 : 0);  // skip root j without a branch
             const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
-            const double inv = rcp_aberth(norm2(a), fast);
+            const double inv = rcp_aberth<false>(norm2(a));
             s = s + mk(a.re * inv, -a.im * inv);
           }
 #endif
