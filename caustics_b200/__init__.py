@@ -7,9 +7,9 @@ The compute lives in hand-written CUDA kernels behind the C ABI of include/caust
 from .primitive import poly_roots, ehrlich_aberth, roots_jvp
 from .point_source import (mag_point_source, lens_eq, lens_eq_det_jac, lens_params,
                            critical_and_caustic_curves)
-from .extended_source import mag_extended_source, mag
+from .extended_source import mag_extended_source, mag, mag_gate
 
 __all__ = ["poly_roots", "ehrlich_aberth", "roots_jvp", "mag_point_source", "lens_eq",
            "lens_eq_det_jac", "lens_params", "mag_extended_source", "mag",
-           "critical_and_caustic_curves"]
+           "critical_and_caustic_curves", "mag_gate"]
 __version__ = "0.1.0"

@@ -53,6 +53,7 @@ SIGNATURES = {
     "caustics_mag_point_source_host": (_i, [_vp, _vp, _i64, _LP, _i, _i, _i]),
     "caustics_bench_fp64_peak": (_i, [_vp, _i, _i, _vp]),
     "caustics_bench_fp64_peak3": (_i, [_vp, _i, _i, _vp]),
+    "caustics_mag_gate": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _d, _LP, _d, _i, _i, _vp]),
     "caustics_ext_contour_capacity": (_i, [_i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "caustics_ext_contours": (_i, [_vp, _vp, _i64, _d, _LP, _i, _i, _i, _vp, ctypes.c_size_t,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

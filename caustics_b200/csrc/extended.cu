@@ -317,6 +317,25 @@ int caustics_ext_contours(const void* w, double* mag, int64_t n, double rho, con
   }
 }
 
+int caustics_mag_gate(const void* w, double* mag, uint8_t* used_hexadecapole, int32_t* list, int32_t* count,
+                      int64_t n, double rho, const caustics_lens* lens, double q, int itmax, int compensated,
+                      void* stream) {
+  if (!lens || lens->nlenses != 2 || n < 0 || !(rho > 0.0) || itmax < 0) return CAUSTICS_ERR_BAD_ARG;
+  if (n == 0) return CAUSTICS_OK;
+  if (n > 0x7fffffffLL || !w || !mag || !list || !count) return CAUSTICS_ERR_BAD_ARG;
+  LensConst L;
+  int rc = caustics_internal_lens_const(lens, &L);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(count, 0, 4, st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  if (compensated)
+    k_gate<true><<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>((const double2*)w, mag, used_hexadecapole, list, count, n, L, rho, q, itmax);
+  else
+    k_gate<false><<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>((const double2*)w, mag, used_hexadecapole, list, count, n, L, rho, q, itmax);
+  return cuda_rc(cudaGetLastError());
+}
+
 int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t n, double rho,
                  const caustics_lens* lens, double q, int npts_limb, int limb_darkening, double u1, int npts_ld,
                  int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream) {

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from .point_source import _c_lens, lens_params
 
-__all__ = ["mag_extended_source", "mag"]
+__all__ = ["mag_extended_source", "mag", "mag_gate"]
 
 _MAX_WS_BYTES = 24 << 30      # per-call workspace budget; larger batches are processed in chunks
 
@@ -237,6 +237,28 @@ def mag_extended_source(w0, rho, nlenses=2, npts_limb=150, limb_darkening=False,
                                            ld=(u1, npts_ld) if limb_darkening else None)
     return _run(w0, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax, roots_compensated,
                 False, 0.0, params)
+
+
+def mag_gate(w_points, rho, roots_itmax=2500, roots_compensated=False, **params):
+    """Binary-lens gate of `mag` on its own (lightcurve.py:202-225): returns (mu_hexadecapole, valid)
+    for every point -- the cheap pass a multi-GPU driver runs first to balance the expensive full
+    integrations (caustics_b200.sharding.balanced_order)."""
+    _lib.require_cuda()
+    L = _lib.lib()
+    p, x_cm = lens_params(2, **params)
+    lens = _c_lens(2, x_cm, **p)
+    flat, restore = _to_device(w_points)
+    n = flat.numel()
+    mag_ = torch.empty(n, dtype=torch.float64, device=flat.device)
+    used = torch.empty(n, dtype=torch.uint8, device=flat.device)
+    lst = torch.empty(max(n, 1), dtype=torch.int32, device=flat.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=flat.device)
+    with torch.cuda.device(flat.device):
+        _lib.check(L.caustics_mag_gate(flat.data_ptr(), mag_.data_ptr(), used.data_ptr(), lst.data_ptr(),
+                                       cnt.data_ptr(), n, float(rho), lens, float(params.get("q", 1.0)),
+                                       int(roots_itmax), int(bool(roots_compensated)),
+                                       torch.cuda.current_stream().cuda_stream))
+    return restore(mag_), restore(used.bool())
 
 
 def mag(w_points, rho, nlenses=2, npts_limb=200, limb_darkening=False, u1=0.0, npts_ld=100,

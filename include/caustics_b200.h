@@ -148,6 +148,14 @@ int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t
                  const caustics_lens* lens, double q, int npts_limb, int limb_darkening, double u1, int npts_ld,
                  int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The gate alone (binary lens, lightcurve.py:202-225): hexadecapole magnification of every point in
+ * mag (n), the validity decision in used_hexadecapole (n, optional), and the compacted indices of
+ * the points that FAIL the tests in list (capacity n) with their number in *count (device int32).
+ * Lets a multi-GPU driver balance the expensive full integrations before dealing them out. */
+int caustics_mag_gate(const void* w, double* mag, uint8_t* used_hexadecapole, int32_t* list, int32_t* count,
+                      int64_t n, double rho, const caustics_lens* lens, double q, int itmax, int compensated,
+                      void* stream);
+
 /* Contours of the images of the source limb, for differentiating the uniform-disk magnification on
  * the host side (the implicit-function rule stays in Python, north_star): per source, the vertices
  * of every closed contour in integration order, closing vertex included.  vz (VMAX, n) complex128,

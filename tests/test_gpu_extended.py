@@ -291,3 +291,14 @@ def test_other_geometries_and_radii(cb, hp):
     got, used = cb.mag(w, 5e-3, nlenses=2, npts_limb=200, return_test=True, **hp)
     want, t_want = extended.mag(w, 5e-3, 2, 200, return_test=True, **hp)
     assert (used == t_want).all() and np.allclose(got, want, rtol=1e-4, atol=0)
+
+
+def test_mag_gate_alone(cb, g):
+    """caustics_mag_gate == the decisions and hexadecapole values inside `mag`"""
+    w = g["lc_w"]
+    mu, ok = cb.mag_gate(w, 1e-2, **HP2)
+    full, used = cb.mag(w, 1e-2, nlenses=2, npts_limb=200, return_test=True, **HP2)
+    assert (ok == used).all()
+    assert np.array_equal(mu[used], full[used])
+    want_mu, want_ok = lens.gate(w, 1e-2, HP2["s"], HP2["q"])
+    assert (ok == want_ok).all() and np.allclose(mu, want_mu, rtol=1e-10)
