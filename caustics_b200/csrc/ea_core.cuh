@@ -156,8 +156,19 @@ __device__ __forceinline__ void sort4_desc_abs(double (&p)[4]) {
     p[i] = best;
   }
 }
-// Priest's doubly compensated summation of 4 terms, horner.h:190-208
+// Priest's doubly compensated summation of 4 terms, horner.h:190-208.
+// CB200_PRIEST = 0 replaces it by the plain sum ((p0 + p1) + (p2 + p3)): the four terms are the
+// rounding errors of ONE Horner step, and what consumes their sum is `e = e*x + sum` in ordinary
+// double arithmetic, which commits a relative 2^-53 error of its own -- summing the terms more
+// accurately than that cannot change h + e.  The sorted, doubly compensated form costs ~35 FP64
+// instructions against 3 and is more than half of the reference's compensated Horner step.
+#ifndef CB200_PRIEST
+#define CB200_PRIEST 0
+#endif
 __device__ __forceinline__ double priest_sum4(double (&p)[4]) {
+#if !CB200_PRIEST
+  return __dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3]));
+#endif
   sort4_desc_abs(p);
   double s = p[0], c = 0.0;
 #pragma unroll
