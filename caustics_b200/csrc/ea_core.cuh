@@ -375,16 +375,26 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
   EAResult res;
   res.sweeps = 0;
   res.converged = !active;
+  // Compensated kernels run in two stages: plain sweeps until every lane of the warp has all roots
+  // through the plain stopping test, then the polishing sweeps.  (The reference lets a root start
+  // polishing while others are still in the plain phase; polishing a root depends on the others only
+  // through the Aberth sum, which steers but does not set the fixed point, so the polished roots are
+  // the same -- golden vectors: identical to 5e-15 -- while the warp never executes the plain and
+  // the compensated evaluation for the same root, and the plain stage runs the straight-line step.)
+  bool stage2 = false;
+  int s1 = 0, it2 = 0;   // own plain sweeps; polishing sweeps since the warp switched
   int it = 0;
   for (; it < itmax; ++it) {
+    if (COMP && !stage2 && __all_sync(0xffffffffu, c1 == FULL)) stage2 = true;
     const unsigned done_bits = COMP ? c2 : c1;
     if (__all_sync(0xffffffffu, done_bits == FULL)) break;
+    if (COMP && stage2) ++it2;
 #pragma unroll 1
     for (int j = 0; j < DEG; ++j) {
       const bool need1 = !((c1 >> j) & 1u);
-      const bool need2 = COMP && !need1 && !((c2 >> j) & 1u);
+      const bool need2 = COMP && stage2 && !need1 && !((c2 >> j) & 1u);
       if (!__any_sync(0xffffffffu, need1 || need2)) continue;
-      if (STRAIGHT && !COMP) {
+      if (STRAIGHT && (!COMP || !stage2)) {
         // warp-uniform choice of the evaluation variant, then one straight-line step
         const bool rv = zre[j * NT] * zre[j * NT] + zim[j * NT] * zim[j * NT] > 1.0;
         const bool all_std = __all_sync(0xffffffffu, !need1 || !rv);
@@ -514,10 +524,16 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
         }
       }
     }
-    const unsigned now = COMP ? c2 : c1;
     if (active && !res.converged) {
-      res.sweeps = it + 1;
-      if (now == FULL) res.converged = true;
+      if (!COMP) {
+        res.sweeps = it + 1;
+        if (c1 == FULL) res.converged = true;
+      } else {
+        // own plain sweeps + polishing sweeps: independent of the other lanes of the warp
+        if (s1 == 0 && c1 == FULL) s1 = it + 1;
+        res.sweeps = (s1 ? s1 : it + 1) + it2;
+        if (c2 == FULL) res.converged = true;
+      }
     }
   }
   return res;

@@ -55,7 +55,10 @@ def test_roots_vs_reference_golden(cb, ea_golden, name, comp):
         assert np.abs(got - want).max() < 1e-11    # same root ORDER as the reference, too
     # sweep counts follow the reference's iteration path
     _, psw, _ = solver.port_solve(np.ascontiguousarray(c[:, ::-1]), compensated=comp, return_stats=True)
-    assert (sweeps == psw).mean() > (0.8 if comp else 0.95)
+    if not comp:
+        assert (sweeps == psw).mean() > 0.95
+    else:   # two-stage schedule (plain sweeps, then polishing sweeps): a few sweeps more than interleaved
+        assert sweeps.mean() < psw.mean() + 4
 
 
 @pytest.mark.parametrize("deg", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 16])

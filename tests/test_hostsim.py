@@ -48,8 +48,10 @@ def test_device_solver_logic_vs_golden(hs, ea_golden, name, comp):
     want = ea_golden[name + ("_roots_comp" if comp else "_roots_plain")]
     _, psw, _ = solver.port_solve(c, compensated=comp, return_stats=True)
     # reference-compatible init: the iteration path is the reference's -> same order, same sweeps
-    if name != "fixture":  # all-real polynomials: see the note in ea_core.cuh (Bini guesses there)
-        assert (np.abs(sw) == psw).mean() > (0.8 if comp else 0.97)  # comp exit test is ulp-sensitive
+    if name != "fixture" and not comp:  # all-real polynomials: see the note in ea_core.cuh (Bini guesses there)
+        assert (np.abs(sw) == psw).mean() > 0.97
+    if comp and name != "fixture":  # two-stage schedule: plain sweeps, then polishing sweeps (never fewer than the reference's)
+        assert (np.abs(sw) >= psw - 1).mean() > 0.97 and np.abs(sw).mean() < psw.mean() + 4
     assert (sw > 0).all()
     if comp:
         assert set_distance(got, ea_golden[name + "_roots_comp"]).max() < 1e-12
