@@ -60,6 +60,11 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
   return fma(h, e, y);
 }
 #endif
+// sqrt(x) for x >= 0 (exact zero allowed), branch-free
+__device__ __forceinline__ double sqrt_fast(double x) {
+  const double r = rsqrt_fast(x);
+  return x > 0.0 ? x * r : 0.0;
+}
 __device__ __forceinline__ cd crecip(cd a) {
   double inv = rcp_fast(norm2(a));
   return mk(a.re * inv, -a.im * inv);

@@ -199,10 +199,10 @@ __device__ __forceinline__ cd comp_step(cd acc, cd x, cd add, cd& err, double (&
   // error terms: (e0, e2), (-e1, e3), (er, ei), (fr, fi)
   double re4[4] = {e0, -e1, er, fr};
   double im4[4] = {e2, e3, ei, fi};
-  ab[0] = sqrt(e0 * e0 + e2 * e2);
-  ab[1] = sqrt(e1 * e1 + e3 * e3);
-  ab[2] = sqrt(er * er + ei * ei);
-  ab[3] = sqrt(fr * fr + fi * fi);
+  ab[0] = sqrt_fast(e0 * e0 + e2 * e2);
+  ab[1] = sqrt_fast(e1 * e1 + e3 * e3);
+  ab[2] = sqrt_fast(er * er + ei * ei);
+  ab[3] = sqrt_fast(fr * fr + fi * fi);
   err = mk(priest_sum4(re4), priest_sum4(im4));
   return mk(vr, vi);
 }
