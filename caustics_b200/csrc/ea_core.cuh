@@ -5,18 +5,29 @@
 // reversed-polynomial evaluation for |z| > 1, the same stopping tests and -- when `compensated` --
 // the same second polishing phase built on error-free transformations with a running error bound.
 // What is B200-specific is the execution shape:
-//   * coefficients and |coefficients| live in registers (Horner loops fully unrolled, static
-//     register indices); the roots live in shared memory in [root][thread] planes so that the
-//     rolled loop over roots can index them dynamically without bank conflicts;
+//   * coefficients live in registers (Horner loops fully unrolled, static register indices); the
+//     roots and the |coefficients| live in shared memory in [index][thread] planes so that the rolled
+//     loop over roots can index them dynamically without bank conflicts and the kernel fits 5 CTAs
+//     of 128 threads per SM at 96 registers;
 //   * the standard and the reversed evaluation are ONE instruction stream: the branch of the
 //     reference (|z| > 1) becomes per-lane selects of the evaluation point and the coefficient
-//     order, so a warp never executes both paths;
+//     order (select-free variants when a warp vote finds the lanes agree), so a warp never executes
+//     both paths;
+//   * a cold-start root step is one straight-line basic block (prologue, Horner, Aberth sum,
+//     correction, predicated store); warm starts use a branchy step that skips the Aberth sum when an
+//     evaluation only confirms convergence;
 //   * convergence is a per-lane bit mask; a (sweep, root) step is skipped when a warp vote says no
 //     lane needs it, and the sweep loop ends on a warp vote (the reference's per-polynomial loop
 //     exit, lifted to the warp).  Each lane still stops updating a root exactly when the reference
-//     would, so the iteration path of every polynomial is the reference's.
+//     would, so in the default mode the iteration path of every polynomial is the reference's
+//     (same sweep counts, same root order); results do not depend on the batch layout;
 //   * coefficients are normalised by a power of two on load (exact, roots unchanged) so that |.|^2
-//     comparisons can replace hypot() everywhere.
+//     comparisons can replace hypot() everywhere; reciprocals / square roots are branch-free
+//     (hardware seed + Newton);
+//   * compensated kernels run the plain sweeps first and the polishing sweeps afterwards, with the
+//     per-step error terms summed plainly (see priest_sum4) -- same polished roots as the reference.
+// The FP64 pipe is the bound; a DFMA with three distinct register operands issues at 69 % of the
+// constant-operand rate on B200 and the kernel sits at that ceiling.
 #pragma once
 #include "cplx.cuh"
 
@@ -468,32 +479,13 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
         if (upd) {
           // Aberth sum over the other roots (:31-40) and the (reversed) correction (:41,:56-57)
           cd s = mk(0, 0);
-#if CB200_ABERTH_MODE == 2
-          // two terms per reciprocal: 1/a + 1/b = (a + b) conj(ab) / |ab|^2
-#pragma unroll
-          for (int i = 0; i + 1 < DEG - 1; i += 2) {
-            const int i0 = i + (i >= j ? 1 : 0), i1 = i + 1 + (i + 1 >= j ? 1 : 0);
-            const cd a = z - mk(zre[i0 * NT], zim[i0 * NT]);
-            const cd b = z - mk(zre[i1 * NT], zim[i1 * NT]);
-            const cd ab = a * b, apb = a + b;
-            const double inv = rcp_aberth<false>(norm2(ab));
-            s = s + mk((apb.re * ab.re + apb.im * ab.im) * inv, (apb.im * ab.re - apb.re * ab.im) * inv);
-          }
-          if ((DEG - 1) & 1) {
-            const int ii = DEG - 2 + (DEG - 2 >= j ? 1 : 0);
-            const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
-            const double inv = rcp_aberth<false>(norm2(a));
-            s = s + mk(a.re * inv, -a.im * inv);
-          }
-#else
 #pragma unroll
           for (int i = 0; i < DEG - 1; ++i) {
             const int ii = i + (i >= j ? 1 : 0);  // skip root j without a branch
             const cd a = z - mk(zre[ii * NT], zim[ii * NT]);
             const double inv = rcp_aberth<false>(norm2(a));
-            s = s + mk(a.re * inv, -a.im * inv);
+            s = mk(fma(a.re, inv, s.re), fma(-a.im, inv, s.im));
           }
-#endif
           cd num = h, den = hd;
           if (rev) {
             const cd z2 = z * z;
