@@ -24,6 +24,18 @@ class Lens(ctypes.Structure):
                 ("r3_im", ctypes.c_double), ("x_cm", ctypes.c_double)]
 
 
+class MagPSDescriptor(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int64), ("lens", Lens), ("itmax", ctypes.c_int32), ("compensated", ctypes.c_uint8),
+                ("flags", ctypes.c_uint8), ("reserved", ctypes.c_uint8 * 2)]
+
+
+class MagExtDescriptor(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int64), ("lens", Lens), ("rho", ctypes.c_double), ("u1", ctypes.c_double),
+                ("q", ctypes.c_double), ("workspace_bytes", ctypes.c_uint64), ("npts_limb", ctypes.c_int32),
+                ("npts_ld", ctypes.c_int32), ("itmax", ctypes.c_int32), ("limb_darkening", ctypes.c_uint8),
+                ("compensated", ctypes.c_uint8), ("gate", ctypes.c_uint8), ("reserved", ctypes.c_uint8)]
+
+
 class EADescriptor(ctypes.Structure):
     _fields_ = [("size", ctypes.c_int64), ("deg", ctypes.c_int32), ("itmax", ctypes.c_int32),
                 ("compensated", ctypes.c_uint8), ("custom_init", ctypes.c_uint8),
@@ -45,6 +57,8 @@ SIGNATURES = {
     "caustics_ea_solve_host": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i]),
     "caustics_release_workspace": (None, []),
     "caustics_ea_xla": (None, [_vp, ctypes.POINTER(_vp), ctypes.c_char_p, ctypes.c_size_t]),
+    "caustics_mag_ps_xla": (None, [_vp, ctypes.POINTER(_vp), ctypes.c_char_p, ctypes.c_size_t]),
+    "caustics_mag_ext_xla": (None, [_vp, ctypes.POINTER(_vp), ctypes.c_char_p, ctypes.c_size_t]),
     "caustics_last_xla_error": (_i, []),
     "caustics_ea_make_descriptor": (ctypes.c_size_t, [ctypes.POINTER(EADescriptor), _i64, _i, _i, _i, _i, _i]),
     "caustics_images_point_source": (_i, [_vp, _vp, _vp, _vp, _i64, _LP, _i, _i, _i, _i, _vp]),

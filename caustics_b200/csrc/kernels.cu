@@ -449,6 +449,37 @@ void caustics_ea_xla(void* stream, void** buffers, const char* opaque, size_t op
                                        d.compensated, d.custom_init, d.flags, stream);
 }
 
+static_assert(sizeof(caustics_mag_ps_descriptor) == 72 && sizeof(caustics_mag_ext_descriptor) == 112 &&
+                  sizeof(caustics_ea_descriptor) == 24 && sizeof(caustics_lens) == 56,
+              "descriptor layouts are part of the ABI");
+
+void caustics_mag_ps_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len) {
+  if (opaque_len != sizeof(caustics_mag_ps_descriptor) || !opaque || !buffers) {
+    g_last_xla_error = CAUSTICS_ERR_BAD_DESCRIPTOR;
+    return;
+  }
+  caustics_mag_ps_descriptor d;
+  memcpy(&d, opaque, sizeof(d));
+  g_last_xla_error = caustics_mag_point_source(buffers[0], (double*)buffers[1], nullptr, d.n, &d.lens, d.itmax,
+                                               d.compensated, d.flags, stream);
+}
+
+void caustics_mag_ext_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len) {
+  if (opaque_len != sizeof(caustics_mag_ext_descriptor) || !opaque || !buffers) {
+    g_last_xla_error = CAUSTICS_ERR_BAD_DESCRIPTOR;
+    return;
+  }
+  caustics_mag_ext_descriptor d;
+  memcpy(&d, opaque, sizeof(d));
+  g_last_xla_error =
+      d.gate ? caustics_mag(buffers[0], (double*)buffers[1], nullptr, d.n, d.rho, &d.lens, d.q, d.npts_limb,
+                            d.limb_darkening, d.u1, d.npts_ld, d.itmax, d.compensated, buffers[2],
+                            (size_t)d.workspace_bytes, stream)
+             : caustics_mag_extended_source(buffers[0], (double*)buffers[1], d.n, d.rho, &d.lens, d.npts_limb,
+                                            d.limb_darkening, d.u1, d.npts_ld, d.itmax, d.compensated, buffers[2],
+                                            (size_t)d.workspace_bytes, stream);
+}
+
 int caustics_images_point_source(const void* w, const void* z_init, void* z, uint8_t* mask,
                                  int64_t n, const caustics_lens* lens, int itmax, int compensated,
                                  int custom_init, int flags, void* stream) {

@@ -71,6 +71,33 @@ typedef struct caustics_ea_descriptor {
   int32_t pad;
 } caustics_ea_descriptor;
 
+/* Opaque descriptors of the two magnification custom calls (no reference counterpart: the
+ * reference lowers them to thousands of XLA ops around "gpu_ehrlich_aberth"; same legacy signature). */
+typedef struct caustics_mag_ps_descriptor {
+  int64_t n;
+  caustics_lens lens;
+  int32_t itmax;
+  uint8_t compensated;
+  uint8_t flags;
+  uint8_t reserved[2];
+} caustics_mag_ps_descriptor;
+
+typedef struct caustics_mag_ext_descriptor {
+  int64_t n;
+  caustics_lens lens;
+  double rho;
+  double u1;
+  double q;                 /* user's mass ratio, gate only */
+  uint64_t workspace_bytes; /* size of buffers[2] */
+  int32_t npts_limb;
+  int32_t npts_ld;
+  int32_t itmax;
+  uint8_t limb_darkening;
+  uint8_t compensated;
+  uint8_t gate;             /* 1: lightcurve.py mag (hexadecapole where valid), 0: mag_extended_source */
+  uint8_t reserved;
+} caustics_mag_ext_descriptor;
+
 /* library / device queries (no compute) */
 const char* caustics_version(void);
 int caustics_device_count(void);
@@ -108,6 +135,11 @@ void caustics_release_workspace(void);
  * nothing is launched and the sticky error is readable with caustics_last_xla_error(). */
 void caustics_ea_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len);
 int caustics_last_xla_error(void);
+/* buffers = [w (n) complex128, mag (n) float64]; opaque = caustics_mag_ps_descriptor bytes */
+void caustics_mag_ps_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+/* buffers = [w (n) complex128, mag (n) float64, workspace (descriptor.workspace_bytes, an extra
+ * uint8 result XLA allocates as scratch)]; opaque = caustics_mag_ext_descriptor bytes */
+void caustics_mag_ext_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len);
 /* fills *out; returns sizeof(caustics_ea_descriptor) */
 size_t caustics_ea_make_descriptor(caustics_ea_descriptor* out, int64_t size, int deg, int itmax,
                                    int compensated, int custom_init, int flags);

@@ -33,6 +33,7 @@ def test_struct_layouts(built_lib):
     assert built_lib.caustics_ea_make_descriptor(ctypes.byref(d), 123456789012, 10, 2500, 1, 0, 3) == ctypes.sizeof(d) == 24
     assert (d.size, d.deg, d.itmax, d.compensated, d.custom_init, d.flags) == (123456789012, 10, 2500, 1, 0, 3)
     assert ctypes.sizeof(_lib.Lens) == 56
+    assert ctypes.sizeof(_lib.MagPSDescriptor) == 72 and ctypes.sizeof(_lib.MagExtDescriptor) == 112
 
 
 def test_argument_errors_without_compute(built_lib):
@@ -51,6 +52,11 @@ def test_argument_errors_without_compute(built_lib):
     bufs = (ctypes.c_void_p * 3)()
     L.caustics_ea_xla(None, bufs, b"xx", 2)
     assert L.caustics_last_xla_error() == 3
+    for fn in (L.caustics_mag_ps_xla, L.caustics_mag_ext_xla):
+        L.caustics_ea_xla(None, bufs, bytes(_lib.EADescriptor(deg=5)), 24)     # size 0: clears the sticky error
+        assert L.caustics_last_xla_error() == 0
+        fn(None, bufs, b"xx", 2)
+        assert L.caustics_last_xla_error() == 3
     assert b"degree" in L.caustics_error_string(2)
 
 

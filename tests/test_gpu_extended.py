@@ -302,3 +302,46 @@ def test_mag_gate_alone(cb, g):
     assert np.array_equal(mu[used], full[used])
     want_mu, want_ok = lens.gate(w, 1e-2, HP2["s"], HP2["q"])
     assert (ok == want_ok).all() and np.allclose(mu, want_mu, rtol=1e-10)
+
+
+def test_xla_magnification_entries(cb, g):
+    """caustics_mag_ps_xla / caustics_mag_ext_xla: what an XLA custom call would bind"""
+    import ctypes
+    from caustics_b200 import _lib
+    from caustics_b200.point_source import _c_lens, lens_params
+    L = _lib.lib()
+    p, x_cm = lens_params(2, **HP2)
+    lens = _c_lens(2, x_cm, **p)
+    w = torch.from_numpy(g["b_w_0.01"][:16]).cuda()
+    mag = torch.empty(16, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    d = _lib.MagPSDescriptor(n=16, lens=lens, itmax=2500, compensated=0, flags=0)
+    L.caustics_mag_ps_xla(st, (ctypes.c_void_p * 2)(w.data_ptr(), mag.data_ptr()), bytes(d), ctypes.sizeof(d))
+    assert L.caustics_last_xla_error() == 0
+    assert torch.equal(mag, cb.mag_point_source(w, nlenses=2, **HP2))
+    for gate in (0, 1):
+        nb = L.caustics_ext_workspace_bytes(16, 2, 200, 1, 100)
+        ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        d = _lib.MagExtDescriptor(n=16, lens=lens, rho=1e-2, u1=0.7, q=HP2["q"], workspace_bytes=nb, npts_limb=200,
+                                  npts_ld=100, itmax=2500, limb_darkening=1, compensated=0, gate=gate)
+        L.caustics_mag_ext_xla(st, (ctypes.c_void_p * 3)(w.data_ptr(), mag.data_ptr(), ws.data_ptr()), bytes(d),
+                               ctypes.sizeof(d))
+        assert L.caustics_last_xla_error() == 0
+        fn = cb.mag if gate else cb.mag_extended_source
+        want = fn(w, 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7, npts_ld=100, **HP2)
+        assert torch.equal(mag, torch.as_tensor(want).cuda())
+
+
+def test_small_batch_variants_bitwise(cb, g):
+    """<= 16384 sources run the warp-per-source / shared-memory phase variants, larger batches the
+    thread-per-source ones: same arithmetic, so the same sources give bit-identical magnifications"""
+    w = np.concatenate([g["b_w_0.01"], g["b_w_0.001"]])
+    for ld in (False, True):
+        kw = dict(nlenses=2, npts_limb=200, limb_darkening=ld, u1=0.4, npts_ld=50, **HP2)
+        small = cb.mag_extended_source(w, 1e-2, **kw)
+        big = cb.mag_extended_source(np.tile(w, 16400 // len(w) + 1), 1e-2, **kw)
+        assert len(big) > 16384 and np.array_equal(big[:len(w)], small) and np.array_equal(big[-len(w):], small)
+    wt = g["t_w_0.01"]
+    small = cb.mag_extended_source(wt, 1e-2, nlenses=3, npts_limb=200, **HP3)
+    big = cb.mag_extended_source(np.tile(wt, 16400 // len(wt) + 1), 1e-2, nlenses=3, npts_limb=200, **HP3)
+    assert np.array_equal(big[:len(wt)], small)
