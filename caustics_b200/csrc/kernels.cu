@@ -200,6 +200,43 @@ ps_kernel(const double2* __restrict__ w_in, GridSpec g, const double2* __restric
   }
 }
 
+// _images_point_source_sequential (point_source.py:1711-1759): a path of source positions is a scan --
+// position 0 starts from the default initial estimates, position k from the images of position k-1
+// (custom_init), so row j of the result follows one image along the path.  One thread per path; the
+// roots never leave shared memory between positions.
+template <int NL, bool COMP>
+__global__ void __launch_bounds__(NT)
+ps_seq_kernel(const double2* __restrict__ w_in, double2* __restrict__ z_out, uint8_t* __restrict__ mask_out,
+              int64_t npaths, int64_t n, LensConst L, int itmax) {
+  constexpr int DEG = NL * NL + 1;
+  __shared__ EASmem<DEG, COMP, NT> sm;
+  const int tid = threadIdx.x;
+  const int64_t idx = (int64_t)blockIdx.x * NT + tid;
+  const bool active = idx < npaths;
+  for (int64_t k = 0; k < n; ++k) {
+    cd w = mk(0.3, 0.2);
+    if (active) {
+      const double2 v = __ldg(w_in + idx * n + k);
+      w = mk(v.x + L.x_cm, v.y);
+    }
+    cd p[DEG + 1];
+    lens_poly<NL>(L, w, p);
+    ea_normalise<DEG>(p);
+    ea_solve_thread<DEG, COMP, NT, false>(p, sm, tid, active, k > 0, EA_INIT_REFERENCE, itmax);
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < DEG; ++j) {
+        const cd z = mk(sm.zre[j][tid], sm.zim[j][tid]);
+        bool real_image;
+        double detj;
+        image_eval<NL>(L, z, w, real_image, detj);
+        z_out[(idx * DEG + j) * n + k] = make_double2(z.re, z.im);
+        mask_out[(idx * DEG + j) * n + k] = real_image ? 1 : 0;
+      }
+    }
+  }
+}
+
 int make_lens_const(const caustics_lens* lens, LensConst* out) {
   if (!lens) return CAUSTICS_ERR_BAD_ARG;
   LensConst L;
@@ -494,6 +531,25 @@ int caustics_images_point_source(const void* w, const void* z_init, void* z, uin
   if (L.nlenses == 2)
     return launch_ps<2, PS_IMAGES>((const double2*)w, g, (const double2*)z_init, (double2*)z, mask, nullptr, nullptr, n, L, itmax, compensated, custom_init, flags, st);
   return launch_ps<3, PS_IMAGES>((const double2*)w, g, (const double2*)z_init, (double2*)z, mask, nullptr, nullptr, n, L, itmax, compensated, custom_init, flags, st);
+}
+
+int caustics_images_point_source_sequential(const void* w, void* z, uint8_t* mask, int64_t npaths, int64_t n,
+                                            const caustics_lens* lens, int itmax, int compensated, void* stream) {
+  LensConst L;
+  int rc = make_lens_const(lens, &L);
+  if (rc) return rc;
+  if (npaths < 0 || n < 0 || itmax < 0) return CAUSTICS_ERR_BAD_ARG;
+  if (npaths == 0 || n == 0) return CAUSTICS_OK;
+  if (!w || !z || !mask) return CAUSTICS_ERR_BAD_ARG;
+  const int64_t nblk = (npaths + NT - 1) / NT;
+  if (nblk > 0x7fffffffLL) return CAUSTICS_ERR_BAD_ARG;
+  dim3 grid((unsigned)nblk), block(NT);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CB200_SEQ(NL, COMP) ps_seq_kernel<NL, COMP><<<grid, block, 0, st>>>((const double2*)w, (double2*)z, mask, npaths, n, L, itmax)
+  if (L.nlenses == 2) { if (compensated) CB200_SEQ(2, true); else CB200_SEQ(2, false); }
+  else                { if (compensated) CB200_SEQ(3, true); else CB200_SEQ(3, false); }
+#undef CB200_SEQ
+  return cuda_rc(cudaGetLastError());
 }
 
 int caustics_mag_point_source(const void* w, double* mag, uint8_t* nimages, int64_t n,

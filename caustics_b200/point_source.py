@@ -197,6 +197,35 @@ def _images_point_source(w, nlenses=2, roots_itmax=2500, roots_compensated=False
     return (z, mask) if is_t else (z.numpy(), mask.numpy())
 
 
+def _images_point_source_sequential(w, nlenses=2, roots_itmax=2500, roots_compensated=False, **params):
+    """point_source.py:1711-1759: images along a 1-D path `w` (n,), every position warm-started from the
+    previous one's images, so row j follows one image.  Returns z (deg, n), mask (deg, n).  Leading
+    batch axes are allowed: w (..., n) -> z (..., deg, n); each path is one thread of one launch."""
+    if nlenses not in (2, 3):
+        raise ValueError("`nlenses` has to be 2 or 3.")
+    _lib.require_cuda()
+    is_t = isinstance(w, torch.Tensor)
+    wd = w if is_t else torch.as_tensor(np.asarray(w, dtype=np.complex128))
+    on_dev = wd.is_cuda
+    wd = wd.to(device="cuda" if not on_dev else wd.device, dtype=torch.complex128).resolve_conj().resolve_neg().contiguous()
+    if wd.dim() < 1:
+        raise ValueError("`w` has to be at least one-dimensional (a path of source positions)")
+    n = wd.shape[-1]
+    npaths = wd.numel() // max(n, 1)
+    deg = nlenses**2 + 1
+    z = torch.empty(tuple(wd.shape[:-1]) + (deg, n), dtype=torch.complex128, device=wd.device)
+    mask = torch.empty(z.shape, dtype=torch.uint8, device=wd.device)
+    lens = _c_lens(nlenses, 0.0, **params)
+    with torch.cuda.device(wd.device):
+        _lib.check(_lib.lib().caustics_images_point_source_sequential(
+            wd.data_ptr(), z.data_ptr(), mask.data_ptr(), npaths, n, lens, int(roots_itmax),
+            int(bool(roots_compensated)), torch.cuda.current_stream().cuda_stream))
+    mask = mask.bool()
+    if not on_dev:
+        z, mask = z.cpu(), mask.cpu()
+    return (z, mask) if is_t else (z.numpy(), mask.numpy())
+
+
 def mag_point_source(w, nlenses=2, roots_itmax=2500, roots_compensated=False, flags=0, **params):
     """Point-source magnification at source positions `w` (complex128, any shape); high-level
     parameters s, q[, q3, r3, psi] as in the reference (point_source.py:1762-1830)."""

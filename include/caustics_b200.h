@@ -144,6 +144,13 @@ void caustics_mag_ext_xla(void* stream, void** buffers, const char* opaque, size
 size_t caustics_ea_make_descriptor(caustics_ea_descriptor* out, int64_t size, int deg, int itmax,
                                    int compensated, int custom_init, int flags);
 
+/* _images_point_source_sequential (point_source.py:1711-1759): npaths independent 1-D paths of n
+ * source positions each; position 0 of a path is solved from the default initial estimates, position
+ * k > 0 is warm-started from the images of position k-1, so row j follows one image along the path.
+ * w (npaths, n) complex128 -> z (npaths, deg, n) complex128, mask (npaths, deg, n) uint8. */
+int caustics_images_point_source_sequential(const void* w, void* z, uint8_t* mask, int64_t npaths, int64_t n,
+                                            const caustics_lens* lens, int itmax, int compensated, void* stream);
+
 /* ---- kernel 2: fused point-source images / magnification -----------------------------------
  * w (n) complex128 source positions (the x_cm shift in `lens` is added inside).
  * images: z (deg, n) complex128 with the root axis FIRST like the reference, mask (deg, n) uint8,

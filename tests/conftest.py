@@ -24,6 +24,15 @@ def ps_golden():
 
 
 @pytest.fixture(scope="session")
+def seq_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "seq_golden.npz"))
+
+
+SEQ_PARAMS = {"b": (2, dict(a=0.45, e1=1 / 1.2)),
+              "t": (3, dict(a=0.698, e1=0.02809, e2=0.9687, r3=-0.0197 - 0.95087j))}
+
+
+@pytest.fixture(scope="session")
 def built_lib():
     """Build (if stale) and load the product library."""
     from caustics_b200 import build, _lib

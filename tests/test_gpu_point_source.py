@@ -137,3 +137,28 @@ def test_single_lens_and_grad(cb):
     fd = (cb.mag_point_source(w, nlenses=2, s=0.9 + h, q=0.2).sum() -
           cb.mag_point_source(w, nlenses=2, s=0.9 - h, q=0.2).sum()) / (2 * h)
     assert abs(s.grad.item() - fd.item()) < 1e-4 * max(1.0, abs(fd.item()))
+
+
+@pytest.mark.parametrize("k", ["b", "t"])
+def test_sequential_images(cb, seq_golden, k):
+    """_images_point_source_sequential: warm-started scan along a path; rows follow images like the
+    reference's (same Gauss-Seidel order from the same warm starts)"""
+    from conftest import SEQ_PARAMS
+    from caustics_b200.point_source import _images_point_source_sequential
+    nl, p = SEQ_PARAMS[k]
+    w, zg, mg = seq_golden[f"{k}_w"], seq_golden[f"{k}_z"], seq_golden[f"{k}_mask"]
+    z, m = _images_point_source_sequential(w, nlenses=nl, **p)
+    assert z.shape == zg.shape and np.array_equal(m, mg)
+    # ordered; 1e-9: coefficient rounding x conditioning of the triple-lens polynomial (tests/test_oracle.py)
+    assert np.abs(z - zg)[mg].max() < (1e-12 if k == "b" else 1e-9)
+    for i in range(z.shape[1]):                      # every root as an unordered set
+        assert set_distance(z[:, i][None], zg[:, i][None]).max() < 1e-9
+    # batched paths: each path is independent; compensated agrees
+    wb = torch.from_numpy(np.stack([w, w[::-1].copy(), w + 1e-3])).cuda()
+    zb, mb = _images_point_source_sequential(wb, nlenses=nl, **p)
+    assert zb.shape == (3,) + zg.shape and torch.equal(zb[0].cpu(), torch.from_numpy(z))
+    zc, mc = _images_point_source_sequential(wb, nlenses=nl, roots_compensated=True, **p)
+    assert torch.equal(mc[0].cpu(), torch.from_numpy(mg))
+    assert np.abs(zc[0].cpu().numpy() - zg)[mg].max() < (1e-12 if k == "b" else 1e-9)
+    zo, mo = lens.images_point_source_sequential(w, nl, roots_compensated=True, **p)
+    assert np.array_equal(mo, mg) and np.abs(zc[0].cpu().numpy() - zo)[mo].max() < (1e-12 if k == "b" else 1e-9)
