@@ -8,8 +8,10 @@ from .primitive import poly_roots, ehrlich_aberth, roots_jvp
 from .point_source import (mag_point_source, lens_eq, lens_eq_det_jac, lens_params,
                            critical_and_caustic_curves)
 from .extended_source import mag_extended_source, mag, mag_gate
+from .lightcurve import AnnualParallaxTrajectory, marginalized_log_likelihood, light_curve_log_likelihood
 
 __all__ = ["poly_roots", "ehrlich_aberth", "roots_jvp", "mag_point_source", "lens_eq",
            "lens_eq_det_jac", "lens_params", "mag_extended_source", "mag",
-           "critical_and_caustic_curves", "mag_gate"]
+           "critical_and_caustic_curves", "mag_gate", "AnnualParallaxTrajectory",
+           "marginalized_log_likelihood", "light_curve_log_likelihood"]
 __version__ = "0.1.0"

@@ -63,6 +63,8 @@ SIGNATURES = {
     "caustics_ea_make_descriptor": (ctypes.c_size_t, [ctypes.POINTER(EADescriptor), _i64, _i, _i, _i, _i, _i]),
     "caustics_images_point_source": (_i, [_vp, _vp, _vp, _vp, _i64, _LP, _i, _i, _i, _i, _vp]),
     "caustics_images_point_source_sequential": (_i, [_vp, _vp, _vp, _i64, _i64, _LP, _i, _i, _vp]),
+    "caustics_trajectory": (_i, [_vp, _vp, _i64, _d, _d, _d, _d, _d, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "caustics_marginalized_log_likelihood": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "caustics_mag_point_source": (_i, [_vp, _vp, _vp, _i64, _LP, _i, _i, _i, _vp]),
     "caustics_mag_point_source_grid": (_i, [_d, _d, _d, _d, _i64, _i64, _i64, _vp, _LP, _i, _i, _i, _vp]),
     "caustics_mag_point_source_host": (_i, [_vp, _vp, _i64, _LP, _i, _i, _i]),

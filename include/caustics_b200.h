@@ -20,6 +20,8 @@
  *   caustics_mag_point_source     src/caustics/point_source.py:1762-1830 mag_point_source
  *   caustics_mag_extended_source  src/caustics/extended_source.py:741-904 mag_extended_source
  *   caustics_mag                  src/caustics/lightcurve.py:99-254 mag
+ *   caustics_trajectory           src/caustics/trajectory.py:106-158 AnnualParallaxTrajectory.compute
+ *   caustics_marginalized_log_likelihood  src/caustics/linalg.py:55-70 (diagonal covariance)
  *
  * complex128 arrays are passed as `const void*` to interleaved (re, im) doubles, C order.
  */
@@ -194,6 +196,22 @@ int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t
 int caustics_mag_gate(const void* w, double* mag, uint8_t* used_hexadecapole, int32_t* list, int32_t* count,
                       int64_t n, double rho, const caustics_lens* lens, double q, int itmax, int compensated,
                       void* stream);
+
+/* ---- either side of the magnification in a light-curve likelihood -------------
+ * caustics_trajectory: AnnualParallaxTrajectory.compute (src/caustics/trajectory.py:106-158) with the
+ * Sun's projected position/velocity tables (t_jpl, s_e, s_n, s_e_dot, s_n_dot: n_jpl doubles each,
+ * what trajectory.py:60-104 derives from the JPL ephemeris) passed in; n_jpl = 0: rectilinear motion.
+ * t (n) float64 -> w (n) complex128 = u_e + i u_n.  psi/piE are the polar parametrisation
+ * (piEE = piE sin psi, piEN = piE cos psi).
+ * caustics_marginalized_log_likelihood: marginalized_log_likelihood, diagonal covariance
+ * (src/caustics/linalg.py:55-70) for ONE light curve: out (3 doubles, device) = F_s, F_b, log-likelihood.
+ * Deterministic (one CTA, fixed summation order).  All pointers are device pointers; nothing
+ * synchronises, so trajectory -> caustics_mag -> likelihood is one stream-ordered enqueue. */
+int caustics_trajectory(const double* t, void* w, int64_t n, double t0, double tE, double u0, double psi,
+                        double piE, const double* t_jpl, const double* s_e, const double* s_n,
+                        const double* s_e_dot, const double* s_n_dot, int n_jpl, void* stream);
+int caustics_marginalized_log_likelihood(const double* mag, const double* fobs, const double* c_inv, int64_t n,
+                                         double* out, void* stream);
 
 /* Contours of the images of the source limb, for differentiating the uniform-disk magnification on
  * the host side (the implicit-function rule stays in Python, north_star): per source, the vertices
