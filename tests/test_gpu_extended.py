@@ -334,13 +334,18 @@ def test_xla_magnification_entries(cb, g):
 
 def test_small_batch_variants_bitwise(cb, g):
     """<= 16384 sources run the warp-per-source / shared-memory phase variants, larger batches the
-    thread-per-source ones: same arithmetic, so the same sources give bit-identical magnifications"""
+    thread-per-source ones: same arithmetic, so the same sources give bit-identical uniform-disk
+    magnifications (limb-darkened: identical terms, different summation order)"""
     w = np.concatenate([g["b_w_0.01"], g["b_w_0.001"]])
     for ld in (False, True):
         kw = dict(nlenses=2, npts_limb=200, limb_darkening=ld, u1=0.4, npts_ld=50, **HP2)
         small = cb.mag_extended_source(w, 1e-2, **kw)
         big = cb.mag_extended_source(np.tile(w, 16400 // len(w) + 1), 1e-2, **kw)
-        assert len(big) > 16384 and np.array_equal(big[:len(w)], small) and np.array_equal(big[-len(w):], small)
+        assert len(big) > 16384
+        if ld:   # the warp-per-source limb-darkened sum adds the per-vertex terms in another order
+            assert np.allclose(big[:len(w)], small, rtol=1e-13) and np.allclose(big[-len(w):], small, rtol=1e-13)
+        else:
+            assert np.array_equal(big[:len(w)], small) and np.array_equal(big[-len(w):], small)
     wt = g["t_w_0.01"]
     small = cb.mag_extended_source(wt, 1e-2, nlenses=3, npts_limb=200, **HP3)
     big = cb.mag_extended_source(np.tile(wt, 16400 // len(wt) + 1), 1e-2, nlenses=3, npts_limb=200, **HP3)
