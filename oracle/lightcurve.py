@@ -33,9 +33,12 @@ def trajectory(t, tables=None, parametrization="cartesian", **params):
 
 
 def marginalized_log_likelihood(A_list, fobs_list, C_inv_list):
-    """linalg.py:55-70, dense_covariance=False"""
+    """linalg.py:55-70, dense_covariance=False.  Like the reference it materialises diag(C_inv)
+    (n x n doubles): keep n to a few thousand."""
     ll, betas = 0.0, []
     for A, fobs, C_inv in zip(A_list, fobs_list, C_inv_list):
+        if len(A) > 20000:
+            raise MemoryError("oracle restatement builds an n x n matrix; use n <= 20000")
         M = np.stack([A, np.ones_like(A)]).T
         MTCinvM = M.T @ np.diag(C_inv) @ M
         Sigma = np.linalg.solve(MTCinvM, np.eye(2))

@@ -74,10 +74,18 @@ def test_likelihood_kernel(g):
     assert ll2 == ll and isinstance(b2[0], torch.Tensor)
     # ragged / tiny / large
     rng = np.random.default_rng(3)
+    def direct(A, f, c):   # the same normal equations without the oracle's n x n diag(C_inv)
+        M = np.stack([A, np.ones_like(A)]).T
+        S = np.linalg.inv(M.T @ (c[:, None] * M))
+        b = S @ (M.T @ (c * f))
+        return b, -0.5 * np.sum((f - M @ b) ** 2 * c) + 0.5 * np.log(np.linalg.det(2 * np.pi * S))
     for n in (2, 3, 1023, 1025, 200001):
         A = 1 + rng.uniform(0, 5, n); c = rng.uniform(1, 4, n); f = 2 * A + 1 + 0.1 * rng.standard_normal(n)
         (b,), l = cb.marginalized_log_likelihood([A], [f], [c])
-        (bo,), lo = olc.marginalized_log_likelihood([A], [f], [c])
+        bo, lo = direct(A, f, c)
+        if n <= 1025:      # the oracle follows the reference and materialises diag(C_inv): small n only
+            (bo2,), lo2 = olc.marginalized_log_likelihood([A], [f], [c])
+            assert np.allclose(bo, bo2, rtol=1e-9) and abs(lo - lo2) < 1e-9 * max(1.0, abs(lo2))
         assert np.allclose(b, bo, rtol=1e-9) and abs(l - lo) < 1e-9 * max(1.0, abs(lo))
     with pytest.raises(NotImplementedError):
         cb.marginalized_log_likelihood(As, fs, cs, dense_covariance=True)
