@@ -92,6 +92,23 @@ def main():
         emit("C3 full LD contour integrations only", "evals/s", nfull, t)
         t = timeit(lambda: cb.mag_extended_source(wf, 1e-2, nlenses=2, npts_limb=200, **HP2), reps=3, warm=1)
         emit("C3 same points, uniform disk", "evals/s", nfull, t)
+        # f3: one likelihood evaluation = trajectory -> mag -> marginalised likelihood, wall clock incl.
+        # the single 24-byte read-back (what an HMC step calls)
+        tt = torch.linspace(-40.0, 40.0, n, dtype=torch.float64, device="cuda")
+        tp = dict(t0=0.0, tE=20.0, u0=0.1, piEE=0.0, piEN=0.0)
+        traj = cb.AnnualParallaxTrajectory()
+        A0 = cb.mag(traj.compute(tt, **tp), 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7, npts_ld=100, **HP2)
+        fobs = 2.0 * A0 + 0.5
+        cinv = torch.full_like(fobs, 1e4)
+        def like():
+            return cb.light_curve_log_likelihood(tt, fobs, cinv, traj, 1e-2, tp, HP2, npts_limb=200,
+                                                 limb_darkening=True, u1=0.7, npts_ld=100)
+        like(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            like()
+        dt = (time.perf_counter() - t0) / 5
+        emit("C3 likelihood closure: trajectory -> mag (LD, gated) -> marginalised log-likelihood, n=10^4, wall clock", "evals/s", n, dt)
         if args.cpu:
             from oracle import extended      # CPU baseline leg only
             sub = np.linspace(-2, 2, n)[::100] + 0.1j
