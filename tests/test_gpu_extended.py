@@ -350,3 +350,38 @@ def test_small_batch_variants_bitwise(cb, g):
     small = cb.mag_extended_source(wt, 1e-2, nlenses=3, npts_limb=200, **HP3)
     big = cb.mag_extended_source(np.tile(wt, 16400 // len(wt) + 1), 1e-2, nlenses=3, npts_limb=200, **HP3)
     assert np.array_equal(big[:len(wt)], small)
+
+
+def test_c4_gradient_subset(cb):
+    """gradient of the triple-lens uniform-disk magnification w.r.t. (s, q, q3, r3, psi,
+    rho) on a 10^2-point subset of the C4 trajectory vs central finite differences (fixed sampling and
+    topology, vertices re-polished at the shifted parameters; see the test above for why)."""
+    from caustics_b200 import extended_source as es
+    # the C2/C4 lens (a, e1, e2, r3) = (0.698, 0.02809, 0.9687, -0.0197-0.95087i) in high-level parameters
+    a, e1, e2, r3c = 0.698, 0.02809, 0.9687, -0.0197 - 0.95087j
+    q = e2 / e1
+    base = dict(s=2 * a, q=q, q3=q / e1 - 1 - q, r3=abs(r3c), psi=float(np.angle(r3c)))
+    p, x_cm = cb.lens_params(3, **base)
+    assert abs(p["e1"] - e1) < 1e-15 and abs(p["e2"] - e2) < 1e-13 and abs(p["r3"] - r3c) < 1e-15
+    rho0 = 1e-2
+    w = torch.from_numpy(np.linspace(-2, 2, 100_000)[500::1000] + 0.1j - x_cm).cuda()
+    assert w.numel() == 100
+    wt = torch.from_numpy(np.random.default_rng(5).uniform(0.5, 1.5, 100)).cuda()   # weights: no cancellation
+    t = {k: torch.tensor(v, dtype=torch.float64, device="cuda", requires_grad=True) for k, v in base.items()}
+    rho = torch.tensor(rho0, dtype=torch.float64, device="cuda", requires_grad=True)
+    m = cb.mag_extended_source(w, rho, nlenses=3, npts_limb=200, **t)
+    plain = cb.mag_extended_source(w, rho0, nlenses=3, npts_limb=200, **base)
+    assert torch.allclose(m.detach(), plain, rtol=1e-9)
+    (m * wt).sum().backward()
+    cont = es._get_contours(w, rho0, 3, 200, 2500, False, base)
+
+    def frozen(rho_=rho0, **over):
+        with torch.no_grad():
+            return (es._mag_from_contours(cont, w.reshape(-1), rho_, 3, dict(base, **over), newton_steps=5) * wt).sum().item()
+
+    for k, v in base.items():
+        h = 1e-8 * max(1.0, abs(v))
+        fd = (frozen(**{k: v + h}) - frozen(**{k: v - h})) / (2 * h)
+        assert abs(t[k].grad.item() - fd) <= 1e-3 * max(abs(fd), 1e-3), (k, t[k].grad.item(), fd)
+    fd = (frozen(rho_=rho0 + 1e-9) - frozen(rho_=rho0 - 1e-9)) / 2e-9
+    assert abs(rho.grad.item() - fd) <= 1e-3 * max(abs(fd), 1.0)
