@@ -46,6 +46,15 @@ inline int limb_chains() {
   return k;
 }   // below this many sources the warp-per-source selection is used
 
+// Phase-variant mask: 1 warp-per-source selection, 2 stitching on a shared-memory copy of the tracks,
+// 4 warp-per-source limb-darkened sum.  CAUSTICS_B200_SMALL_MASK overrides the batch-size rule
+// (experiments only).
+inline int small_mask(bool small_batch) {
+  static int k = -2;
+  if (k == -2) { const char* e = getenv("CAUSTICS_B200_SMALL_MASK"); k = e ? atoi(e) : -1; }
+  return k >= 0 ? (k & 7) : (small_batch ? 7 : 0);
+}
+
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUSTICS_ERR_CUDA_BASE + (int)e; }
 
 // ---- kernels: thin wrappers around the phase bodies of extended_core.cuh ------------------------
@@ -176,7 +185,7 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
     k_align_chains<D><<<gs, NT, 0, st>>>(cfg, b);
   } else k_limb_walk<(NL == 1 ? 2 : NL)><<<gs, NT, 0, st>>>(cfg, b, L);
   for (int r = 0; r < NITER; ++r) {
-    if (cfg.small) k_refine_select_warp<D><<<(unsigned)((cfg.S + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, r);
+    if (cfg.small & 1) k_refine_select_warp<D><<<(unsigned)((cfg.S + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, r);
     else k_refine_select<D><<<gs, NT, 0, st>>>(cfg, b, r);
     if (NL == 1) k_refine_solve_single<<<gr, NT, 0, st>>>(cfg, b, L, r);
     else if (cfg.comp) k_refine_solve<(NL == 1 ? 2 : NL), true><<<gr, NT, 0, st>>>(cfg, b, L, r);
@@ -184,7 +193,7 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
   }
   k_tracks<D><<<gs, NT, 0, st>>>(cfg, b);
   const size_t stage_bytes = (size_t)cfg.NP * D * 17 + (size_t)cfg.NP * 8 + 64;
-  if (cfg.small && stage_bytes <= 200 * 1024) {
+  if ((cfg.small & 2) && stage_bytes <= 200 * 1024) {
     if (stage_bytes > 48 * 1024)
       cudaFuncSetAttribute(k_contours_staged<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
     k_contours_staged<D><<<(unsigned)cfg.S, 32, stage_bytes, st>>>(cfg, b, L);
@@ -194,7 +203,7 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
   if (cfg.ld) {
     const unsigned gv = (unsigned)(((int64_t)cfg.VMAX * cfg.S + NT - 1) / NT);
     k_ld_pq<NL><<<gv, NT, 0, st>>>(cfg, b, L);
-    if (cfg.small) k_ld_sum_warp<<<(unsigned)((cfg.S + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b);
+    if (cfg.small & 4) k_ld_sum_warp<<<(unsigned)((cfg.S + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b);
     else k_ld_sum<<<gs, NT, 0, st>>>(cfg, b);
   }
   return cuda_rc(cudaGetLastError());
@@ -226,8 +235,9 @@ static int ext_driver(const void* w, double* mag, uint8_t* test_out, int64_t n, 
   // small-batch (warp-per-source / staged) phase variants: few sources to integrate.  With the gate on
   // only the points that fail it are integrated (a few per cent of a light curve), so the bound on n is
   // 16x higher there.
-  cfg.small = n <= (gate && lens->nlenses == 2 ? 16 * SMALL_BATCH : SMALL_BATCH);
-  if (cfg.small && cfg.N0 >= 32) cfg.chains = limb_chains();
+  const bool small_batch = n <= (gate && lens->nlenses == 2 ? 16 * SMALL_BATCH : SMALL_BATCH);
+  cfg.small = small_mask(small_batch);
+  if (small_batch && cfg.N0 >= 32) cfg.chains = limb_chains();
   if (n > 0x7fffffffLL / (cfg.VMAX > NADD_MAX ? cfg.VMAX : NADD_MAX)) return CAUSTICS_ERR_BAD_ARG;  // index range of one call
   if (!w || !mag || !workspace) return CAUSTICS_ERR_BAD_ARG;
   const Layout lay = make_layout(cfg);
@@ -298,8 +308,8 @@ int caustics_ext_contours(const void* w, double* mag, int64_t n, double rho, con
   int rc = make_cfg(n, rho, lens->nlenses, npts_limb, 0, 0.0, 100, itmax, compensated, &cfg);
   if (rc) return rc;
   if (n == 0) return CAUSTICS_OK;
-  cfg.small = n <= SMALL_BATCH;
-  if (cfg.small && cfg.N0 >= 32) cfg.chains = limb_chains();
+  cfg.small = small_mask(n <= SMALL_BATCH);
+  if (n <= SMALL_BATCH && cfg.N0 >= 32) cfg.chains = limb_chains();
   if (n > 0x7fffffffLL / cfg.VMAX) return CAUSTICS_ERR_BAD_ARG;
   if (!w || !workspace || !vz || !vtheta || !vcid || !vcount || !cpar || !cstart || !ncont) return CAUSTICS_ERR_BAD_ARG;
   const Layout lay = make_layout(cfg);

@@ -39,7 +39,7 @@ struct ExtCfg {
   int nl, D, N0, nadd, NP;
   double rho;
   int itmax, comp, ld, n1, n2, VMAX, CMAX;
-  int small;        // 1: use the small-batch (warp-per-source / shared-memory staged) phase variants
+  int small;        // mask of small-batch phase variants: 1 warp select, 2 staged contours, 4 warp LD sum
   int chains;       // limb walk split into this many independently started chains (small batches)
   int emit;         // 1: k_contours also writes the contour vertex lists (z, theta, contour id) for the host
   double u1;
