@@ -130,25 +130,33 @@ def test_c3_light_curve_subset(cb):
     assert np.allclose(got[far], ps[far], rtol=1e-3)
 
 
-def _oracle_ld_c3(x):
-    return extended.mag_extended_source(x, 1e-2, 2, 200, True, 0.7, 100, **HP2)
-
-
 def test_c3_every_full_integration(cb):
     """config 3 at full size: EVERY point of the 10^4-point light curve that fails the hexadecapole gate
     (565 limb-darkened contour integrations) against the oracle; the kernels follow the reference's
     warm-start chain, so the agreement is at rounding level, far inside the 1e-4 bar"""
-    import os
-    from concurrent.futures import ProcessPoolExecutor
+    import _oracle_workers as ow
     w = c1_w()
     got, used = cb.mag(w, 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7, npts_ld=100,
                        return_test=True, **HP2)
     idx = np.flatnonzero(~np.asarray(used))
     assert 400 < len(idx) < 800
-    with ProcessPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
-        want = np.array(list(ex.map(_oracle_ld_c3, w[idx], chunksize=8)))
+    want = ow.pool_map(ow.oracle_ld_c3, w[idx])
     rel = np.abs(np.asarray(got)[idx] / want - 1)
     assert rel.max() < 1e-4
+    assert np.median(rel) < 1e-10
+
+
+def test_c4_sample_vs_oracle(cb):
+    """config 4: every 250th point of the 10^5-point triple-lens trajectory (400 uniform-disk contour
+    integrations, caustic crossings included) against the oracle"""
+    import _oracle_workers as ow
+    hp = ow.c4_hp()
+    _, x_cm = cb.lens_params(3, **hp)
+    w = np.linspace(-2, 2, 100_000)[::250] + 0.1j - x_cm
+    got = cb.mag_extended_source(w, 1e-2, nlenses=3, npts_limb=200, **hp)
+    want = ow.pool_map(ow.oracle_c4, w, chunksize=4)
+    rel = np.abs(got / want - 1)
+    assert rel.max() < 1e-4, (rel.max(), w[np.argmax(rel)])
     assert np.median(rel) < 1e-10
 
 
