@@ -415,3 +415,27 @@ def test_c4_gradient_subset(cb):
         assert abs(t[k].grad.item() - fd) <= 1e-3 * max(abs(fd), 1e-3), (k, t[k].grad.item(), fd)
     fd = (frozen(rho_=rho0 + 1e-9) - frozen(rho_=rho0 - 1e-9)) / 2e-9
     assert abs(rho.grad.item() - fd) <= 1e-3 * max(abs(fd), 1.0)
+
+
+@pytest.mark.parametrize("rho", [1e-1, 1e-2])
+def test_contour_invariants(cb, g, rho):
+    """tests/test_extended_source.py:121-132 (no duplicated limb images) and :209-256 (every stitched
+    contour closes), on the contours the kernels export (caustics_ext_contours), triple lens near caustics"""
+    from caustics_b200 import extended_source as es
+    w = torch.from_numpy(g[f"t_w_{rho}"]).cuda()
+    cont = es._get_contours(w, rho, 3, 200, 2500, False, HP3)
+    vz, vcid, valid, cpar = (cont[k].cpu().numpy() for k in ("vz", "vcid", "valid", "cpar"))
+    area_sum = np.zeros(w.numel())
+    for s in range(w.numel()):
+        z, c = vz[valid[:, s], s], vcid[valid[:, s], s]
+        assert len(z) > 100
+        for cid in np.unique(c):
+            zc = z[c == cid]
+            assert zc[0] == zc[-1], "closing vertex repeats the first one"
+            body = zc[:-1]
+            assert len(np.unique(body)) == len(body), "duplicated vertex inside a contour"
+            assert np.abs(np.diff(zc)).max() < 0.5          # no wild jump left after stitching
+            x, y = zc.real, zc.imag
+            area_sum[s] += cpar[cid, s] * 0.5 * np.sum(x[:-1] * y[1:] - x[1:] * y[:-1])
+    mags = cb.mag_extended_source(w, rho, nlenses=3, npts_limb=200, **HP3).cpu().numpy()
+    assert np.allclose(np.abs(area_sum) / (np.pi * rho**2), mags, rtol=1e-9)
