@@ -531,4 +531,65 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
   return res;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lane-per-root solve for batches too small to fill the machine with one thread per polynomial.
+// A warp holds G = 32 / DEG polynomials; lane g*DEG + r owns root r of polynomial g and evaluates the
+// polynomial at it, the Aberth sum reads the other roots by shuffle.  All roots of a polynomial are
+// updated from the previous sweep's values (Jacobi order) -- with the warm starts this is used for,
+// the roots are inside the cubic regime and it costs no extra sweep.  Same stopping test per root as
+// the reference (|p(z)| <= 2^-53 b, a converged root is frozen), plain mode only.
+// p: normalised coefficients low->high (identical in all lanes of a group); z: the lane's root (in:
+// warm start, out: converged root); valid: lane owns a root.  Returns the sweeps used.
+#ifndef CB200_HOSTSIM
+template <int DEG>
+__device__ __forceinline__ int ea_solve_group(const cd (&p)[DEG + 1], cd& z, int lane, bool valid, int itmax) {
+  const int base = (lane / DEG) * DEG;
+  AlphaRegs<DEG, 1> al;
+#pragma unroll
+  for (int i = 0; i <= DEG; ++i) al.v[i] = cabs_fast(p[i]) * fma(3.8284271247461900976, (double)i, 1.0);
+  bool conv = !valid;
+  int it = 0;
+  for (; it < itmax; ++it) {
+    if (__all_sync(0xffffffffu, conv)) break;
+    const double az2 = norm2(z);
+    const bool rev = az2 > 1.0;
+    const double rs = az2 > 0.0 ? rsqrt_fast(az2) : 0.0;
+    const double absz = az2 * rs;
+    cd x = z;
+    double ax = absz;
+    if (rev) {
+      const double inv = rs * rs;
+      x = mk(z.re * inv, -z.im * inv);
+      ax = rs;
+    }
+    cd h, hd;
+    double b;
+    horner_plain<DEG, 2, AlphaRegs<DEG, 1> >(p, al, x, ax, rev, h, hd, b);
+    const double thr = EA_EPS * b;
+    const bool big = norm2(h) > thr * thr;
+    cd s = mk(0, 0);
+#pragma unroll
+    for (int i = 0; i < DEG; ++i) {
+      const double ore = __shfl_sync(0xffffffffu, z.re, base + i), oim = __shfl_sync(0xffffffffu, z.im, base + i);
+      const cd a = z - mk(ore, oim);
+      const double inv = (base + i != lane) ? rcp_aberth<false>(norm2(a)) : 0.0;
+      s = mk(fma(a.re, inv, s.re), fma(-a.im, inv, s.im));
+    }
+    cd num = h, den = hd;
+    if (rev) {
+      const cd z2 = z * z;
+      num = z2 * h;
+      den = ((double)DEG * z) * h - hd;
+    }
+    den = den - num * s;
+    const cd corr = cdiv(num, den);
+    if (!conv) {
+      if (big) z = z - corr;
+      else conv = true;
+    }
+  }
+  return it;
+}
+#endif
+
 }  // namespace cb200

@@ -47,12 +47,21 @@ inline int limb_chains() {
 }   // below this many sources the warp-per-source selection is used
 
 // Phase-variant mask: 1 warp-per-source selection, 2 stitching on a shared-memory copy of the tracks,
-// 4 warp-per-source limb-darkened sum.  CAUSTICS_B200_SMALL_MASK overrides the batch-size rule
-// (experiments only).
-inline int small_mask(bool small_batch) {
+// 4 warp-per-source limb-darkened sum, 8 lane-per-root limb walk, 16 lane-per-root refinement solves.
+// The batch-size rules below were measured on one B200 (npts_limb = 200; profiles/README.md): the
+// lane-per-root walk wins up to ~8192 sources, the lane-per-root refinement only for the binary lens
+// up to ~2048 (with ten roots per polynomial the Jacobi sweeps' long tail costs more than it saves).
+// `scale` = 16 for gated binary light curves, where only a few per cent of the points are integrated.
+// CAUSTICS_B200_SMALL_MASK overrides the rules (experiments only).
+inline int small_mask(int64_t n, int nlenses, int64_t scale) {
   static int k = -2;
   if (k == -2) { const char* e = getenv("CAUSTICS_B200_SMALL_MASK"); k = e ? atoi(e) : -1; }
-  return k >= 0 ? (k & 7) : (small_batch ? 7 : 0);
+  if (k >= 0) return k & 31;
+  int m = 0;
+  if (n <= scale * SMALL_BATCH) m |= 7;
+  if (n <= scale * 8192) m |= 8;
+  if (nlenses == 2 && n <= scale * 2048) m |= 16;
+  return m;
 }
 
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUSTICS_ERR_CUDA_BASE + (int)e; }
@@ -62,6 +71,15 @@ template <int NL>
 __global__ void __launch_bounds__(NT) k_limb_walk(ExtCfg cfg, ExtBuf b, LensConst L) {
   __shared__ EASmem<NL * NL + 1, false, NT> sm;
   limb_walk_body<NL, NT>(cfg, b, L, sm, threadIdx.x, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+template <int NL>
+__global__ void __launch_bounds__(NT) k_limb_walk_group(ExtCfg cfg, ExtBuf b, LensConst L) {
+  __shared__ EASmem<NL * NL + 1, false, NT> sm;
+  limb_walk_group_body<NL, NT>(cfg, b, L, sm, threadIdx.x, (int64_t)blockIdx.x * (NT / 32) + threadIdx.x / 32);
+}
+template <int NL>
+__global__ void __launch_bounds__(NT) k_refine_solve_group(ExtCfg cfg, ExtBuf b, LensConst L, int round) {
+  refine_solve_group_body<NL>(cfg, b, L, round, threadIdx.x, (int64_t)blockIdx.x * (NT / 32) + threadIdx.x / 32);
 }
 template <int NL>
 __global__ void __launch_bounds__(NT) k_limb_walk_chains(ExtCfg cfg, ExtBuf b, LensConst L) {
@@ -183,11 +201,20 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
   else if (cfg.chains > 1) {
     k_limb_walk_chains<(NL == 1 ? 2 : NL)><<<(unsigned)(((int64_t)cfg.chains * cfg.S + NT - 1) / NT), NT, 0, st>>>(cfg, b, L);
     k_align_chains<D><<<gs, NT, 0, st>>>(cfg, b);
+  } else if (cfg.small & 8) {
+    constexpr int G = 32 / (NL == 1 ? 5 : NL * NL + 1);   // sources per warp
+    const int64_t warps = (cfg.S + G - 1) / G;
+    k_limb_walk_group<(NL == 1 ? 2 : NL)><<<(unsigned)((warps + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, L);
   } else k_limb_walk<(NL == 1 ? 2 : NL)><<<gs, NT, 0, st>>>(cfg, b, L);
   for (int r = 0; r < NITER; ++r) {
     if (cfg.small & 1) k_refine_select_warp<D><<<(unsigned)((cfg.S + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, r);
     else k_refine_select<D><<<gs, NT, 0, st>>>(cfg, b, r);
     if (NL == 1) k_refine_solve_single<<<gr, NT, 0, st>>>(cfg, b, L, r);
+    else if ((cfg.small & 16) && !cfg.comp) {
+      constexpr int G = 32 / (NL == 1 ? 5 : NL * NL + 1);
+      const int64_t warps = ((int64_t)cfg.nadd * cfg.S + G - 1) / G;
+      k_refine_solve_group<(NL == 1 ? 2 : NL)><<<(unsigned)((warps + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, L, r);
+    }
     else if (cfg.comp) k_refine_solve<(NL == 1 ? 2 : NL), true><<<gr, NT, 0, st>>>(cfg, b, L, r);
     else k_refine_solve<(NL == 1 ? 2 : NL), false><<<gr, NT, 0, st>>>(cfg, b, L, r);
   }
@@ -235,9 +262,9 @@ static int ext_driver(const void* w, double* mag, uint8_t* test_out, int64_t n, 
   // small-batch (warp-per-source / staged) phase variants: few sources to integrate.  With the gate on
   // only the points that fail it are integrated (a few per cent of a light curve), so the bound on n is
   // 16x higher there.
-  const bool small_batch = n <= (gate && lens->nlenses == 2 ? 16 * SMALL_BATCH : SMALL_BATCH);
-  cfg.small = small_mask(small_batch);
-  if (small_batch && cfg.N0 >= 32) cfg.chains = limb_chains();
+  const int64_t scale = gate && lens->nlenses == 2 ? 16 : 1;
+  cfg.small = small_mask(n, lens->nlenses, scale);
+  if (n <= scale * SMALL_BATCH && cfg.N0 >= 32) cfg.chains = limb_chains();
   if (n > 0x7fffffffLL / (cfg.VMAX > NADD_MAX ? cfg.VMAX : NADD_MAX)) return CAUSTICS_ERR_BAD_ARG;  // index range of one call
   if (!w || !mag || !workspace) return CAUSTICS_ERR_BAD_ARG;
   const Layout lay = make_layout(cfg);
@@ -308,7 +335,7 @@ int caustics_ext_contours(const void* w, double* mag, int64_t n, double rho, con
   int rc = make_cfg(n, rho, lens->nlenses, npts_limb, 0, 0.0, 100, itmax, compensated, &cfg);
   if (rc) return rc;
   if (n == 0) return CAUSTICS_OK;
-  cfg.small = small_mask(n <= SMALL_BATCH);
+  cfg.small = small_mask(n, lens->nlenses, 1);
   if (n <= SMALL_BATCH && cfg.N0 >= 32) cfg.chains = limb_chains();
   if (n > 0x7fffffffLL / cfg.VMAX) return CAUSTICS_ERR_BAD_ARG;
   if (!w || !workspace || !vz || !vtheta || !vcid || !vcount || !cpar || !cstart || !ncont) return CAUSTICS_ERR_BAD_ARG;

@@ -39,7 +39,7 @@ struct ExtCfg {
   int nl, D, N0, nadd, NP;
   double rho;
   int itmax, comp, ld, n1, n2, VMAX, CMAX;
-  int small;        // mask of small-batch phase variants: 1 warp select, 2 staged contours, 4 warp LD sum
+  int small;        // mask of small-batch phase variants: 1 warp select, 2 staged contours, 4 warp LD sum, 8 lane-per-root walk
   int chains;       // limb walk split into this many independently started chains (small batches)
   int emit;         // 1: k_contours also writes the contour vertex lists (z, theta, contour id) for the host
   double u1;
@@ -146,6 +146,53 @@ __device__ void limb_walk_body(const ExtCfg& cfg, const ExtBuf& b, const LensCon
     }
   }
 }
+
+// Small batches, lane-per-root: a warp walks G = 32 / D sources, lane g*D + r follows image track r of
+// source g.  Limb point 0 is the same cold Gauss-Seidel solve as in limb_walk_body (on the group's first
+// lane: same initial estimates, same root order); every later point is warm-started in registers and
+// solved by ea_solve_group.  The dependent chain per limb point shrinks from D root updates to one.
+#ifndef CB200_HOSTSIM
+template <int NL, int NT>
+__device__ void limb_walk_group_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,
+                                     EASmem<NL * NL + 1, false, NT>& sm, int tid, int64_t warp_id) {
+  constexpr int D = NL * NL + 1, G = 32 / D;
+  const int lane = tid & 31, grp = lane / D, r = lane - grp * D;
+  const int64_t s = warp_id * G + grp;
+  const bool valid = grp < G && s < nsrc(cfg, b);
+  const cd w0 = valid ? source_centre(cfg, b, L, s) : mk(0.3, 0.2);
+  {
+    cd p[D + 1];
+    lens_poly<NL>(L, limb_point(w0, cfg.rho, theta_init(0, cfg.N0)), p);
+    ea_normalise<D>(p);
+    ea_solve_thread<D, false, NT, CB200_EXT_STRAIGHT != 0>(p, sm, tid, valid && r == 0, false, EA_INIT_REFERENCE, cfg.itmax);
+  }
+  __syncwarp();
+  cd z = mk(0.05 + 0.1 * lane, 0.07 * lane);   // idle lanes: distinct dummies
+  if (valid) z = mk(sm.zre[r][tid - r], sm.zim[r][tid - r]);
+  for (int k = 0; k < cfg.N0; ++k) {
+    const double th = theta_init(k, cfg.N0);
+    const cd w = limb_point(w0, cfg.rho, th);
+    if (k > 0) {
+      cd p[D + 1];
+      lens_poly<NL>(L, w, p);
+      ea_normalise<D>(p);
+      ea_solve_group<D>(p, z, lane, valid, cfg.itmax);
+    }
+    if (valid) {
+      bool real_image;
+      double detj;
+      image_eval<NL>(L, z, w, real_image, detj);
+      b.zre[I3(k, r, s)] = z.re;
+      b.zim[I3(k, r, s)] = z.im;
+      b.flg[I3(k, r, s)] = (real_image ? 1 : 0) | (detj > 0 ? 2 : 0) | (detj == 0 ? 4 : 0);
+      if (r == 0) {
+        b.theta[I2(k, s)] = th;
+        b.order[I2(k, s)] = (uint16_t)k;
+      }
+    }
+  }
+}
+#endif
 
 // Small batches: the limb walk is a chain of N0 dependent solves per source, pure latency when there
 // are only a few hundred sources.  It is cut into cfg.chains chains that start cold and run
@@ -453,6 +500,41 @@ __device__ void refine_solve_body(const ExtCfg& cfg, const ExtBuf& b, const Lens
   solve_and_store<NL, COMP, NT>(cfg, b, L, sm, tid, active, w, true, slot, s);
   if (active) update_widths<D>(cfg, b, r, slot, s);
 }
+
+// Small batches, lane-per-root (see limb_walk_group_body): a warp solves G = 32 / D new limb points,
+// lane g*D + j follows image track j of new point g from its left neighbour's root (plain mode).
+#ifndef CB200_HOSTSIM
+template <int NL>
+__device__ void refine_solve_group_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int round, int tid, int64_t warp_id) {
+  constexpr int D = NL * NL + 1, G = 32 / D;
+  const int lane = tid & 31, grp = lane / D, j = lane - grp * D;
+  const int64_t g = warp_id * G + grp;            // (new point, source) pair, sources fastest
+  const int r = (int)(g / cfg.S);
+  const int64_t s = g - (int64_t)r * cfg.S;
+  const bool valid = grp < G && r < cfg.nadd && s < nsrc(cfg, b);
+  const int slot = cfg.N0 + round * cfg.nadd + r;
+  cd w = mk(0.3, 0.2), z = mk(0.05 + 0.1 * lane, 0.07 * lane);
+  if (valid) {
+    w = limb_point(source_centre(cfg, b, L, s), cfg.rho, b.theta[I2(slot, s)]);
+    const int lf = b.left[I2(r, s)];
+    z = mk(b.zre[I3(lf, j, s)] + JIT_RE, b.zim[I3(lf, j, s)] + JIT_IM);
+  }
+  cd p[D + 1];
+  lens_poly<NL>(L, w, p);
+  ea_normalise<D>(p);
+  ea_solve_group<D>(p, z, lane, valid, cfg.itmax);
+  if (valid) {
+    bool real_image;
+    double detj;
+    image_eval<NL>(L, z, w, real_image, detj);
+    b.zre[I3(slot, j, s)] = z.re;
+    b.zim[I3(slot, j, s)] = z.im;
+    b.flg[I3(slot, j, s)] = (real_image ? 1 : 0) | (detj > 0 ? 2 : 0) | (detj == 0 ? 4 : 0);
+  }
+  __syncwarp();
+  if (valid && j == 0) update_widths<D>(cfg, b, r, slot, s);
+}
+#endif
 
 __device__ void refine_solve_single_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int round, int64_t g) {
   const int r = (int)(g / cfg.S);
