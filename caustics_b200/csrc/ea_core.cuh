@@ -533,30 +533,37 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
 
 // ---------------------------------------------------------------------------------------------
 // Lane-per-root solve for batches too small to fill the machine with one thread per polynomial.
-// A warp holds G = 32 / DEG polynomials; lane g*DEG + r owns root r of polynomial g and evaluates the
-// polynomial at it, the Aberth sum reads the other roots by shuffle.  All roots of a polynomial are
-// updated from the previous sweep's values (Jacobi order) -- with the warm starts this is used for,
-// the roots are inside the cubic regime and it costs no extra sweep.  Same stopping test per root as
-// the reference (|p(z)| <= 2^-53 b, a converged root is frozen), plain mode only.
+// A warp holds G = 32 / DEG polynomials; lane g*DEG + r owns root r of polynomial g.  One sweep =
+//   (A) every lane evaluates the polynomial (value, derivative, bound) at its own root -- the
+//       expensive part, in parallel -- and applies the reference's stopping test;
+//   (B) the roots that have to move are corrected ONE AFTER THE OTHER in root order: the group's
+//       lanes each form their term 1/(z_j - z_i) of the Aberth sum with the roots as they are now
+//       (roots < j already moved in this sweep), a shuffle tree adds them, lane j applies the correction.
+// That is the reference's Gauss-Seidel sweep (ehrlich_aberth.h:100-143) -- root j is evaluated at the
+// value it had when the sweep started, its Aberth sum sees the already-updated roots -- with the
+// per-polynomial dependent chain cut from DEG evaluations to one; only the order in which the DEG - 1
+// terms of a sum are added differs from ea_solve_thread (rounding level: which root a lane converges to,
+// hence the labelling of the image tracks, is the thread solver's).  Plain mode only.
 // p: normalised coefficients low->high (identical in all lanes of a group); z: the lane's root (in:
 // warm start, out: converged root); valid: lane owns a root.  Returns the sweeps used.
 #ifndef CB200_HOSTSIM
 template <int DEG>
 __device__ __forceinline__ int ea_solve_group(const cd (&p)[DEG + 1], cd& z, int lane, bool valid, int itmax) {
-  const int base = (lane / DEG) * DEG;
+  constexpr unsigned FULLW = 0xffffffffu;
+  const int base = (lane / DEG) * DEG, r = lane - base;
   AlphaRegs<DEG, 1> al;
 #pragma unroll
   for (int i = 0; i <= DEG; ++i) al.v[i] = cabs_fast(p[i]) * fma(3.8284271247461900976, (double)i, 1.0);
   bool conv = !valid;
   int it = 0;
   for (; it < itmax; ++it) {
-    if (__all_sync(0xffffffffu, conv)) break;
+    if (__all_sync(FULLW, conv)) break;
+    // (A) evaluation at the own root
     const double az2 = norm2(z);
     const bool rev = az2 > 1.0;
     const double rs = az2 > 0.0 ? rsqrt_fast(az2) : 0.0;
-    const double absz = az2 * rs;
     cd x = z;
-    double ax = absz;
+    double ax = az2 * rs;
     if (rev) {
       const double inv = rs * rs;
       x = mk(z.re * inv, -z.im * inv);
@@ -566,26 +573,34 @@ __device__ __forceinline__ int ea_solve_group(const cd (&p)[DEG + 1], cd& z, int
     double b;
     horner_plain<DEG, 2, AlphaRegs<DEG, 1> >(p, al, x, ax, rev, h, hd, b);
     const double thr = EA_EPS * b;
-    const bool big = norm2(h) > thr * thr;
-    cd s = mk(0, 0);
-#pragma unroll
-    for (int i = 0; i < DEG; ++i) {
-      const double ore = __shfl_sync(0xffffffffu, z.re, base + i), oim = __shfl_sync(0xffffffffu, z.im, base + i);
-      const cd a = z - mk(ore, oim);
-      const double inv = (base + i != lane) ? rcp_aberth<false>(norm2(a)) : 0.0;
-      s = mk(fma(a.re, inv, s.re), fma(-a.im, inv, s.im));
-    }
+    const bool upd = !conv && norm2(h) > thr * thr;
+    conv = conv || !upd;
     cd num = h, den = hd;
     if (rev) {
       const cd z2 = z * z;
       num = z2 * h;
       den = ((double)DEG * z) * h - hd;
     }
-    den = den - num * s;
-    const cd corr = cdiv(num, den);
-    if (!conv) {
-      if (big) z = z - corr;
-      else conv = true;
+    // (B) corrections in root order
+    const unsigned moving = __ballot_sync(FULLW, upd);
+#pragma unroll 1
+    for (int j = 0; j < DEG; ++j) {
+      // does root j move in any of the warp's polynomials?  (lanes j, DEG + j, 2 DEG + j, ...)
+      unsigned sel = 0;
+#pragma unroll
+      for (int g = 0; g < 32 / DEG; ++g) sel |= 1u << (g * DEG + j);
+      if (!(moving & sel)) continue;
+      const cd zj = mk(__shfl_sync(FULLW, z.re, base + j), __shfl_sync(FULLW, z.im, base + j));
+      const cd a = zj - z;
+      const double inv = (r != j && base + DEG <= 32) ? rcp_aberth<false>(norm2(a)) : 0.0;
+      double tr = a.re * inv, ti = -a.im * inv;
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) {
+        const double ur = __shfl_down_sync(FULLW, tr, off), ui = __shfl_down_sync(FULLW, ti, off);
+        if (r + off < DEG) { tr += ur; ti += ui; }
+      }
+      const cd s = mk(__shfl_sync(FULLW, tr, base), __shfl_sync(FULLW, ti, base));
+      if (upd && r == j) z = z - cdiv(num, den - num * s);
     }
   }
   return it;

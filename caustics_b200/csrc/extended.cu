@@ -48,9 +48,8 @@ inline int limb_chains() {
 
 // Phase-variant mask: 1 warp-per-source selection, 2 stitching on a shared-memory copy of the tracks,
 // 4 warp-per-source limb-darkened sum, 8 lane-per-root limb walk, 16 lane-per-root refinement solves.
-// The batch-size rules below were measured on one B200 (npts_limb = 200; profiles/README.md): the
-// lane-per-root walk wins up to ~8192 sources, the lane-per-root refinement only for the binary lens
-// up to ~2048 (with ten roots per polynomial the Jacobi sweeps' long tail costs more than it saves).
+// The batch-size rules below were measured on one B200 (npts_limb = 200): the lane-per-root walk wins
+// up to ~8192 (binary) / ~4096 (triple) sources, the lane-per-root refinement up to ~2048 / ~128.
 // `scale` = 16 for gated binary light curves, where only a few per cent of the points are integrated.
 // CAUSTICS_B200_SMALL_MASK overrides the rules (experiments only).
 inline int small_mask(int64_t n, int nlenses, int64_t scale) {
@@ -59,8 +58,8 @@ inline int small_mask(int64_t n, int nlenses, int64_t scale) {
   if (k >= 0) return k & 31;
   int m = 0;
   if (n <= scale * SMALL_BATCH) m |= 7;
-  if (n <= scale * 8192) m |= 8;
-  if (nlenses == 2 && n <= scale * 2048) m |= 16;
+  if (n <= scale * (nlenses == 2 ? 8192 : 4096)) m |= 8;
+  if (n <= scale * (nlenses == 2 ? 2048 : 128)) m |= 16;
   return m;
 }
 

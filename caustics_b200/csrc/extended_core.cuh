@@ -150,7 +150,7 @@ __device__ void limb_walk_body(const ExtCfg& cfg, const ExtBuf& b, const LensCon
 // Small batches, lane-per-root: a warp walks G = 32 / D sources, lane g*D + r follows image track r of
 // source g.  Limb point 0 is the same cold Gauss-Seidel solve as in limb_walk_body (on the group's first
 // lane: same initial estimates, same root order); every later point is warm-started in registers and
-// solved by ea_solve_group.  The dependent chain per limb point shrinks from D root updates to one.
+// solved by ea_solve_group (the same Gauss-Seidel sweep with the D evaluations done in parallel).
 #ifndef CB200_HOSTSIM
 template <int NL, int NT>
 __device__ void limb_walk_group_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,

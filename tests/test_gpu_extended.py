@@ -365,8 +365,8 @@ def test_xla_magnification_entries(cb, g):
 def test_small_batch_variants(cb, g):
     """Small batches run the latency-oriented phase variants (lane-per-root limb walk and refinement
     solves, warp-per-source selection and limb-darkened sum, stitching on a shared-memory copy), large
-    batches the thread-per-source ones.  Same algorithm, same warm-start chain: the roots differ by the
-    Gauss-Seidel vs Jacobi rounding only, the magnifications by ~1e-10 at most."""
+    batches the thread-per-source ones.  Same algorithm, same warm-start chain and Gauss-Seidel order:
+    only the summation order inside an Aberth sum differs, the magnifications by ~1e-11."""
     w = np.concatenate([g["b_w_0.01"], g["b_w_0.001"]])
     for ld in (False, True):
         kw = dict(nlenses=2, npts_limb=200, limb_darkening=ld, u1=0.4, npts_ld=50, **HP2)
@@ -375,11 +375,11 @@ def test_small_batch_variants(cb, g):
         big = cb.mag_extended_source(np.tile(w, 16400 // len(w) + 1), 1e-2, **kw)    # no small-batch variant
         assert len(big) > 16384 and 2048 < len(mid) <= 8192
         for other in (mid, big):
-            assert np.allclose(other[:len(w)], small, rtol=1e-8) and np.allclose(other[-len(w):], small, rtol=1e-8)
+            assert np.allclose(other[:len(w)], small, rtol=1e-9) and np.allclose(other[-len(w):], small, rtol=1e-9)
     wt = g["t_w_0.01"]
     small = cb.mag_extended_source(wt, 1e-2, nlenses=3, npts_limb=200, **HP3)
     big = cb.mag_extended_source(np.tile(wt, 16400 // len(wt) + 1), 1e-2, nlenses=3, npts_limb=200, **HP3)
-    assert np.allclose(big[:len(wt)], small, rtol=1e-8)
+    assert np.allclose(big[:len(wt)], small, rtol=1e-9)
 
 
 def test_c4_gradient_subset(cb):
