@@ -146,7 +146,15 @@ __global__ void __launch_bounds__(32) k_contours_staged(ExtCfg cfg, ExtBuf b, Le
 }
 template <int NL>
 __global__ void __launch_bounds__(NT) k_ld_pq(ExtCfg cfg, ExtBuf b, LensConst L) {
-  ld_pq_body<NL>(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
+  // grid-stride over (vertex, source) with the sources that are actually integrated fastest: with the
+  // gate on, the grid would otherwise be sized for every point of the light curve and ~95 % of its CTAs
+  // would start only to exit (VMAX * S < 2^31 is checked by the driver)
+  const unsigned ns = (unsigned)nsrc(cfg, b);
+  const unsigned total = (unsigned)cfg.VMAX * ns;
+  for (unsigned g = blockIdx.x * NT + threadIdx.x; g < total; g += gridDim.x * NT) {
+    const unsigned v = g / ns;
+    ld_pq_item<NL>(cfg, b, L, (int)v, (int64_t)(g - v * ns));
+  }
 }
 __global__ void __launch_bounds__(NT) k_ld_sum(ExtCfg cfg, ExtBuf b) {
   ld_sum_body(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
@@ -227,7 +235,8 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
     k_contours<D><<<gs, NT, 0, st>>>(cfg, b, L);
   }
   if (cfg.ld) {
-    const unsigned gv = (unsigned)(((int64_t)cfg.VMAX * cfg.S + NT - 1) / NT);
+    const int64_t gv_all = ((int64_t)cfg.VMAX * cfg.S + NT - 1) / NT;
+    const unsigned gv = (unsigned)(gv_all < 148 * 64 ? gv_all : 148 * 64);
     k_ld_pq<NL><<<gv, NT, 0, st>>>(cfg, b, L);
     if (cfg.small & 4) k_ld_sum_warp<<<(unsigned)((cfg.S + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b);
     else k_ld_sum<<<gs, NT, 0, st>>>(cfg, b);

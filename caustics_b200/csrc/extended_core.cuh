@@ -922,9 +922,10 @@ __device__ __forceinline__ double brightness(const LensConst& L, cd z, cd w0, do
     for (int j = 0; j < NL; ++j) s1 = s1 + L.eps[j] * crecip(zb - conj(L.r[j]));
   }
   const double r2 = norm2((z - s1) - w0) * inv_rho2;
-  double B;
-  if (r2 <= 1.0) B = 1.0 + sqrt(fmax(1.0 - r2, 0.0));
-  else B = 1.0 - sqrt(fmax(1.0 - 1.0 / r2, 0.0));
+  // one branch-free square root for both sides of the limb (integrate.py:37-43)
+  const bool inside = r2 <= 1.0;
+  const double q = sqrt_fast(fmax(inside ? 1.0 - r2 : 1.0 - rcp_fast(fmax(r2, 1.0)), 0.0));
+  const double B = inside ? 1.0 + q : 1.0 - q;
   return 3.0 / (3.0 - u1) * (u1 * B + 1.0 - 2.0 * u1);
 }
 // two Gauss-Legendre panels [a, split] (n1 nodes) and [split, b] (n2 nodes), integrate.py:56-75.
@@ -953,9 +954,14 @@ __device__ double two_panel(const ExtCfg& cfg, const ExtBuf& bf, const LensConst
 }
 
 template <int NL>
+__device__ void ld_pq_item(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int v, int64_t s);
+template <int NL>
 __device__ void ld_pq_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t g) {
   const int v = (int)(g / cfg.S);
-  const int64_t s = g - (int64_t)v * cfg.S;
+  ld_pq_item<NL>(cfg, b, L, v, g - (int64_t)v * cfg.S);
+}
+template <int NL>
+__device__ void ld_pq_item(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int v, int64_t s) {
   if (v >= cfg.VMAX || s >= nsrc(cfg, b)) return;
   if (v >= b.vcount[s]) return;
   const cd w0 = source_centre(cfg, b, L, s);
