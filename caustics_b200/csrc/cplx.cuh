@@ -40,6 +40,7 @@ __device__ __forceinline__ cd cfma(cd a, cd b, cd c) {
 #ifdef CB200_HOSTSIM
 __device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
 __device__ __forceinline__ double rsqrt_fast(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ double rcp_fast1(double x) { return 1.0 / x; }
 #else
 __device__ __forceinline__ double rcp_fast(double x) {
   double y;
@@ -47,6 +48,13 @@ __device__ __forceinline__ double rcp_fast(double x) {
   double e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+// one Newton step: relative error ~2^-44, for quadrature integrands
+__device__ __forceinline__ double rcp_fast1(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
   return fma(y, e, y);
 }
 __device__ __forceinline__ double rsqrt_fast(double x) {

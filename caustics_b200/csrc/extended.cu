@@ -146,14 +146,16 @@ __global__ void __launch_bounds__(32) k_contours_staged(ExtCfg cfg, ExtBuf b, Le
 }
 template <int NL>
 __global__ void __launch_bounds__(NT) k_ld_pq(ExtCfg cfg, ExtBuf b, LensConst L) {
-  // grid-stride over (vertex, source) with the sources that are actually integrated fastest: with the
-  // gate on, the grid would otherwise be sized for every point of the light curve and ~95 % of its CTAs
-  // would start only to exit (VMAX * S < 2^31 is checked by the driver)
-  const unsigned ns = (unsigned)nsrc(cfg, b);
-  const unsigned total = (unsigned)cfg.VMAX * ns;
+  // grid-stride over the (source, vertex) pairs of the sources that are actually integrated (with the
+  // gate on, a grid sized for every point of the light curve would start ~95 % of its CTAs only to
+  // exit), vertices fastest: a warp takes 32 consecutive vertices of ONE source, so it is either full
+  // or past that source's vertex count -- the arithmetic (2 x npts_ld lens-equation evaluations per
+  // vertex) dwarfs the strided 16-byte loads.  (VMAX * S < 2^31 is checked by the driver.)
+  const unsigned ns = (unsigned)nsrc(cfg, b), vmax = (unsigned)cfg.VMAX;
+  const unsigned total = vmax * ns;
   for (unsigned g = blockIdx.x * NT + threadIdx.x; g < total; g += gridDim.x * NT) {
-    const unsigned v = g / ns;
-    ld_pq_item<NL>(cfg, b, L, (int)v, (int64_t)(g - v * ns));
+    const unsigned s = g / vmax;
+    ld_pq_item<NL>(cfg, b, L, (int)(g - s * vmax), (int64_t)s);
   }
 }
 __global__ void __launch_bounds__(NT) k_ld_sum(ExtCfg cfg, ExtBuf b) {

@@ -914,17 +914,20 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
 // inside the disk, 1 - sqrt(1 - 1/r^2) outside.
 template <int NL>
 __device__ __forceinline__ double brightness(const LensConst& L, cd z, cd w0, double inv_rho2, double u1) {
+  // lens equation with one-Newton reciprocals (2^-44): this is a quadrature integrand
   cd s1 = mk(0, 0);
   const cd zb = conj(z);
-  if (NL == 1) s1 = crecip(zb);
-  else {
 #pragma unroll
-    for (int j = 0; j < NL; ++j) s1 = s1 + L.eps[j] * crecip(zb - conj(L.r[j]));
+  for (int j = 0; j < (NL == 1 ? 1 : NL); ++j) {
+    const cd d = NL == 1 ? zb : zb - conj(L.r[j]);
+    const double inv = (NL == 1 ? 1.0 : L.eps[j]) * rcp_fast1(norm2(d));
+    s1 = mk(fma(d.re, inv, s1.re), fma(-d.im, inv, s1.im));
   }
   const double r2 = norm2((z - s1) - w0) * inv_rho2;
-  // one branch-free square root for both sides of the limb (integrate.py:37-43)
+  // one branch-free square root for both sides of the limb (integrate.py:37-43); sqrt_fast returns 0
+  // for a non-positive argument, which is the reference's clamp
   const bool inside = r2 <= 1.0;
-  const double q = sqrt_fast(fmax(inside ? 1.0 - r2 : 1.0 - rcp_fast(fmax(r2, 1.0)), 0.0));
+  const double q = sqrt_fast(inside ? 1.0 - r2 : 1.0 - rcp_fast1(r2));
   const double B = inside ? 1.0 + q : 1.0 - q;
   return 3.0 / (3.0 - u1) * (u1 * B + 1.0 - 2.0 * u1);
 }
