@@ -116,7 +116,6 @@ def main():
             emit("C3 CPU oracle (NumPy restatement + reference solver), 1 core, every 100th point", "evals/s", len(sub), dt)
     if want("C4"):
         n = 100_000
-        hp3 = dict(s=2 * 0.698, q=0.9687 / 0.02809, q3=0.1, r3=0.95, psi=-1.59)   # placeholder mapping not used
         # C4 lens is given in low-level parameters -> call the C ABI directly
         w = torch.from_numpy(np.linspace(-2, 2, n) + 0.1j).cuda()
         lens_c = cb.point_source._c_lens(3, 0.0, **C2P)
