@@ -439,3 +439,26 @@ def test_contour_invariants(cb, g, rho):
             area_sum[s] += cpar[cid, s] * 0.5 * np.sum(x[:-1] * y[1:] - x[1:] * y[:-1])
     mags = cb.mag_extended_source(w, rho, nlenses=3, npts_limb=200, **HP3).cpu().numpy()
     assert np.allclose(np.abs(area_sum) / (np.pi * rho**2), mags, rtol=1e-9)
+
+
+def test_cuda_graph_capture(cb, g):
+    """SURVEY 8b (ownership): the launchers only enqueue on the caller's stream -- no allocation, no
+    synchronisation, no host round trip -- so whole calls can be captured in a CUDA graph and replayed
+    on new inputs (what an HMC loop does with a fixed-size light curve)."""
+    w = torch.from_numpy(g["b_w_0.01"].copy()).cuda()
+    kw = dict(nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7, npts_ld=100, **HP2)
+    cb.mag_point_source(w, nlenses=2, **HP2); cb.mag(w, 1e-2, **kw); cb.mag_extended_source(w, 1e-2, **kw)   # warm-up
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ps = cb.mag_point_source(w, nlenses=2, **HP2)
+        ext = cb.mag_extended_source(w, 1e-2, **kw)
+        lc = cb.mag(w, 1e-2, **kw)
+    w2 = torch.from_numpy(g["b_w_0.001"].copy()).cuda() * 0.5 + w * 0.5
+    w.copy_(w2)
+    graph.replay()
+    torch.cuda.synchronize()
+    got = [t.clone() for t in (ps, ext, lc)]
+    want = (cb.mag_point_source(w2, nlenses=2, **HP2), cb.mag_extended_source(w2, 1e-2, **kw), cb.mag(w2, 1e-2, **kw))
+    for a, b_ in zip(got, want):
+        assert torch.equal(a, b_)
