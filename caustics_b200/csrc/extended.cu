@@ -194,6 +194,12 @@ __global__ void __launch_bounds__(NT) k_gate(const double2* w_in, double* mag, u
                       (int64_t)blockIdx.x * NT + threadIdx.x);
 }
 
+// a piece of a host-computed table passed by value (kernel arguments are copied at enqueue / capture)
+struct TabChunk { static constexpr int N = 256; double v[N]; };
+__global__ void k_store_table(TabChunk c, double* dst, int m) {
+  if ((int)threadIdx.x < m) dst[threadIdx.x] = c.v[threadIdx.x];
+}
+
 // fills list = 0..n-1 and count = n (nlenses != 2: full integration everywhere, lightcurve.py:226-227)
 __global__ void k_iota(int32_t* list, int32_t* count, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,14 +297,19 @@ static int ext_driver(const void* w, double* mag, uint8_t* test_out, int64_t n, 
   int32_t* list = (int32_t*)(base + lay.list);
   int32_t* count = (int32_t*)(base + lay.count);
   if (cfg.ld) {
-    // Gauss-Legendre tables: computed on the host, copied with the stream (pageable source: the copy
-    // is staged before the call returns, so the stack buffer may go out of scope)
+    // Gauss-Legendre tables: computed on the host and handed to the device as KERNEL ARGUMENTS, 256
+    // doubles per launch.  (A cudaMemcpyAsync from this stack buffer would be fine eagerly, but a
+    // captured CUDA graph would replay the copy from a dead host address.)
     double tab[2 * 2048];
     const int nn = cfg.n1 + cfg.n2;
     leggauss(cfg.n1, tab, tab + nn);
     leggauss(cfg.n2, tab + cfg.n1, tab + nn + cfg.n1);
-    cudaError_t e = cudaMemcpyAsync(base + lay.gl, tab, (size_t)nn * 16, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return cuda_rc(e);
+    for (int off = 0; off < 2 * nn; off += TabChunk::N) {
+      TabChunk c;
+      const int m = 2 * nn - off < TabChunk::N ? 2 * nn - off : TabChunk::N;
+      memcpy(c.v, tab + off, (size_t)m * sizeof(double));
+      k_store_table<<<1, TabChunk::N, 0, st>>>(c, (double*)(base + lay.gl) + off, m);
+    }
   }
   if (gate && lens->nlenses == 2) {
     cudaError_t e = cudaMemsetAsync(count, 0, 4, st);

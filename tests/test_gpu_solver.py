@@ -237,3 +237,18 @@ def test_pathological_inputs_terminate(cb):
     keep = np.setdiff1d(np.arange(256), [3, 40, 77, 100, 130])
     assert np.array_equal(out[keep], ref[keep])
     assert np.abs(out[100]).min() < 1e-300      # the root at the origin
+
+
+def test_poly_roots_under_cuda_graph(cb, ea_golden):
+    """the launcher only enqueues: capture once, replay on new coefficients"""
+    c = torch.from_numpy(np.ascontiguousarray(ea_golden["rand5_coeffs"])).cuda()
+    cb.poly_roots(c, itmax=2500)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        z = cb.poly_roots(c, itmax=2500)
+        zc = cb.poly_roots(c, itmax=2500, compensated=True)
+    c.mul_(1.5 - 0.25j).add_(0.01)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(z, cb.poly_roots(c, itmax=2500)) and torch.equal(zc, cb.poly_roots(c, itmax=2500, compensated=True))

@@ -114,3 +114,36 @@ def test_light_curve_log_likelihood_closure(g):
     (bo,), lo = olc.marginalized_log_likelihood([Afull], [f], [1 / sig**2])
     assert np.allclose(beta, bo, rtol=1e-10) and abs(ll - lo) < 1e-9 * abs(lo)
     assert abs(beta[0] - 2.5) < 0.01 and abs(beta[1] - 0.4) < 0.01
+
+
+@pytest.mark.gpu
+def test_closure_under_cuda_graph(g):
+    """trajectory -> mag -> likelihood captured once, replayed with new times/fluxes: the per-step cost of
+    an HMC likelihood is one graph launch and one 24-byte read"""
+    import torch
+    import caustics_b200 as cb
+    from caustics_b200.lightcurve import _loglike_device
+    hp = dict(s=0.9, q=0.2)
+    tp = dict(t0=0.7, tE=20.0, u0=0.1, piEE=0.0, piEN=0.0)
+    traj = cb.AnnualParallaxTrajectory()
+    t = torch.linspace(-25.0, 25.0, 300, dtype=torch.float64, device="cuda")
+    f = torch.empty_like(t)
+    cinv = torch.full_like(t, 1e4)
+    kw = dict(nlenses=2, npts_limb=100, limb_darkening=True, u1=0.3, npts_ld=50, **hp)
+
+    def eager(tt, ff):
+        A = cb.mag(traj.compute(tt, **tp), 1e-2, **kw)
+        return A, _loglike_device(A, ff, cinv)
+
+    A0, _ = eager(t, f)
+    f.copy_(2.5 * A0 + 0.4)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        A, out = eager(t, f)
+    t.add_(0.37)                       # new times -> new trajectory, new magnifications
+    f.mul_(1.01)
+    graph.replay()
+    torch.cuda.synchronize()
+    A_want, out_want = eager(t, f)
+    assert torch.equal(A, A_want) and torch.equal(out, out_want)
