@@ -95,7 +95,8 @@ def main():
         # f3: one likelihood evaluation = trajectory -> mag -> marginalised likelihood, wall clock incl.
         # the single 24-byte read-back (what an HMC step calls)
         tt = torch.linspace(-40.0, 40.0, n, dtype=torch.float64, device="cuda")
-        tp = dict(t0=0.0, tE=20.0, u0=0.1, piEE=0.0, piEN=0.0)
+        # psi = atan2(piEE, piEN) = pi/2: u = tau - 0.1i, the mirror image of the C3 trajectory (no parallax tables)
+        tp = dict(t0=0.0, tE=20.0, u0=0.1, piEE=1e-12, piEN=0.0)
         traj = cb.AnnualParallaxTrajectory()
         A0 = cb.mag(traj.compute(tt, **tp), 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7, npts_ld=100, **HP2)
         fobs = 2.0 * A0 + 0.5
