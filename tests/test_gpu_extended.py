@@ -462,3 +462,31 @@ def test_cuda_graph_capture(cb, g):
     want = (cb.mag_point_source(w2, nlenses=2, **HP2), cb.mag_extended_source(w2, 1e-2, **kw), cb.mag(w2, 1e-2, **kw))
     for a, b_ in zip(got, want):
         assert torch.equal(a, b_)
+
+
+def test_degenerate_inputs(cb, g):
+    """empty batches, scalars, and non-finite / far-away source positions: no hang (itmax bounds every
+    solve), no out-of-range access (run under compute-sanitizer in the round's GPU check), finite
+    neighbours unaffected"""
+    kw = dict(nlenses=2, npts_limb=200, **HP2)
+    for fn in (cb.mag_point_source, lambda w, **k: cb.mag_extended_source(w, 1e-2, **k), lambda w, **k: cb.mag(w, 1e-2, **k)):
+        kk = dict(nlenses=2, **HP2) if fn is cb.mag_point_source else kw
+        assert np.asarray(fn(np.zeros(0, complex), **kk)).shape == (0,)
+        assert np.asarray(fn(0.3 + 0.1j, **kk)).shape == ()
+        assert np.asarray(fn(np.full((2, 3), 0.3 + 0.1j), **kk)).shape == (2, 3)
+    good = g["b_w_0.01"][:6]
+    w = np.concatenate([good, [complex(np.nan, 0.0), complex(np.inf, 1.0), 1e8 + 1e8j, 1e-300 + 0j, 0j]])
+    ref = cb.mag_extended_source(good, 1e-2, limb_darkening=True, u1=0.5, **kw)
+    for itmax in (2500, 30):
+        out = cb.mag_extended_source(w, 1e-2, limb_darkening=True, u1=0.5, roots_itmax=itmax, **kw)
+        assert out.shape == w.shape
+        if itmax == 2500:
+            assert np.array_equal(out[:6], ref)
+            assert abs(out[8] - 1.0) < 1e-6                  # very far from the lens: unmagnified
+            assert np.isfinite(out[9:]).all() and (out[9:] > 1).all()
+    lc, used = cb.mag(w, 1e-2, limb_darkening=True, u1=0.5, return_test=True, **kw)
+    assert lc.shape == w.shape and np.isfinite(lc[:6]).all()
+    ps = cb.mag_point_source(w, nlenses=2, **HP2)
+    assert np.isfinite(ps[:6]).all() and abs(ps[8] - 1.0) < 1e-12
+    t3 = cb.mag_extended_source(np.array([complex(np.nan, np.nan), 0.1 + 0.1j]), 1e-2, nlenses=3, npts_limb=200, **HP3)
+    assert np.isfinite(t3[1])
