@@ -229,6 +229,8 @@ def _images_point_source_sequential(w, nlenses=2, roots_itmax=2500, roots_compen
 def mag_point_source(w, nlenses=2, roots_itmax=2500, roots_compensated=False, flags=0, **params):
     """Point-source magnification at source positions `w` (complex128, any shape); high-level
     parameters s, q[, q3, r3, psi] as in the reference (point_source.py:1762-1830)."""
+    if not isinstance(w, (torch.Tensor, np.ndarray)):
+        w = np.asarray(w, dtype=np.complex128)      # Python scalars / lists
     xp = _xp(w)
     if nlenses == 1:
         z, mask = _images_point_source(w, nlenses=1)

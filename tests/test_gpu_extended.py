@@ -482,7 +482,7 @@ def test_degenerate_inputs(cb, g):
         assert out.shape == w.shape
         if itmax == 2500:
             assert np.array_equal(out[:6], ref)
-            assert abs(out[8] - 1.0) < 1e-6                  # very far from the lens: unmagnified
+            assert abs(out[8] - 1.0) < 1e-3                  # very far from the lens: unmagnified (200-gon area)
             assert np.isfinite(out[9:]).all() and (out[9:] > 1).all()
     lc, used = cb.mag(w, 1e-2, limb_darkening=True, u1=0.5, return_test=True, **kw)
     assert lc.shape == w.shape and np.isfinite(lc[:6]).all()
