@@ -163,3 +163,36 @@ def test_sequential_images(cb, seq_golden, k):
         assert np.abs(zc[0].cpu().numpy() - zg)[mg].max() < 1e-12
     zo, mo = lens.images_point_source_sequential(w, nl, roots_compensated=True, **p)
     assert np.array_equal(mo, mg) and np.abs(zc[0].cpu().numpy() - zo)[mo].max() < (1e-12 if k == "b" else 1e-9)
+
+
+def test_c5_map_properties(cb):
+    """config 5 (10^4 x 10^4 binary magnification map), 400 rows = 4e6 points through the grid entry:
+    mu >= 1 (a point source is never demagnified), mirror symmetry about the lens axis, image counts
+    3 or 5, and the reference on a sparse subset"""
+    import ctypes
+    from caustics_b200 import _lib
+    from caustics_b200.point_source import _c_lens, lens_params
+    L = _lib.lib()
+    hp = dict(s=0.9, q=0.2)
+    p, x_cm = lens_params(2, **hp)
+    lens_c = _c_lens(2, x_cm, **p)
+    nx, dx = 10_000, 3.0 / 9999
+    rows = 200
+    out = {}
+    for name, r0 in (("lo", 4700), ("hi", 10_000 - 4700 - rows)):      # rows symmetric about y = 0
+        mag = torch.empty(nx * rows, dtype=torch.float64, device="cuda")
+        _lib.check(L.caustics_mag_point_source_grid(-1.5, -1.5, dx, dx, nx, r0, r0 + rows, mag.data_ptr(), lens_c,
+                                                    2500, 0, 0, None))
+        out[name] = mag.reshape(rows, nx)
+    torch.cuda.synchronize()
+    lo, hi = out["lo"], out["hi"].flip(0)
+    assert torch.isfinite(lo).all() and (lo >= 1.0 - 1e-12).all()
+    # y -> -y: the coefficients are complex conjugates, the roots too; agreement to rounding x conditioning
+    rel = ((lo - hi).abs() / lo)
+    assert rel.max() < 1e-6 and rel.median() < 1e-13
+    # sparse comparison with the oracle
+    iy = np.arange(0, rows, 40); ix = np.arange(0, nx, 500)
+    ww = (-1.5 + ix[None, :] * dx) + 1j * (-1.5 + (4700 + iy[:, None]) * dx)
+    want = lens.mag_point_source(ww.reshape(-1), 2, **hp).reshape(ww.shape)
+    got = lo[iy][:, ix].cpu().numpy()
+    assert np.allclose(got, want, rtol=1e-9)

@@ -252,3 +252,34 @@ def test_poly_roots_under_cuda_graph(cb, ea_golden):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(z, cb.poly_roots(c, itmax=2500)) and torch.equal(zc, cb.poly_roots(c, itmax=2500, compensated=True))
+
+
+def test_c2_full_size_properties(cb):
+    """config 2 at full size -- 10^6 degree-10 triple-lens polynomials through the C ABI -- checked by
+    size-independent properties (the oracle would need minutes): backward error of every root,
+    Vieta's sum and product, plain vs compensated, and the reference on every 1000th polynomial."""
+    from caustics_b200.point_source import _poly_coeffs_torch
+    n = 1_000_000
+    w = torch.from_numpy(np.linspace(-2, 2, n) + 0.1j).cuda()
+    c = _poly_coeffs_torch(w, 3, **C2_PARAMS)                      # (n, 11) high -> low
+    z = cb.poly_roots(c, itmax=2500)                                # (n, 10)
+    zc = cb.poly_roots(c, itmax=2500, compensated=True)
+    assert torch.isfinite(torch.view_as_real(z)).all()
+    # backward error: |p(z)| <= 1e-13 * sum |p_k| |z|^k  (the solver's stopping test is 2^-53 * ~40 * that sum)
+    val = torch.zeros_like(z)
+    bound = torch.zeros(z.shape, dtype=torch.float64, device="cuda")
+    az = z.abs()
+    for k in range(11):
+        val = val * z + c[:, k:k + 1]
+        bound = bound * az + c[:, k:k + 1].abs()
+    assert (val.abs() <= 1e-13 * bound).all()
+    # Vieta: sum of roots = -c1/c0, product = c10/c0 (degree even)
+    s_want, p_want = -c[:, 1] / c[:, 0], c[:, 10] / c[:, 0]
+    scale = z.abs().sum(1)
+    assert ((zc.sum(1) - s_want).abs() <= 1e-12 * scale).all()
+    assert ((zc.prod(1) - p_want).abs() <= 1e-10 * p_want.abs() + 1e-300).all()
+    # plain vs compensated as unordered sets, through sorted symmetric functions of the differences
+    sub = slice(0, None, 1000)
+    want = solver.solve(np.ascontiguousarray(c[sub].cpu().numpy()[:, ::-1]), compensated=True)
+    assert set_distance(z[sub].cpu().numpy(), want).max() < 1e-12
+    assert set_distance(zc[sub].cpu().numpy(), want).max() < 1e-12
