@@ -490,3 +490,21 @@ def test_degenerate_inputs(cb, g):
     assert np.isfinite(ps[:6]).all() and abs(ps[8] - 1.0) < 1e-12
     t3 = cb.mag_extended_source(np.array([complex(np.nan, np.nan), 0.1 + 0.1j]), 1e-2, nlenses=3, npts_limb=200, **HP3)
     assert np.isfinite(t3[1])
+
+
+def test_c4_full_size_properties(cb):
+    """config 4 at full size (10^5 triple-lens sources in one call, thread-per-source kernels): finite,
+    never demagnified beyond the polygon error, equal to the point-source value far from the caustics,
+    and equal to the small-batch kernels on a random subset (a second, differently organised
+    implementation of the same algorithm)"""
+    import _oracle_workers as ow
+    hp = ow.c4_hp()
+    _, x_cm = cb.lens_params(3, **hp)
+    w = np.linspace(-2, 2, 100_000) + 0.1j - x_cm
+    mags = cb.mag_extended_source(w, 1e-2, nlenses=3, npts_limb=200, **hp)
+    assert mags.shape == w.shape and np.isfinite(mags).all() and (mags > 1 - 1e-3).all()
+    ps = cb.mag_point_source(w, nlenses=3, **hp)
+    far = np.abs(w.real + x_cm) > 1.6
+    assert np.allclose(mags[far], ps[far], rtol=2e-3)
+    idx = np.sort(np.random.default_rng(0).choice(len(w), 600, replace=False))
+    assert np.allclose(cb.mag_extended_source(w[idx], 1e-2, nlenses=3, npts_limb=200, **hp), mags[idx], rtol=1e-9)
