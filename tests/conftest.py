@@ -11,6 +11,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # build the oracle (C restatement; the reference's own solver when /root/reference is mounted) before
+    # collection, so that `skipif(not solver.ref_available())` sees it in a fresh checkout
+    try:
+        from oracle import solver
+        solver.build()
+    except Exception as e:  # the tests that need it fail with the real error
+        print(f"[conftest] oracle build failed: {e!r}")
 
 
 @pytest.fixture(scope="session")
