@@ -132,6 +132,9 @@ def other_configs(cb, L, _lib, torch):
     out["C5_mag_point_source_binary_evals_per_s"] = nx * rows / best(lambda: _lib.check(
         L.caustics_mag_point_source_grid(-1.5, -1.5, 3.0 / 9999, 3.0 / 9999, nx, 4000, 4000 + rows, mag.data_ptr(),
                                          lens_c, 2500, 0, 0, None)))
+    out["C5_mag_point_source_binary_walk_evals_per_s"] = nx * rows / best(lambda: _lib.check(
+        L.caustics_mag_point_source_grid(-1.5, -1.5, 3.0 / 9999, 3.0 / 9999, nx, 4000, 4000 + rows, mag.data_ptr(),
+                                         lens_c, 2500, 0, 4, None)))     # CAUSTICS_FLAG_GRID_WALK
     n4 = 100_000
     w4 = torch.from_numpy(np.linspace(-2, 2, n4) + 0.1j).cuda()
     lens3 = cb.point_source._c_lens(3, 0.0, **LENS)

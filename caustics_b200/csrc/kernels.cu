@@ -10,6 +10,8 @@
 #include "../../include/caustics_b200.h"
 #include "ea_core.cuh"
 #include "lens_core.cuh"
+#include "ps_walk.cuh"
+#include <stdlib.h>
 
 using namespace cb200;
 
@@ -235,6 +237,53 @@ ps_seq_kernel(const double2* __restrict__ w_in, double2* __restrict__ z_out, uin
       }
     }
   }
+}
+
+// Magnification map as warm-started column walks (ps_walk.cuh; CAUSTICS_FLAG_GRID_WALK).  CTA b covers
+// columns (b % ncolblk) * NTW ... and rows (b / ncolblk) * run ... of the requested row block.
+// 128-thread CTAs for the binary lens, 64 for the triple (root + previous-root planes stay < 48 KB).
+template <int NL> struct WalkNT { static constexpr int value = NL == 2 ? 128 : 64; };
+
+template <int NL, bool COMP>
+__global__ void __launch_bounds__(WalkNT<NL>::value)
+ps_grid_walk_kernel(GridSpec g, double* __restrict__ mag, int64_t nrows, int run, int64_t ncolblk, LensConst L,
+                    int itmax, int extrap) {
+  constexpr int DEG = NL * NL + 1, NTW = WalkNT<NL>::value;
+  __shared__ EASmem<DEG, COMP, NTW> sm;
+  __shared__ double pre[DEG][NTW], pim[DEG][NTW];
+  const int tid = threadIdx.x;
+  const int64_t cb = (int64_t)blockIdx.x % ncolblk, rg = (int64_t)blockIdx.x / ncolblk;
+  const int64_t ix = cb * NTW + tid, row0 = rg * run;
+  const bool active = ix < g.nx;
+  const int64_t left = nrows - row0;
+  const int nrun = left < run ? (int)left : run;
+  double wx = active ? fma((double)ix, g.dx, g.x0) : 0.3;
+  wx += L.x_cm;
+  ps_grid_walk_body<NL, COMP, NTW>(wx, g.y0, g.dy, g.row_begin + row0, nrun, mag + row0 * g.nx + (active ? ix : 0), g.nx,
+                                   L, itmax, extrap != 0, sm, &pre[0][tid], &pim[0][tid], tid, active);
+}
+
+// rows per walk: 32 when the map is large enough to fill the machine several times over, shorter walks
+// (more CTAs) for small maps; CAUSTICS_B200_GRID_RUN overrides (experiments)
+int grid_walk_run(int64_t ncolblk, int64_t nrows) {
+  if (const char* e = getenv("CAUSTICS_B200_GRID_RUN")) { const int v = atoi(e); if (v >= 1 && v <= 4096) return v; }
+  int run = 32;
+  while (run > 4 && ncolblk * ((nrows + run - 1) / run) < 148 * 16) run >>= 1;
+  return run;
+}
+
+template <int NL>
+int launch_grid_walk(GridSpec g, double* mag, int64_t nrows, const LensConst& L, int itmax, int compensated, cudaStream_t st) {
+  constexpr int NTW = WalkNT<NL>::value;
+  const int64_t ncolblk = (g.nx + NTW - 1) / NTW;
+  const int run = grid_walk_run(ncolblk, nrows);
+  const int64_t nblk = ncolblk * ((nrows + run - 1) / run);
+  if (nblk > 0x7fffffffLL) return CAUSTICS_ERR_BAD_ARG;
+  const char* e = getenv("CAUSTICS_B200_GRID_EXTRAP");
+  const int extrap = e ? atoi(e) : 1;
+  if (compensated) ps_grid_walk_kernel<NL, true><<<(unsigned)nblk, NTW, 0, st>>>(g, mag, nrows, run, ncolblk, L, itmax, extrap);
+  else ps_grid_walk_kernel<NL, false><<<(unsigned)nblk, NTW, 0, st>>>(g, mag, nrows, run, ncolblk, L, itmax, extrap);
+  return cuda_rc(cudaGetLastError());
 }
 
 int make_lens_const(const caustics_lens* lens, LensConst* out) {
@@ -581,6 +630,9 @@ int caustics_mag_point_source_grid(double x0, double y0, double dx, double dy, i
   if (!mag) return CAUSTICS_ERR_BAD_ARG;
   GridSpec g; g.x0 = x0; g.y0 = y0; g.dx = dx; g.dy = dy; g.nx = nx; g.row_begin = row_begin; g.use = 1;
   cudaStream_t st = (cudaStream_t)stream;
+  if (flags & CAUSTICS_FLAG_GRID_WALK)
+    return L.nlenses == 2 ? launch_grid_walk<2>(g, mag, row_end - row_begin, L, itmax, compensated, st)
+                          : launch_grid_walk<3>(g, mag, row_end - row_begin, L, itmax, compensated, st);
   if (L.nlenses == 2)
     return launch_ps<2, PS_MAG>(nullptr, g, nullptr, nullptr, nullptr, mag, nullptr, n, L, itmax, compensated, 0, flags, st);
   return launch_ps<3, PS_MAG>(nullptr, g, nullptr, nullptr, nullptr, mag, nullptr, n, L, itmax, compensated, 0, flags, st);

@@ -46,6 +46,7 @@ extern "C" {
  * coefficients stored low->high as the reference primitive expects. */
 #define CAUSTICS_FLAG_INIT_BINI 1         /* intended complex Bini estimates: 10-30 % fewer updates, other root order */
 #define CAUSTICS_FLAG_COEFFS_HIGH_FIRST 2 /* coeffs rows are high->low (saves poly_roots' flip, primitive.py:73) */
+#define CAUSTICS_FLAG_GRID_WALK 4         /* caustics_mag_point_source_grid only: warm-started walks along y (below) */
 
 /* Low-level lens parameters, exactly the reference's `_params` dict plus the centre-of-mass shift
  * its public functions add to the source positions (point_source.py:1796-1819).
@@ -165,7 +166,13 @@ int caustics_mag_point_source(const void* w, double* mag, uint8_t* nimages, int6
                               const caustics_lens* lens, int itmax, int compensated, int flags,
                               void* stream);
 /* magnification map: w generated on the fly, w[iy*nx + ix] = (x0 + ix*dx) + i (y0 + iy*dy),
- * rows [row_begin, row_end) written to mag[(iy-row_begin)*nx + ix]. */
+ * rows [row_begin, row_end) written to mag[(iy-row_begin)*nx + ix].
+ * flags & CAUSTICS_FLAG_GRID_WALK: each thread walks a column segment of up to 32 rows, starting every
+ * solve after the first from the extrapolated roots of the rows before -- the reference's custom_init
+ * warm start (point_source.py:1711-1759) applied to a regular map; ~3x fewer root updates.  Every
+ * root still passes the solver's own stopping test, but the iteration path differs from a cold solve,
+ * so a pixel agrees with the default entry to rounding x conditioning (<= 1e-10 relative away from
+ * caustics) rather than bit for bit, and depends on where row_begin cuts the map. */
 int caustics_mag_point_source_grid(double x0, double y0, double dx, double dy, int64_t nx,
                                    int64_t row_begin, int64_t row_end, double* mag,
                                    const caustics_lens* lens, int itmax, int compensated,

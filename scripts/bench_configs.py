@@ -71,7 +71,7 @@ def main():
         w = torch.from_numpy(np.linspace(-2, 2, n) + 0.1j).cuda()
         lens_c = cb.point_source._c_lens(3, 0.0, **C2P)
         mag = torch.empty(n, dtype=torch.float64, device="cuda")
-        for flags in (0, 1):
+        for flags in (0, 1, 4):      # 4 = CAUSTICS_FLAG_GRID_WALK (warm-started column walks)
             t = timeit(lambda: _lib.check(L.caustics_mag_point_source(w.data_ptr(), mag.data_ptr(), None, n, lens_c, 2500, 0, flags, None)))
             emit(f"C2 fused mag_point_source triple n={n} flags={flags}", "evals/s", n, t)
         c = _poly_coeffs_torch(torch.from_numpy(np.linspace(-2, 2, n) + 0.1j).cuda(), 3, **C2P)
@@ -131,7 +131,7 @@ def main():
         p, x_cm = lens_params(2, **HP2)
         lens_c = cb.point_source._c_lens(2, x_cm, **p)
         mag = torch.empty(nx * rows, dtype=torch.float64, device="cuda")
-        for flags in (0, 1):
+        for flags in (0, 1, 4):      # 4 = CAUSTICS_FLAG_GRID_WALK (warm-started column walks)
             t = timeit(lambda: _lib.check(L.caustics_mag_point_source_grid(-1.5, -1.5, 3.0 / 9999, 3.0 / 9999, nx, 4000, 4000 + rows, mag.data_ptr(), lens_c, 2500, 0, flags, None)), reps=3, warm=1)
             emit(f"C5 magnification map rows 4000-6000 of 10^4x10^4 flags={flags}", "evals/s", nx * rows, t)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -2,6 +2,7 @@
 #include "cuda_shim.h"
 #include "../../caustics_b200/csrc/ea_core.cuh"
 #include "../../caustics_b200/csrc/lens_core.cuh"
+#include "../../caustics_b200/csrc/ps_walk.cuh"
 using namespace cb200;
 
 template <int DEG, bool COMP>
@@ -63,6 +64,37 @@ int hostsim_mag_ps(const double* w, double* mag, double* coeffs_out, int64_t n, 
   else return 1;
   return 0;
 }
+}
+
+// the map walk of ps_walk.cuh, one column at a time (the kernel's CTA/lanes only decide which thread
+// owns which column segment)
+template <int NL, bool COMP>
+static void grid_walk_all(double x0, double y0, double dx, double dy, int64_t nx, int64_t row_begin, int64_t row_end,
+                          double* mag, const LensConst& L, int itmax, int run, int extrap) {
+  constexpr int DEG = NL * NL + 1;
+  static EASmem<DEG, COMP, 1> sm;
+  double pre[DEG], pim[DEG];
+  const int64_t nrows = row_end - row_begin;
+  for (int64_t row0 = 0; row0 < nrows; row0 += run)
+    for (int64_t ix = 0; ix < nx; ++ix) {
+      const int nrun = (int)std::min<int64_t>(run, nrows - row0);
+      const double wx = fma((double)ix, dx, x0) + L.x_cm;
+      ps_grid_walk_body<NL, COMP, 1>(wx, y0, dy, row_begin + row0, nrun, mag + row0 * nx + ix, nx, L, itmax, extrap != 0,
+                                     sm, pre, pim, 0, true);
+    }
+}
+extern "C" int hostsim_grid_walk(double x0, double y0, double dx, double dy, int64_t nx, int64_t row_begin, int64_t row_end,
+                                 double* mag, int nlenses, const double* eps, const double* r, const double* H,
+                                 const double* G, double x_cm, int itmax, int comp, int run, int extrap) {
+  LensConst L; memset(&L, 0, sizeof(L));
+  L.nlenses = nlenses; L.x_cm = x_cm;
+  for (int i = 0; i < 3; ++i) { L.eps[i] = eps[i]; L.r[i] = mk(r[2 * i], r[2 * i + 1]); }
+  for (int i = 0; i < 4; ++i) L.H[i] = mk(H[2 * i], H[2 * i + 1]);
+  for (int i = 0; i < 3; ++i) L.G[i] = mk(G[2 * i], G[2 * i + 1]);
+  if (nlenses == 2) { if (comp) grid_walk_all<2, true>(x0, y0, dx, dy, nx, row_begin, row_end, mag, L, itmax, run, extrap); else grid_walk_all<2, false>(x0, y0, dx, dy, nx, row_begin, row_end, mag, L, itmax, run, extrap); }
+  else if (nlenses == 3) { if (comp) grid_walk_all<3, true>(x0, y0, dx, dy, nx, row_begin, row_end, mag, L, itmax, run, extrap); else grid_walk_all<3, false>(x0, y0, dx, dy, nx, row_begin, row_end, mag, L, itmax, run, extrap); }
+  else return 1;
+  return 0;
 }
 
 // ---- kernel family 3 (extended source): the phase bodies driven sequentially over the sources ----

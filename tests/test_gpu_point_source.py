@@ -196,3 +196,43 @@ def test_c5_map_properties(cb):
     want = lens.mag_point_source(ww.reshape(-1), 2, **hp).reshape(ww.shape)
     got = lo[iy][:, ix].cpu().numpy()
     assert np.allclose(got, want, rtol=1e-9)
+
+
+@pytest.mark.parametrize("nl,hp,r0", [(2, dict(s=0.9, q=0.2), 5250), (3, dict(s=0.9, q=0.2, q3=0.1, r3=0.8, psi=1.0), 6150)])
+def test_map_walk(cb, nl, hp, r0):
+    """CAUSTICS_FLAG_GRID_WALK (csrc/ps_walk.cuh): the C5 map solved as warm-started column walks against
+    the cold per-pixel kernel on 100 full-width rows that cross the caustic (10^6 pixels), and against the
+    oracle on a sparse subset"""
+    nx, dx, rows = 10_000, 3.0 / 9999, 100
+    cold = cb.mag_point_source_map(-1.5, -1.5, dx, dx, nx, nx, nlenses=nl, rows=(r0, r0 + rows), walk=False, **hp)
+    walk = cb.mag_point_source_map(-1.5, -1.5, dx, dx, nx, nx, nlenses=nl, rows=(r0, r0 + rows), walk=True, **hp)
+    assert cold.shape == walk.shape == (rows, nx)
+    assert cold.max().item() > 30                       # caustic crossings are in the block
+    rel = ((walk - cold).abs() / cold).reshape(-1)
+    assert torch.isfinite(walk).all() and (walk >= 1.0 - 1e-12).all()
+    # rounding x conditioning: the bound the cold kernel meets against its own mirror image (test_c5_map_properties)
+    assert rel.median().item() < 1e-13 and rel.max().item() < 1e-6
+    assert (rel > 1e-10).float().mean().item() < 2e-3
+    iy = np.arange(0, rows, 9); ix = np.arange(0, nx, 250)
+    ww = (-1.5 + ix[None, :] * dx) + 1j * (-1.5 + (r0 + iy[:, None]) * dx)
+    want = lens.mag_point_source(ww.reshape(-1), nl, **hp).reshape(ww.shape)
+    assert np.allclose(walk[iy][:, ix].cpu().numpy(), want, rtol=1e-9)
+
+
+def test_map_walk_shapes(cb):
+    """walks shorter than a run, row counts the run length does not divide, widths below one CTA, a
+    compensated solve, an empty block; every pixel against the cold kernel"""
+    hp = dict(s=0.9, q=0.2)
+    dx = 3.0 / 9999
+    for nx, ny, rows in ((257, 64, (10, 30)), (5, 200, (0, 200)), (1000, 37, (0, 37)), (129, 3, (1, 2))):
+        kw = dict(nlenses=2, rows=rows, **hp)
+        a = cb.mag_point_source_map(-0.2, 0.05, dx, dx, nx, ny, walk=False, **kw)
+        b = cb.mag_point_source_map(-0.2, 0.05, dx, dx, nx, ny, walk=True, **kw)
+        assert a.shape == b.shape == (rows[1] - rows[0], nx)
+        assert torch.allclose(a, b, rtol=1e-7, atol=0) and ((a - b).abs() / a).median().item() < 1e-13
+    c = cb.mag_point_source_map(-0.2, 0.05, dx, dx, 257, 64, nlenses=2, roots_compensated=True, **hp)
+    d = cb.mag_point_source_map(-0.2, 0.05, dx, dx, 257, 64, nlenses=2, roots_compensated=True, walk=False, **hp)
+    assert torch.allclose(c, d, rtol=1e-7, atol=0)
+    assert cb.mag_point_source_map(-0.2, 0.05, dx, dx, 257, 64, nlenses=2, rows=(5, 5), **hp).shape == (0, 257)
+    with pytest.raises(ValueError):
+        cb.mag_point_source_map(0, 0, dx, dx, 10, 10, nlenses=1)

@@ -122,3 +122,61 @@ def test_chain_split_limb_walk(hs, g):
         assert np.allclose(hs_ext(hs, wl, 1e-2, 2, HP2, gate=True)[0], want, rtol=1e-4)
     finally:
         hs.hostsim_set_chains(1)
+
+
+def hs_grid_walk(lib, x0, y0, dx, dy, nx, r0, r1, nl, hp, run=32, extrap=1, comp=False):
+    p, xcm = lens.lens_params(nl, **hp)
+    eps, r, H, G = lens_const(nl, **p)
+    mag = np.zeros((r1 - r0, nx))
+    rc = lib.hostsim_grid_walk(D_(x0), D_(y0), D_(dx), D_(dy), ctypes.c_int64(nx), ctypes.c_int64(r0), ctypes.c_int64(r1),
+                               mag.ctypes.data_as(vp), nl, eps.ctypes.data_as(vp), r.ctypes.data_as(vp),
+                               H.ctypes.data_as(vp), G.ctypes.data_as(vp), D_(xcm), 2500, int(comp), run, extrap)
+    assert rc == 0
+    return mag
+
+
+@pytest.mark.parametrize("nl,hp,col0,r0", [(2, HP2, 4290, 5300), (3, HP3, 4350, 6180)])
+def test_grid_walk(hs, nl, hp, col0, r0):
+    """ps_walk.cuh (CAUSTICS_FLAG_GRID_WALK): warm-started column walks over a magnification map give the
+    oracle's magnification at every pixel -- a patch of the C5 map that crosses the central caustic,
+    with and without extrapolation, run lengths that do and do not divide the row count"""
+    dx = 3.0 / 9999
+    nx, r1 = 40, r0 + 41
+    x0 = -1.5 + col0 * dx          # columns col0, col0 + 2, ...: a fold of the lens's caustic runs through the patch
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(r0, r1))
+    w = (x0 + ix * (2 * dx)) + 1j * (-1.5 + iy * dx)
+    want = lens.mag_point_source(w.reshape(-1), nl, **hp).reshape(w.shape)
+    assert want.max() > 20          # the patch does contain near-caustic pixels
+    for run, extrap in ((32, 1), (7, 1), (32, 0), (1, 1)):
+        got = hs_grid_walk(hs, x0, -1.5, 2 * dx, dx, nx, r0, r1, nl, hp, run=run, extrap=extrap)
+        rel = np.abs(got / want - 1)
+        # rounding x conditioning: the same bound the cold kernel is held to on this map (test_c5_map_properties)
+        assert rel.max() < 1e-9 and np.median(rel) < 1e-13, (run, extrap, rel.max())
+
+
+def test_grid_walk_sweep_counts(hs):
+    """what the walk buys: Ehrlich-Aberth sweeps per pixel from a cold start, from the previous row's roots
+    and from the linear extrapolation of the previous two rows (the device solver compiled for the host)"""
+    from test_hostsim import hs_solve
+    p, x_cm = lens.lens_params(2, **HP2)
+    dx = 3.0 / 9999
+    rng = np.random.default_rng(1)
+    xs = -1.5 + rng.integers(0, 10000, 500) * dx
+    r0 = rng.integers(0, 10000 - 8, 500)
+    sw = {"cold": [], "warm": [], "extrap": []}
+    zw = ze = ze_prev = None
+    for k in range(8):
+        c = lens.poly_coeffs(xs + 1j * (-1.5 + (r0 + k) * dx) + x_cm, 2, **p)[:, ::-1]
+        zc, s = hs_solve(hs, c, flags=1)
+        sw["cold"].append(np.abs(s).mean())
+        if k == 0:
+            zw, ze, ze_prev = zc, zc, zc
+            continue
+        zw, s = hs_solve(hs, c, custom_init=True, ri=zw, flags=1)
+        sw["warm"].append(np.abs(s).mean())
+        z2, s = hs_solve(hs, c, custom_init=True, ri=2 * ze - ze_prev, flags=1)
+        ze_prev, ze = ze, z2
+        assert (s > 0).all()
+        if k >= 2:
+            sw["extrap"].append(np.abs(s).mean())
+    assert np.mean(sw["cold"]) > 6.5 and np.mean(sw["warm"]) < 3.1 and np.mean(sw["extrap"]) < 2.15
