@@ -257,10 +257,31 @@ ps_grid_walk_kernel(GridSpec g, double* __restrict__ mag, int64_t nrows, int run
   const bool active = ix < g.nx;
   const int64_t left = nrows - row0;
   const int nrun = left < run ? (int)left : run;
-  double wx = active ? fma((double)ix, g.dx, g.x0) : 0.3;
-  wx += L.x_cm;
-  ps_grid_walk_body<NL, COMP, NTW>(wx, g.y0, g.dy, g.row_begin + row0, nrun, mag + row0 * g.nx + (active ? ix : 0), g.nx,
-                                   L, itmax, extrap != 0, sm, &pre[0][tid], &pim[0][tid], tid, active);
+  WalkColumn src;
+  src.wx = (active ? fma((double)ix, g.dx, g.x0) : 0.3) + L.x_cm;
+  src.y0 = g.y0; src.dy = g.dy; src.row_abs0 = g.row_begin + row0;
+  ps_walk_body<NL, COMP, NTW>(src, nrun, active ? nrun : 0, mag + row0 * g.nx + (active ? ix : 0), g.nx,
+                              L, itmax, extrap != 0, sm, &pre[0][tid], &pim[0][tid], tid);
+}
+
+// A 1-D array of source positions whose consecutive elements are neighbours (CAUSTICS_FLAG_PATH_WALK):
+// thread t owns elements [t * run, (t + 1) * run).
+template <int NL, bool COMP>
+__global__ void __launch_bounds__(WalkNT<NL>::value)
+ps_path_walk_kernel(const double* __restrict__ w, double* __restrict__ mag, int64_t n, int run, LensConst L,
+                    int itmax, int extrap) {
+  constexpr int DEG = NL * NL + 1, NTW = WalkNT<NL>::value;
+  __shared__ EASmem<DEG, COMP, NTW> sm;
+  __shared__ double pre[DEG][NTW], pim[DEG][NTW];
+  const int tid = threadIdx.x;
+  const int64_t first = ((int64_t)blockIdx.x * NTW + tid) * run;
+  const int64_t left = n - first;
+  const int nrun = left <= 0 ? 0 : (left < run ? (int)left : run);
+  WalkPath src;
+  src.w = w + 2 * (nrun ? first : 0);
+  src.x_cm = L.x_cm;
+  ps_walk_body<NL, COMP, NTW>(src, run, nrun, mag + (nrun ? first : 0), 1, L, itmax, extrap != 0, sm,
+                              &pre[0][tid], &pim[0][tid], tid);
 }
 
 // rows per walk: 32 when the map is large enough to fill the machine several times over, shorter walks
@@ -270,6 +291,29 @@ int grid_walk_run(int64_t ncolblk, int64_t nrows) {
   int run = 32;
   while (run > 4 && ncolblk * ((nrows + run - 1) / run) < 148 * 16) run >>= 1;
   return run;
+}
+
+// elements per thread of a path walk: long enough to amortise the cold first solve, short enough that
+// the batch still fills the machine (>= ~16 warps per SM)
+int path_walk_run(int64_t n) {
+  if (const char* e = getenv("CAUSTICS_B200_PATH_RUN")) { const int v = atoi(e); if (v >= 1 && v <= 4096) return v; }
+  int run = 32;
+  while (run > 1 && n / run < 148 * 16 * 32) run >>= 1;
+  return run;
+}
+
+template <int NL>
+int launch_path_walk(const void* w, double* mag, int64_t n, const LensConst& L, int itmax, int compensated, cudaStream_t st) {
+  constexpr int NTW = WalkNT<NL>::value;
+  const int run = path_walk_run(n);
+  const int64_t nthreads = (n + run - 1) / run;
+  const int64_t nblk = (nthreads + NTW - 1) / NTW;
+  if (nblk > 0x7fffffffLL) return CAUSTICS_ERR_BAD_ARG;
+  const char* e = getenv("CAUSTICS_B200_GRID_EXTRAP");
+  const int extrap = e ? atoi(e) : 1;
+  if (compensated) ps_path_walk_kernel<NL, true><<<(unsigned)nblk, NTW, 0, st>>>((const double*)w, mag, n, run, L, itmax, extrap);
+  else ps_path_walk_kernel<NL, false><<<(unsigned)nblk, NTW, 0, st>>>((const double*)w, mag, n, run, L, itmax, extrap);
+  return cuda_rc(cudaGetLastError());
 }
 
 template <int NL>
@@ -612,6 +656,9 @@ int caustics_mag_point_source(const void* w, double* mag, uint8_t* nimages, int6
   if (!w || !mag) return CAUSTICS_ERR_BAD_ARG;
   GridSpec g; memset(&g, 0, sizeof(g));
   cudaStream_t st = (cudaStream_t)stream;
+  if ((flags & CAUSTICS_FLAG_PATH_WALK) && !nimages && path_walk_run(n) > 1)
+    return L.nlenses == 2 ? launch_path_walk<2>(w, mag, n, L, itmax, compensated, st)
+                          : launch_path_walk<3>(w, mag, n, L, itmax, compensated, st);
   if (L.nlenses == 2)
     return launch_ps<2, PS_MAG>((const double2*)w, g, nullptr, nullptr, nullptr, mag, nimages, n, L, itmax, compensated, 0, flags, st);
   return launch_ps<3, PS_MAG>((const double2*)w, g, nullptr, nullptr, nullptr, mag, nimages, n, L, itmax, compensated, 0, flags, st);

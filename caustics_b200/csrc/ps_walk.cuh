@@ -1,4 +1,5 @@
-// Magnification map as a warm-started walk (opt-in, CAUSTICS_FLAG_GRID_WALK).
+// Point-source magnification as warm-started walks (opt-in: CAUSTICS_FLAG_GRID_WALK for maps,
+// CAUSTICS_FLAG_PATH_WALK for trajectories).
 //
 // A map pixel's lens polynomial differs from its neighbour's by O(dy), so its roots do too.  The
 // reference exploits exactly this along the limb of an extended source and along a 1-D path
@@ -12,6 +13,8 @@
 // the host, tests/test_hostsim.py::test_grid_walk).  The stopping test is the solver's own
 // (|p(z)| <= 2^-53 * sum |p_i||z|^i, ehrlich_aberth.h:109), so every returned root meets the same
 // backward-error bound as a cold solve; the image filter and the Jacobian sum are unchanged.
+// The same walk serves a 1-D array of source positions whose consecutive elements are neighbours (a
+// trajectory; CAUSTICS_FLAG_PATH_WALK): one thread owns a run of consecutive elements.
 // A warm solve that fails (no convergence within 64 sweeps, or a non-finite root because two
 // extrapolated guesses coincided) is redone cold, which also resets the extrapolation history.
 #pragma once
@@ -22,18 +25,20 @@ namespace cb200 {
 
 constexpr int PS_WALK_WARM_ITMAX = 64;
 
-// pre/pim: this thread's previous-row roots, element j at [j * NT] (only touched when extrap).
-// mag_out: this thread's first output, rows `out_stride` apart.
-template <int NL, bool COMP, int NT>
-__device__ __forceinline__ void ps_grid_walk_body(double wx, double y0, double dy, int64_t row_abs0, int nrun,
-                                                  double* mag_out, int64_t out_stride, const LensConst& L,
-                                                  int itmax, bool extrap, EASmem<NL * NL + 1, COMP, NT>& sm,
-                                                  double* pre, double* pim, int tid, bool active) {
+// pre/pim: this thread's previous-position roots, element j at [j * NT] (only touched when extrap).
+// wsrc(k) = source position k of this thread's walk (x_cm already added); mag_out: the thread's first
+// output, consecutive positions `out_stride` apart.  `nsteps` is the warp-uniform loop bound, `nrun`
+// (<= nsteps) the positions this thread really owns.
+template <int NL, bool COMP, int NT, class WSRC>
+__device__ __forceinline__ void ps_walk_body(const WSRC& wsrc, int nsteps, int nrun, double* mag_out,
+                                             int64_t out_stride, const LensConst& L, int itmax, bool extrap,
+                                             EASmem<NL * NL + 1, COMP, NT>& sm, double* pre, double* pim, int tid) {
   constexpr int DEG = NL * NL + 1;
   double* zre = &sm.zre[0][tid];
   double* zim = &sm.zim[0][tid];
-  for (int k = 0; k < nrun; ++k) {
-    const cd w = mk(wx, fma((double)(row_abs0 + k), dy, y0));
+  for (int k = 0; k < nsteps; ++k) {
+    const bool active = k < nrun;
+    const cd w = wsrc(active ? k : 0);
     cd p[DEG + 1];
     lens_poly<NL>(L, w, p);
     ea_normalise<DEG>(p);
@@ -76,5 +81,18 @@ __device__ __forceinline__ void ps_grid_walk_body(double wx, double y0, double d
     }
   }
 }
+
+// map column: position k = (wx, y0 + (row_abs0 + k) dy)
+struct WalkColumn {
+  double wx, y0, dy;
+  int64_t row_abs0;
+  __device__ __forceinline__ cd operator()(int k) const { return mk(wx, fma((double)(row_abs0 + k), dy, y0)); }
+};
+// 1-D path segment: position k = w[k] + x_cm
+struct WalkPath {
+  const double* w;   // (re, im) pairs
+  double x_cm;
+  __device__ __forceinline__ cd operator()(int k) const { return mk(w[2 * k] + x_cm, w[2 * k + 1]); }
+};
 
 }  // namespace cb200

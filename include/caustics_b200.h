@@ -47,6 +47,8 @@ extern "C" {
 #define CAUSTICS_FLAG_INIT_BINI 1         /* intended complex Bini estimates: 10-30 % fewer updates, other root order */
 #define CAUSTICS_FLAG_COEFFS_HIGH_FIRST 2 /* coeffs rows are high->low (saves poly_roots' flip, primitive.py:73) */
 #define CAUSTICS_FLAG_GRID_WALK 4         /* caustics_mag_point_source_grid only: warm-started walks along y (below) */
+#define CAUSTICS_FLAG_PATH_WALK 8         /* caustics_mag_point_source only: consecutive elements of w are neighbours
+                                             (a trajectory) -> warm-started walks along the array (below) */
 
 /* Low-level lens parameters, exactly the reference's `_params` dict plus the centre-of-mass shift
  * its public functions add to the source positions (point_source.py:1796-1819).
@@ -158,7 +160,14 @@ int caustics_images_point_source_sequential(const void* w, void* z, uint8_t* mas
  * w (n) complex128 source positions (the x_cm shift in `lens` is added inside).
  * images: z (deg, n) complex128 with the root axis FIRST like the reference, mask (deg, n) uint8,
  *         z_init (n, deg) complex128 root axis LAST like the reference's z_init (custom_init).
- * mag:    mag (n) float64 = sum over real images of 1/|det J|.  nimages (n) uint8 or NULL. */
+ * mag:    mag (n) float64 = sum over real images of 1/|det J|.  nimages (n) uint8 or NULL.
+ *         flags & CAUSTICS_FLAG_PATH_WALK (with nimages == NULL): the caller states that w is a path, i.e.
+ *         w[i+1] is close to w[i]; each thread then owns a run of consecutive elements and starts every
+ *         solve after its first from the extrapolated roots of the elements before (the reference's
+ *         custom_init warm start, point_source.py:1711-1759).  Same stopping test, other iteration path:
+ *         agrees with the default to rounding x conditioning; an array that is not a path is still solved
+ *         correctly (a failed warm solve is redone cold), only slower.  Batches too small to fill the GPU
+ *         with runs of >= 2 elements take the default kernel. */
 int caustics_images_point_source(const void* w, const void* z_init, void* z, uint8_t* mask,
                                  int64_t n, const caustics_lens* lens, int itmax, int compensated,
                                  int custom_init, int flags, void* stream);

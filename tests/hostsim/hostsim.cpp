@@ -78,10 +78,32 @@ static void grid_walk_all(double x0, double y0, double dx, double dy, int64_t nx
   for (int64_t row0 = 0; row0 < nrows; row0 += run)
     for (int64_t ix = 0; ix < nx; ++ix) {
       const int nrun = (int)std::min<int64_t>(run, nrows - row0);
-      const double wx = fma((double)ix, dx, x0) + L.x_cm;
-      ps_grid_walk_body<NL, COMP, 1>(wx, y0, dy, row_begin + row0, nrun, mag + row0 * nx + ix, nx, L, itmax, extrap != 0,
-                                     sm, pre, pim, 0, true);
+      WalkColumn src;
+      src.wx = fma((double)ix, dx, x0) + L.x_cm; src.y0 = y0; src.dy = dy; src.row_abs0 = row_begin + row0;
+      ps_walk_body<NL, COMP, 1>(src, nrun, nrun, mag + row0 * nx + ix, nx, L, itmax, extrap != 0, sm, pre, pim, 0);
     }
+}
+template <int NL, bool COMP>
+static void path_walk_all(const double* w, double* mag, int64_t n, const LensConst& L, int itmax, int run, int extrap) {
+  constexpr int DEG = NL * NL + 1;
+  static EASmem<DEG, COMP, 1> sm;
+  double pre[DEG], pim[DEG];
+  for (int64_t first = 0; first < n; first += run) {
+    WalkPath src; src.w = w + 2 * first; src.x_cm = L.x_cm;
+    ps_walk_body<NL, COMP, 1>(src, run, (int)std::min<int64_t>(run, n - first), mag + first, 1, L, itmax, extrap != 0, sm, pre, pim, 0);
+  }
+}
+extern "C" int hostsim_path_walk(const double* w, double* mag, int64_t n, int nlenses, const double* eps, const double* r,
+                                 const double* H, const double* G, double x_cm, int itmax, int comp, int run, int extrap) {
+  LensConst L; memset(&L, 0, sizeof(L));
+  L.nlenses = nlenses; L.x_cm = x_cm;
+  for (int i = 0; i < 3; ++i) { L.eps[i] = eps[i]; L.r[i] = mk(r[2 * i], r[2 * i + 1]); }
+  for (int i = 0; i < 4; ++i) L.H[i] = mk(H[2 * i], H[2 * i + 1]);
+  for (int i = 0; i < 3; ++i) L.G[i] = mk(G[2 * i], G[2 * i + 1]);
+  if (nlenses == 2) { if (comp) path_walk_all<2, true>(w, mag, n, L, itmax, run, extrap); else path_walk_all<2, false>(w, mag, n, L, itmax, run, extrap); }
+  else if (nlenses == 3) { if (comp) path_walk_all<3, true>(w, mag, n, L, itmax, run, extrap); else path_walk_all<3, false>(w, mag, n, L, itmax, run, extrap); }
+  else return 1;
+  return 0;
 }
 extern "C" int hostsim_grid_walk(double x0, double y0, double dx, double dy, int64_t nx, int64_t row_begin, int64_t row_end,
                                  double* mag, int nlenses, const double* eps, const double* r, const double* H,

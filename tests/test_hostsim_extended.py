@@ -180,3 +180,27 @@ def test_grid_walk_sweep_counts(hs):
         if k >= 2:
             sw["extrap"].append(np.abs(s).mean())
     assert np.mean(sw["cold"]) > 6.5 and np.mean(sw["warm"]) < 3.1 and np.mean(sw["extrap"]) < 2.15
+
+
+def test_path_walk(hs):
+    """CAUSTICS_FLAG_PATH_WALK device code: a trajectory solved as warm-started runs of consecutive
+    elements == the oracle; an array that is NOT a path (random positions) is still solved correctly"""
+    def walk(w, nl, hp, run, extrap=1):
+        p, xcm = lens.lens_params(nl, **hp)
+        eps, r, H, G = lens_const(nl, **p)
+        w = np.ascontiguousarray(w, dtype=complex)
+        mag = np.zeros(w.size)
+        assert hs.hostsim_path_walk(w.ctypes.data_as(vp), mag.ctypes.data_as(vp), ctypes.c_int64(w.size), nl,
+                                    eps.ctypes.data_as(vp), r.ctypes.data_as(vp), H.ctypes.data_as(vp),
+                                    G.ctypes.data_as(vp), D_(xcm), 2500, 0, run, extrap) == 0
+        return mag
+    for nl, hp in ((2, HP2), (3, HP3)):
+        w = np.linspace(-2, 2, 1_000_000)[400_000:404_000] + 0.1j      # C1/C2 spacing, inside the caustic region
+        want = lens.mag_point_source(w, nl, **hp)
+        for run in (8, 13):
+            rel = np.abs(walk(w, nl, hp, run) / want - 1)
+            assert rel.max() < 1e-9 and np.median(rel) < 1e-13, (nl, run, rel.max())
+        rng = np.random.default_rng(3)
+        wr = rng.uniform(-1.5, 1.5, 600) + 1j * rng.uniform(-1.5, 1.5, 600)
+        rel = np.abs(walk(wr, nl, hp, 8) / lens.mag_point_source(wr, nl, **hp) - 1)
+        assert rel.max() < 1e-8 and np.median(rel) < 1e-13, (nl, rel.max())
