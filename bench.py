@@ -138,6 +138,13 @@ def other_configs(cb, L, _lib, torch):
     n4 = 100_000
     w4 = torch.from_numpy(np.linspace(-2, 2, n4) + 0.1j).cuda()
     lens3 = cb.point_source._c_lens(3, 0.0, **LENS)
+    # C2 as the fused point-source magnification (coefficients + solve + filter + Jacobian in one kernel),
+    # per-point cold solves and CAUSTICS_FLAG_PATH_WALK (the trajectory as warm-started runs)
+    w2 = torch.from_numpy(np.linspace(-2, 2, n) + 0.1j).cuda()
+    m2 = torch.empty(n, dtype=torch.float64, device="cuda")
+    for key, fl in (("C2_mag_point_source_triple_evals_per_s", 0), ("C2_mag_point_source_triple_path_walk_evals_per_s", 8)):
+        out[key] = n / best(lambda: _lib.check(L.caustics_mag_point_source(w2.data_ptr(), m2.data_ptr(), None, n, lens3,
+                                                                            2500, 0, fl, None)))
     m4 = torch.empty(n4, dtype=torch.float64, device="cuda")
     nbytes = L.caustics_ext_workspace_bytes(n4, 3, 200, 0, 100)
     ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
