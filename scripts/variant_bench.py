@@ -34,6 +34,9 @@ out["deg10_bini_ms"] = t(lambda: cb.poly_roots(c10, itmax=2500, flags=1))
 out["deg5_ms"] = t(lambda: cb.poly_roots(c5, itmax=2500))
 out["rand10_ms"] = t(lambda: cb.poly_roots(r10, itmax=2500))
 out["deg10_comp_ms"] = t(lambda: cb.poly_roots(c10, itmax=2500, compensated=True), reps=5)
+dx = 3.0 / 9999
+for walk in (False, True):
+    out["c5_walk_ms" if walk else "c5_cold_ms"] = t(lambda: cb.mag_point_source_map(-1.5, -1.5, dx, dx, 10000, 10000, rows=(4000, 6000), walk=walk, s=0.9, q=0.2), reps=5)
 z = cb.poly_roots(c10[:20000], itmax=2500, compensated=True).cpu().numpy()
 np.save(sys.argv[1], z)
 _, sw = cb.primitive._solve_flat(c10[:100000], None, 2500, False, False, 2, return_sweeps=True)
