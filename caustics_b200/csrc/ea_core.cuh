@@ -407,7 +407,7 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
 #pragma unroll
   for (int i = 0; i <= DEG; ++i) al.set(i, al.get(i) * fma(3.8284271247461900976, (double)i, 1.0));  // :96-99
   double thrA2 = 0.0;   // (EPS * sum alpha_i)^2 with a 1e-9 margin: see CB200_LAZY_BOUND
-  if (STRAIGHT && CB200_LAZY_BOUND) {
+  if (CB200_LAZY_BOUND) {
     double asum = 0.0;
 #pragma unroll
     for (int i = 0; i <= DEG; ++i) asum += al.get(i);
@@ -470,9 +470,13 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
       const cd z = mk(zre[j * NT], zim[j * NT]);
       const double az2 = norm2(z);
       const bool rev = az2 > 1.0;  // |z| > 1, ehrlich_aberth.h:106
-      // |z| and (reversed lanes) 1/z, 1/|z| from one reciprocal square root
-      const double rs = az2 > 0.0 ? rsqrt_fast(az2) : 0.0;
-      const double absz = az2 * rs;
+      // |z| and (reversed lanes) 1/z, 1/|z| from one reciprocal square root; standard lanes need |z| only
+      // for the bound polynomial, which is evaluated lazily (CB200_LAZY_BOUND)
+      double rs = 0.0, absz = 0.0;
+      if (!CB200_LAZY_BOUND || rev || (COMP && need2)) {
+        rs = az2 > 0.0 ? rsqrt_fast(az2) : 0.0;
+        absz = az2 * rs;
+      }
       cd x = z;
       double ax = absz;
       if (rev) {
@@ -486,13 +490,25 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
       const bool all_std = __all_sync(0xffffffffu, !need1 || !rev);
       const bool all_rev = __all_sync(0xffffffffu, !need1 || rev);
       if (need1) {
-        double b;
-        if (all_std) horner_plain<DEG, 0, ALPHA>(p, al, x, ax, rev, h, hd, b);
-        else if (all_rev) horner_plain<DEG, 1, ALPHA>(p, al, x, ax, rev, h, hd, b);
-        else horner_plain<DEG, 2, ALPHA>(p, al, x, ax, rev, h, hd, b);
-        const double thr = EA_EPS * b;
-        if (norm2(h) > thr * thr) upd = true;  // |h| > EPS*b, :109/:122
-        else c1 |= (1u << j);
+        double b = 0.0;
+        if (all_std) horner_plain<DEG, 0, ALPHA, !CB200_LAZY_BOUND>(p, al, x, ax, rev, h, hd, b);
+        else if (all_rev) horner_plain<DEG, 1, ALPHA, !CB200_LAZY_BOUND>(p, al, x, ax, rev, h, hd, b);
+        else horner_plain<DEG, 2, ALPHA, !CB200_LAZY_BOUND>(p, al, x, ax, rev, h, hd, b);
+        const double nh = norm2(h);
+        if (CB200_LAZY_BOUND && nh > thrA2) {
+          upd = true;                                   // |h| > EPS * sum alpha_i >= EPS*b
+        } else {
+          if (CB200_LAZY_BOUND) {
+            if (!rev && !(COMP && need2)) {
+              const double r0 = az2 > 0.0 ? rsqrt_fast(az2) : 0.0;
+              ax = az2 * r0;
+            }
+            b = horner_bound<DEG, 2, ALPHA>(al, ax, rev);
+          }
+          const double thr = EA_EPS * b;
+          if (nh > thr * thr) upd = true;  // |h| > EPS*b, :109/:122
+          else c1 |= (1u << j);
+        }
       }
       if (COMP) {
         if (need2) {
