@@ -6,7 +6,7 @@ TAG=${TAG:-r01}
 KREGEX=${KREGEX:-ea_kernel}
 python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -2
 # launch list of the bench command (cold-cache, serialised: compare shares)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_${TAG}.log 2>&1
 # full capture of the top kernel
 ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 3 -c 1 \
