@@ -88,19 +88,31 @@ __device__ __forceinline__ void ea_normalise(cd (&p)[DEG + 1]) {
   }
 }
 
-// log for the initial estimates.  CB200_FAST_LOG: exponent * ln 2 + single-precision log2 of the
-// mantissa (~1e-7 absolute), enough for starting values; 0: libm double log.
-#ifndef CB200_FAST_LOG
-#define CB200_FAST_LOG 0
+// log for the initial estimates (one per coefficient).  libm's log() is ~175 instructions with its
+// special-case handling and constant loads -- 5 % of the whole degree-10 kernel -- so the default is the
+// classic argument reduction x = 2^k (1 + f), sqrt(1/2) < 1 + f < sqrt(2), s = f / (2 + f),
+// log(1 + f) = f - (f^2/2 - s (f^2/2 + R(s^2))) with the degree-7 minimax R of the public fdlibm e_log.c
+// (error < 1 ulp: it differs from libm's result in the last bit for ~3 % of arguments, which is also how far
+// the reference's host libm and CUDA's libm are apart).  Arguments are the positive, finite |coefficients|;
+// a denormal is treated as ~2^-1023, good enough for a starting radius.  CB200_LIBM_LOG=1: libm.
+#ifndef CB200_LIBM_LOG
+#define CB200_LIBM_LOG 0
 #endif
 __device__ __forceinline__ double ea_log(double a) {
-#if CB200_FAST_LOG && !defined(CB200_HOSTSIM)
-  const int hi = __double2hiint(a), lo = __double2loint(a);
-  const int e = ((hi >> 20) & 0x7ff) - 1023;
-  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);   // mantissa in [1, 2)
-  return ((double)e + (double)__log2f((float)m)) * 0.6931471805599453;
-#else
+#if CB200_LIBM_LOG
   return log(a);
+#else
+  const int hi = __double2hiint(a), lo = __double2loint(a);
+  double k = (double)(((hi >> 20) & 0x7ff) - 1023);
+  double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);   // mantissa in [1, 2)
+  if (m > 1.4142135623730951) { m *= 0.5; k += 1.0; }
+  const double f = m - 1.0;
+  const double s = f * rcp_fast(2.0 + f);
+  const double z = s * s, w = z * z;
+  const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
+  const double t2 = z * (6.666666666666735130e-01 + w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
+  const double hfsq = 0.5 * f * f;
+  return k * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + (t2 + t1)) + k * 1.90821492927058770002e-10)) - f);
 #endif
 }
 

@@ -23,6 +23,7 @@ static inline double __dsub_rn(double a, double b) { volatile double r = a - b; 
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline int __double2hiint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(u >> 32); }
+static inline int __double2loint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(uint32_t)u; }
 static inline double __hiloint2double(int hi, int lo) {
   uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &u, 8); return x;
 }
