@@ -64,3 +64,28 @@ def test_device_solver_logic_vs_golden(hs, ea_golden, name, comp):
     if comp:
         assert set_distance(got_b, ea_golden[name + "_roots_comp"]).max() < 1e-12
     assert np.abs(sw_b).mean() <= np.abs(sw).mean() + 0.2
+
+
+def test_lazy_bound_is_bit_identical(hs, ea_golden):
+    """CB200_LAZY_BOUND (ea_core.cuh) only skips work whose result cannot matter: the device solver compiled
+    with and without it returns the same roots and the same sweep counts, bit for bit -- cold starts, warm
+    starts, plain and compensated, reference-compatible and Bini estimates"""
+    so = os.path.join(HS, "libhostsim_nolazy.so")
+    srcs = [os.path.join(HS, "hostsim.cpp")] + [os.path.join(ROOT, "caustics_b200", "csrc", f)
+                                                for f in os.listdir(os.path.join(ROOT, "caustics_b200", "csrc")) if f.endswith(".cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-DCB200_LAZY_BOUND=0",
+                        "-o", so, os.path.join(HS, "hostsim.cpp"), "-lm"], check=True)
+    ref = ctypes.CDLL(so)
+    for name in ("fixture", "c1", "c2", "rand6", "rand10"):
+        c = ea_golden[name + "_coeffs"]
+        c = c.reshape(-1, c.shape[-1])[:, ::-1]
+        for comp in (False, True):
+            for flags in (0, 1):
+                a, sa = hs_solve(hs, c, comp=comp, flags=flags)
+                b, sb = hs_solve(ref, c, comp=comp, flags=flags)
+                assert np.array_equal(a.view(np.uint64), b.view(np.uint64)) and np.array_equal(sa, sb), (name, comp, flags)
+            ri = np.roll(a, 1, axis=0) * (1 + 1e-4)          # warm start from a neighbour's roots (branchy step)
+            a, sa = hs_solve(hs, c, comp=comp, custom_init=True, ri=ri)
+            b, sb = hs_solve(ref, c, comp=comp, custom_init=True, ri=ri)
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)) and np.array_equal(sa, sb), (name, comp, "warm")
