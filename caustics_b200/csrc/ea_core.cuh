@@ -303,12 +303,18 @@ __device__ __forceinline__ double horner_bound(const ALPHA& al, double ax, bool 
 #ifndef CB200_LAZY_BOUND
 #define CB200_LAZY_BOUND 1
 #endif
-template <int DEG, int MODE, int NT, class ALPHA, bool FAST>
+// PASSZ: the caller hands over the root and |z|^2 it already loaded for the variant vote (plain kernels:
+// 2 shared loads and 2 FP64 instructions fewer per step, headline 1.648 -> 1.609 ms); the compensated kernels
+// reload them here instead, because keeping them live across the vote costs their plain stage registers
+// (measured: 4.13 -> 4.49 ms with PASSZ).
+template <int DEG, int MODE, int NT, class ALPHA, bool FAST, bool PASSZ>
 __device__ __forceinline__ void ea_step_plain(const cd (&p)[DEG + 1], const ALPHA& al,
                                               double* zre, double* zim, int j, bool need, unsigned& c1,
-                                              double thrA2) {
-  const cd z = mk(zre[j * NT], zim[j * NT]);
-  const double az2 = norm2(z);
+                                              double thrA2, cd z, double az2) {
+  if (!PASSZ) {
+    z = mk(zre[j * NT], zim[j * NT]);
+    az2 = norm2(z);
+  }
   const bool rev = MODE == 2 ? az2 > 1.0 : MODE == 1;
   double rs = 0.0, absz = 0.0;
   if (!CB200_LAZY_BOUND || MODE != 0) {
@@ -393,7 +399,7 @@ struct EAResult {
 // STRAIGHT selects the straight-line plain step (best for cold starts, where ~90 % of the evaluations
 // are followed by an update) or the branchy one that skips the Aberth sum when no lane updates (best
 // for warm starts, where every root's second evaluation only confirms convergence).
-template <int DEG, bool COMP, int NT, bool STRAIGHT = (CB200_STRAIGHT_LINE != 0)>
+template <int DEG, bool COMP, int NT, bool STRAIGHT = (CB200_STRAIGHT_LINE != 0), bool PASSZ = !COMP>
 __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASmem<DEG, COMP, NT>& sm,
                                                     int tid, bool active, bool custom_init,
                                                     int init_mode, int itmax, bool fast = false) {
@@ -464,17 +470,26 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
       if (!__any_sync(0xffffffffu, need1 || need2)) continue;
       if (STRAIGHT && (!COMP || !stage2)) {
         // warp-uniform choice of the evaluation variant, then one straight-line step
-        const bool rv = zre[j * NT] * zre[j * NT] + zim[j * NT] * zim[j * NT] > 1.0;
+        cd zj = mk(0, 0);
+        double az2j = 0.0;
+        bool rv;
+        if (PASSZ) {
+          zj = mk(zre[j * NT], zim[j * NT]);
+          az2j = norm2(zj);
+          rv = az2j > 1.0;
+        } else {
+          rv = zre[j * NT] * zre[j * NT] + zim[j * NT] * zim[j * NT] > 1.0;
+        }
         const bool all_std = __all_sync(0xffffffffu, !need1 || !rv);
         const bool all_rev = __all_sync(0xffffffffu, !need1 || rv);
         if (fast) {
-          if (all_std) ea_step_plain<DEG, 0, NT, ALPHA, true>(p, al, zre, zim, j, need1, c1, thrA2);
-          else if (all_rev) ea_step_plain<DEG, 1, NT, ALPHA, true>(p, al, zre, zim, j, need1, c1, thrA2);
-          else ea_step_plain<DEG, 2, NT, ALPHA, true>(p, al, zre, zim, j, need1, c1, thrA2);
+          if (all_std) ea_step_plain<DEG, 0, NT, ALPHA, true, PASSZ>(p, al, zre, zim, j, need1, c1, thrA2, zj, az2j);
+          else if (all_rev) ea_step_plain<DEG, 1, NT, ALPHA, true, PASSZ>(p, al, zre, zim, j, need1, c1, thrA2, zj, az2j);
+          else ea_step_plain<DEG, 2, NT, ALPHA, true, PASSZ>(p, al, zre, zim, j, need1, c1, thrA2, zj, az2j);
         } else {
-          if (all_std) ea_step_plain<DEG, 0, NT, ALPHA, false>(p, al, zre, zim, j, need1, c1, thrA2);
-          else if (all_rev) ea_step_plain<DEG, 1, NT, ALPHA, false>(p, al, zre, zim, j, need1, c1, thrA2);
-          else ea_step_plain<DEG, 2, NT, ALPHA, false>(p, al, zre, zim, j, need1, c1, thrA2);
+          if (all_std) ea_step_plain<DEG, 0, NT, ALPHA, false, PASSZ>(p, al, zre, zim, j, need1, c1, thrA2, zj, az2j);
+          else if (all_rev) ea_step_plain<DEG, 1, NT, ALPHA, false, PASSZ>(p, al, zre, zim, j, need1, c1, thrA2, zj, az2j);
+          else ea_step_plain<DEG, 2, NT, ALPHA, false, PASSZ>(p, al, zre, zim, j, need1, c1, thrA2, zj, az2j);
         }
         continue;
       }

@@ -62,7 +62,7 @@ __device__ __forceinline__ void ps_walk_body(const WSRC& wsrc, int nsteps, int n
       redo = active && !(r.converged && chk < 1e300);
     }
     if (__any_sync(0xffffffffu, redo)) {
-      ea_solve_thread<DEG, COMP, NT>(p, sm, tid, redo, false, EA_INIT_BINI, itmax, true);
+      ea_solve_thread<DEG, COMP, NT, true, false>(p, sm, tid, redo, false, EA_INIT_BINI, itmax, true);
       if (extrap && redo) {
 #pragma unroll
         for (int j = 0; j < DEG; ++j) { pre[j * NT] = zre[j * NT]; pim[j * NT] = zim[j * NT]; }
