@@ -204,3 +204,24 @@ def test_path_walk(hs):
         wr = rng.uniform(-1.5, 1.5, 600) + 1j * rng.uniform(-1.5, 1.5, 600)
         rel = np.abs(walk(wr, nl, hp, 8) / lens.mag_point_source(wr, nl, **hp) - 1)
         assert rel.max() < 1e-8 and np.median(rel) < 1e-13, (nl, rel.max())
+
+
+def test_walk_degenerate_inputs(hs):
+    """walk device code on degenerate maps: zero step (every pixel the same), NaN / huge origins, itmax too small
+    for any solve to converge -- terminates, and finite inputs still give the oracle's value"""
+    dx = 3.0 / 9999
+    same = hs_grid_walk(hs, 0.05, 0.1, 0.0, 0.0, 3, 0, 40, 2, HP2)
+    want = lens.mag_point_source(np.array([0.05 + 0.1j]), 2, **HP2)[0]
+    assert np.allclose(same, want, rtol=1e-10)
+    for x0 in (np.nan, np.inf, 1e8, 1e-300):
+        m = hs_grid_walk(hs, x0, 0.1, dx, dx, 4, 0, 9, 2, HP2, run=4)
+        assert m.shape == (9, 4)
+        if np.isfinite(x0):
+            ix, iy = np.meshgrid(np.arange(4), np.arange(9))
+            assert np.allclose(m, lens.mag_point_source(((x0 + ix * dx) + 1j * (0.1 + iy * dx)).reshape(-1), 2, **HP2).reshape(9, 4), rtol=1e-9)
+    p, xcm = lens.lens_params(2, **HP2)
+    eps, r, H, G = lens_const(2, **p)
+    mag = np.zeros((20, 4))
+    assert hs.hostsim_grid_walk(D_(-0.2), D_(0.05), D_(dx), D_(dx), ctypes.c_int64(4), ctypes.c_int64(0), ctypes.c_int64(20),
+                                mag.ctypes.data_as(vp), 2, eps.ctypes.data_as(vp), r.ctypes.data_as(vp), H.ctypes.data_as(vp),
+                                G.ctypes.data_as(vp), D_(xcm), 2, 0, 8, 1) == 0     # itmax = 2
