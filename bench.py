@@ -41,7 +41,7 @@ LENS = dict(a=0.698, e1=0.02809, e2=0.9687, r3=-0.0197 - 0.95087j)
 F_UPDATE = 28 * DEG + 21          # flop per plain root update, SURVEY 8(d)
 INIT_FLOP = 600                   # initial estimates + |coefficients| per polynomial
 UPDATES_PER_POLY = 95.2           # plain root updates per polynomial on this workload
-NCU_DRAM_BYTES_PER_LAUNCH = 3.05e8  # 176 MB read + 129 MB written, profiles/r01_ncu_ea_kernel_deg10.csv
+NCU_DRAM_BYTES_PER_LAUNCH = 2.98e8  # 176.1 MB read + 121.9 MB written, profiles/r01b_ncu_ea_kernel_deg10.csv
 CONFIG = {"workload": "C2: ehrlich_aberth on 10^6 degree-10 triple-lens polynomials per GPU "
                       "(w=linspace(-2,2,N*10^6)+0.1i sliced per rank), plain mode, itmax=2500, "
                       "reference-compatible initial estimates",
