@@ -333,7 +333,7 @@ def main():
                             "frac": hbm_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (the other ranks would wait ~10 s)
             from oracle import solver
             cs = np.ascontiguousarray(coeffs[:, ::-1])       # the whole step: ~10 s on one host core
             ncs = cs.shape[0]
