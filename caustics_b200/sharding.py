@@ -7,7 +7,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "sharded_apply", "balanced_order"]
+__all__ = ["shard_bounds", "sharded_apply", "balanced_order", "row_block", "sharded_rows"]
 
 
 def shard_bounds(n, world, rank):
@@ -54,3 +54,39 @@ def sharded_apply(fn, x, group=None, gather=True):
     out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return out[:n]
+
+
+def row_block(nrows, world, rank, align=1):
+    """Row block [lo, hi) of rank `rank` for a map of `nrows` rows: contiguous, equal to within one
+    `align`-row unit.  With align = 32 (the walk length of csrc/ps_walk.cuh) every rank's block starts on a
+    walk boundary of the unsharded map, so a map computed with `walk=True` does not depend on the number of
+    ranks as long as every block is large enough to be given full 32-row walks (the launcher shortens the
+    walks of maps too small to fill the GPU); each column segment is then the same walk wherever it runs.
+    The default (align = 1) balances the rows exactly instead."""
+    units = -(-nrows // align)
+    per = -(-units // world) if world > 0 else units
+    lo = min(rank * per * align, nrows)
+    return lo, min(lo + per * align, nrows)
+
+
+def sharded_rows(fn, nrows, group=None, gather=True, align=1):
+    """Row-sharded evaluation of a map (BASELINE config C5): `fn(lo, hi)` returns this rank's rows as a
+    (hi - lo, ...) tensor; no data-path collective, one all_gather at the end if `gather`.  Example:
+
+        mag = sharded_rows(lambda lo, hi: mag_point_source_map(x0, y0, dx, dy, nx, ny, rows=(lo, hi), s=s, q=q),
+                           ny, align=32)
+
+    Works without an initialised process group (single process)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return fn(0, nrows)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = row_block(nrows, world, rank, align)
+    local = fn(lo, hi)
+    if not gather:
+        return local
+    per = row_block(nrows, world, 0, align)[1]
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: hi - lo] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return out[:nrows]

@@ -69,3 +69,42 @@ def test_shard_bounds_and_balance():
     per = 5
     loads = [cost[perm[r * per:(r + 1) * per]].sum() for r in range(2)]
     assert max(loads) - min(loads) <= 1
+
+
+def _rows_worker(rank, world, port, nrows, align, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    from caustics_b200.sharding import sharded_rows, row_block
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nx = 5
+    full = torch.arange(nrows, dtype=torch.float64)[:, None] * 10 + torch.arange(nx, dtype=torch.float64)[None, :]
+    out = sharded_rows(lambda lo, hi: full[lo:hi].clone(), nrows, align=align)
+    lo, hi = row_block(nrows, world, rank, align)
+    ok = bool(torch.equal(out, full)) and (lo % align == 0 or lo == nrows)
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nrows,align", [(100, 32), (7, 1), (64, 32), (1, 32)])
+def test_sharded_rows_gloo_world2(nrows, align):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, 2, port, nrows, align, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert res == [(0, True), (1, True)]
+
+
+def test_row_block_alignment():
+    from caustics_b200.sharding import row_block
+    for nrows in (0, 1, 31, 32, 33, 1000, 10_000):
+        for world in (1, 2, 4, 8):
+            for align in (1, 32):
+                spans = [row_block(nrows, world, r, align) for r in range(world)]
+                assert spans[0][0] == 0 and spans[-1][1] == nrows
+                assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+                assert all(lo % align == 0 or lo == nrows for lo, _ in spans)
