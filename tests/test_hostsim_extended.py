@@ -225,3 +225,14 @@ def test_walk_degenerate_inputs(hs):
     assert hs.hostsim_grid_walk(D_(-0.2), D_(0.05), D_(dx), D_(dx), ctypes.c_int64(4), ctypes.c_int64(0), ctypes.c_int64(20),
                                 mag.ctypes.data_as(vp), 2, eps.ctypes.data_as(vp), r.ctypes.data_as(vp), H.ctypes.data_as(vp),
                                 G.ctypes.data_as(vp), D_(xcm), 2, 0, 8, 1) == 0     # itmax = 2
+
+
+def test_walk_row_blocks_aligned_to_the_run_are_the_unsharded_map(hs):
+    """sharding.row_block(align=32): row blocks that start on walk boundaries reproduce the unsharded walked map
+    bit for bit (what makes a walked map independent of the number of ranks)"""
+    dx = 3.0 / 9999
+    full = hs_grid_walk(hs, -0.25, 0.08, dx, dx, 6, 0, 80, 2, HP2, run=32)
+    parts = [hs_grid_walk(hs, -0.25, 0.08, dx, dx, 6, lo, hi, 2, HP2, run=32) for lo, hi in ((0, 32), (32, 64), (64, 80))]
+    assert np.array_equal(np.concatenate(parts), full)
+    off = hs_grid_walk(hs, -0.25, 0.08, dx, dx, 6, 10, 50, 2, HP2, run=32)      # unaligned block: other walks,
+    assert np.allclose(off, full[10:50], rtol=1e-9) and not np.array_equal(off, full[10:50])   # same map to rounding
