@@ -72,6 +72,15 @@ __device__ __forceinline__ double rcp_aberth(double x) {
 #endif
 }
 constexpr unsigned EA_COMP_CAP = 12;  // see ea_solve_thread
+#if defined(CB200_HOSTSIM) && defined(CB200_HOSTSIM_COUNT)
+// work counters of the host-compiled test build (tests/hostsim): polynomial evaluations and root updates
+static long long g_ea_evals = 0, g_ea_updates = 0;
+#define CB200_COUNT_EVAL(n) (g_ea_evals += (n))
+#define CB200_COUNT_UPD(n) (g_ea_updates += (n))
+#else
+#define CB200_COUNT_EVAL(n) ((void)0)
+#define CB200_COUNT_UPD(n) ((void)0)
+#endif
 
 // Power-of-two normalisation of the coefficients: p_i *= 2^-e with e = exponent of max |component|.
 template <int DEG>
@@ -374,6 +383,8 @@ __device__ __forceinline__ void ea_step_plain(const cd (&p)[DEG + 1], const ALPH
     zim[j * NT] = z.im - corr.im;
   }
   if (need && !big) c1 |= (1u << j);
+  CB200_COUNT_EVAL(need ? 1 : 0);
+  CB200_COUNT_UPD(need && big ? 1 : 0);
 }
 
 // Shared-memory planes owned by one CTA of NT threads.
@@ -516,6 +527,7 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
       // warp votes are taken by all lanes, outside the per-lane branch
       const bool all_std = __all_sync(0xffffffffu, !need1 || !rev);
       const bool all_rev = __all_sync(0xffffffffu, !need1 || rev);
+      CB200_COUNT_EVAL(need1 ? 1 : 0);
       if (need1) {
         double b = 0.0;
         if (all_std) horner_plain<DEG, 0, ALPHA, !CB200_LAZY_BOUND>(p, al, x, ax, rev, h, hd, b);
@@ -563,6 +575,7 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
           else c2 |= (1u << j);
         }
       }
+      CB200_COUNT_UPD(upd ? 1 : 0);
       if (__any_sync(0xffffffffu, upd)) {
         if (upd) {
           // Aberth sum over the other roots (:31-40) and the (reversed) correction (:41,:56-57)

@@ -33,6 +33,15 @@ constexpr int NITER = 10;          // refinement rounds, extended_source.py:71
 constexpr int MAXSEG = 30;         // 3 * (nlenses^2 + 1), extended_source.py:279-280
 constexpr int MAXPARTS = 10;       // per track, extended_source.py:202-203
 constexpr double JIT_RE = 3.1e-7, JIT_IM = -5.3e-7;  // fixed stand-ins for U(+-1e-6) (:83-85)
+#ifndef CB200_EXT_PREDICT
+#define CB200_EXT_PREDICT 0
+#endif
+#ifndef CB200_EXT_PREDICT_MAXSTEP2
+#define CB200_EXT_PREDICT_MAXSTEP2 1e-2
+#endif
+#ifndef CB200_EXT_PREDICT_SEP
+#define CB200_EXT_PREDICT_SEP 1e300   /* predict a root only if (its step)^2 < SEP * (distance to the nearest other root)^2 */
+#endif
 constexpr double DUP_JIT = 7.0e-10;                  // stand-in for U(+-1e-9) (:146)
 
 struct ExtCfg {
@@ -135,9 +144,29 @@ template <int NL, int NT>
 __device__ void limb_walk_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, EASmem<NL * NL + 1, false, NT>& sm, int tid, int64_t s) {
   const bool active = s < nsrc(cfg, b);
   const cd w0 = active ? source_centre(cfg, b, L, s) : mk(0.3, 0.2);
+#if CB200_EXT_PREDICT
+  double ppr[NL * NL + 1], ppi[NL * NL + 1];   // experiment: roots of the limb point before the previous one
+#endif
   for (int k = 0; k < cfg.N0; ++k) {
     const double th = theta_init(k, cfg.N0);
     const cd w = limb_point(w0, cfg.rho, th);
+#if CB200_EXT_PREDICT
+    if (active && k >= 1 && k < cfg.N0 - 1) {   // (the last point repeats theta = -pi: no extrapolation)
+      constexpr int D_ = NL * NL + 1;
+      double cr[D_], ci[D_];
+      for (int j = 0; j < D_; ++j) { cr[j] = sm.zre[j][tid]; ci[j] = sm.zim[j][tid]; }
+      for (int j = 0; j < D_; ++j) {
+        const double dr = cr[j] - ppr[j], di = ci[j] - ppi[j];
+        double sep2 = 1e300;   // squared distance to the nearest other root
+        for (int i = 0; i < D_; ++i)
+          if (i != j) sep2 = fmin(sep2, (cr[j] - cr[i]) * (cr[j] - cr[i]) + (ci[j] - ci[i]) * (ci[j] - ci[i]));
+        if (k >= 2 && dr * dr + di * di < CB200_EXT_PREDICT_MAXSTEP2 && dr * dr + di * di < CB200_EXT_PREDICT_SEP * sep2) {
+          sm.zre[j][tid] = cr[j] + dr; sm.zim[j][tid] = ci[j] + di;
+        }
+        ppr[j] = cr[j]; ppi[j] = ci[j];
+      }
+    }
+#endif
     // roots_compensated is not forwarded to the sequential walk (extended_source.py:104-106)
     solve_and_store<NL, false, NT>(cfg, b, L, sm, tid, active, w, k > 0, k, s);
     if (active) {
@@ -496,6 +525,27 @@ __device__ void refine_solve_body(const ExtCfg& cfg, const ExtBuf& b, const Lens
       sm.zre[j][tid] = b.zre[I3(lf, j, s)] + JIT_RE;
       sm.zim[j][tid] = b.zim[I3(lf, j, s)] + JIT_IM;
     }
+#if CB200_EXT_PREDICT
+    {   // experiment: interpolate between the two ends of the interval the new point splits
+      const int rt = b.right[I2(r, s)];
+      const double tl = b.theta[I2(lf, s)], tr = b.theta[I2(rt, s)], tn = b.theta[I2(slot, s)];
+      const double t = (tn - tl) / (tr - tl);
+      for (int j = 0; j < D; ++j) {
+        const double lr = b.zre[I3(lf, j, s)], li = b.zim[I3(lf, j, s)];
+        const double dr = b.zre[I3(rt, j, s)] - lr, di = b.zim[I3(rt, j, s)] - li;
+        double sep2 = 1e300;
+        for (int i = 0; i < D; ++i)
+          if (i != j) {
+            const double er = lr - b.zre[I3(lf, i, s)], ei = li - b.zim[I3(lf, i, s)];
+            sep2 = fmin(sep2, er * er + ei * ei);
+          }
+        if (dr * dr + di * di < CB200_EXT_PREDICT_MAXSTEP2 && dr * dr + di * di < CB200_EXT_PREDICT_SEP * sep2) {
+          sm.zre[j][tid] += t * dr;
+          sm.zim[j][tid] += t * di;
+        }
+      }
+    }
+#endif
   }
   solve_and_store<NL, COMP, NT>(cfg, b, L, sm, tid, active, w, true, slot, s);
   if (active) update_widths<D>(cfg, b, r, slot, s);

@@ -217,3 +217,10 @@ extern "C" int hostsim_mag_extended(const double* w, double* mag, uint8_t* test_
       }
   return 0;
 }
+
+#ifdef CB200_HOSTSIM_COUNT
+extern "C" void hostsim_counters(long long* out, int reset) {
+  out[0] = cb200::g_ea_evals; out[1] = cb200::g_ea_updates;
+  if (reset) { cb200::g_ea_evals = 0; cb200::g_ea_updates = 0; }
+}
+#endif
