@@ -59,7 +59,10 @@ def register():
             raise NotImplementedError(f"Unsupported dtype {aval.dtype}")     # :187-190
         size, deg = aval.shape[0], aval.shape[1] - 1
         opaque = _descriptor(size, deg, itmax, compensated, custom_init)
-        return jax.ffi.ffi_lowering(_TARGET, backend_config=opaque)(ctx, coeffs, roots_init)
+        # legacy (untyped) custom call: XLA's API_VERSION_ORIGINAL = 1 is the signature without a status
+        # argument, void(stream, buffers, opaque, opaque_len), which is what the reference's gpu_ehrlich_aberth
+        # and caustics_ea_xla have; ffi_lowering defaults to 4 (typed FFI), which takes a dict, not bytes
+        return jax.ffi.ffi_lowering(_TARGET, backend_config=opaque, api_version=1)(ctx, coeffs, roots_init)
 
     def _jvp(args, tangents, itmax=None, compensated=False, custom_init=False):   # :254-324
         p, roots_init = args

@@ -40,7 +40,7 @@ def fake_jax(monkeypatch):
     jax = types.ModuleType("jax")
     jax.ffi = types.SimpleNamespace(
         register_ffi_target=lambda name, capsule, platform, api_version: rec["targets"].append((name, capsule, platform, api_version)),
-        ffi_lowering=lambda target, backend_config: (lambda ctx, *ops: ("custom_call", target, backend_config, len(ops))))
+        ffi_lowering=lambda target, backend_config, api_version=4: (lambda ctx, *ops: ("custom_call", target, backend_config, len(ops), api_version)))
     jax.jit = lambda f: f
     jnp = types.ModuleType("jax.numpy")
     for n in ("zeros", "zeros_like", "complex128"):
@@ -86,7 +86,8 @@ def test_register_and_shapes(fake_jax, built_lib):
     (prim, rule, plat), = fake_jax["lowerings"]
     assert plat == "cuda"
     ctx = types.SimpleNamespace(avals_in=[types.SimpleNamespace(shape=(12, 6), dtype=np.dtype(np.complex128))])
-    kind, target, opaque, nops = rule(ctx, "coeffs", "roots_init", itmax=2500, compensated=True, custom_init=False)
+    kind, target, opaque, nops, api = rule(ctx, "coeffs", "roots_init", itmax=2500, compensated=True, custom_init=False)
+    assert api == 1 and isinstance(opaque, bytes)        # legacy custom call with an opaque byte string
     assert (kind, target, nops) == ("custom_call", "caustics_b200_ehrlich_aberth", 2) and len(opaque) == ctypes.sizeof(_lib.EADescriptor) == 24
     d = _lib.EADescriptor.from_buffer_copy(opaque)
     assert (d.size, d.deg, d.itmax, d.compensated, d.custom_init, d.flags) == (12, 5, 2500, 1, 0, 0)
