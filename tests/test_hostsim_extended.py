@@ -236,3 +236,27 @@ def test_walk_row_blocks_aligned_to_the_run_are_the_unsharded_map(hs):
     assert np.array_equal(np.concatenate(parts), full)
     off = hs_grid_walk(hs, -0.25, 0.08, dx, dx, 6, 10, 50, 2, HP2, run=32)      # unaligned block: other walks,
     assert np.allclose(off, full[10:50], rtol=1e-9) and not np.array_equal(off, full[10:50])   # same map to rounding
+
+
+@pytest.mark.parametrize("key,nl,hp", [("b", 2, HP2), ("t", 3, HP3)])
+def test_grid_walk_vs_reference_map(hs, key, nl, hp):
+    """the walk device code against the REFERENCE's own mag_point_source on two caustic-crossing patches of the
+    C5 grid (tests/golden/map_golden.npz, generated by the reference's Python + compiled solver), and the
+    oracle restatement against the same values"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "map_golden.npz"))
+    x0, y0, dx, dy, nx, r0, r1 = g[key + "_spec"]
+    nx, r0, r1 = int(nx), int(r0), int(r1)
+    want = g[key + "_mag"]
+    assert want.max() > 300          # pixels within a few 1e-6 of the fold
+    # rtol 1e-10, widened next to the fold by the reference's own plain-vs-compensated spread and by the
+    # conditioning of a fold image (mu ~ d^-1/2 in the distance d to the caustic: a relative 1e-16 in the
+    # coefficients moves mu by ~1e-16 mu^2, i.e. 2e-10 at the mu = 1300 pixel of the binary patch)
+    # (the degree-10 coefficients of the triple lens carry ~20x the rounding of the binary ones: 6e-10 at mu = 250)
+    tol = 1e-10 + 10 * np.abs(want / g[key + "_mag_comp"] - 1) + (1e-15 if nl == 2 else 2e-14) * want**2
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(r0, r1))
+    w = (x0 + ix * dx) + 1j * (y0 + iy * dy)
+    assert (np.abs(lens.mag_point_source(w.reshape(-1), nl, **hp).reshape(w.shape) / want - 1) <= tol).all()
+    for run, extrap in ((32, 1), (8, 1), (32, 0)):
+        got = hs_grid_walk(hs, x0, y0, dx, dy, nx, r0, r1, nl, hp, run=run, extrap=extrap)
+        rel = np.abs(got / want - 1)
+        assert (rel <= tol).all() and np.median(rel) < 1e-13, (run, extrap, rel.max())
