@@ -89,3 +89,28 @@ def test_lazy_bound_is_bit_identical(hs, ea_golden):
             a, sa = hs_solve(hs, c, comp=comp, custom_init=True, ri=ri)
             b, sb = hs_solve(ref, c, comp=comp, custom_init=True, ri=ri)
             assert np.array_equal(a.view(np.uint64), b.view(np.uint64)) and np.array_equal(sa, sb), (name, comp, "warm")
+
+
+def test_device_code_update_count_is_the_reference_algorithms(ea_golden):
+    """the work the roofline is computed from: on a C2 sample the device solver (compiled for the host with work
+    counters, -DCB200_HOSTSIM_COUNT) performs the reference algorithm's number of root updates -- 95.2 per polynomial,
+    counted independently by the C oracle (test_oracle.py::test_c2_update_count) -- to a few parts per million, plus
+    exactly one confirming evaluation per root"""
+    so = os.path.join(HS, "libhostsim_count.so")
+    srcs = [os.path.join(HS, "hostsim.cpp")] + [os.path.join(ROOT, "caustics_b200", "csrc", f)
+                                                for f in os.listdir(os.path.join(ROOT, "caustics_b200", "csrc")) if f.endswith(".cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-DCB200_HOSTSIM_COUNT",
+                        "-o", so, os.path.join(HS, "hostsim.cpp"), "-lm"], check=True)
+    lib = ctypes.CDLL(so)
+    w = np.linspace(-2, 2, 1_000_000)[::500] + 0.1j
+    c = np.ascontiguousarray(lens.poly_coeffs(w, 3, **C2_PARAMS)[:, ::-1])
+    out = (ctypes.c_longlong * 2)()
+    lib.hostsim_counters(out, 1)
+    hs_solve(lib, c)
+    lib.hostsim_counters(out, 1)
+    evals, updates = out[0], out[1]
+    _, _, st = solver.port_solve(c, return_stats=True)
+    assert abs(updates - st[0]) <= 1e-4 * st[0]
+    assert 95.0 < updates / len(c) < 95.4
+    assert evals - updates == 10 * len(c)
