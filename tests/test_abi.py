@@ -68,6 +68,10 @@ def test_fails_loudly_without_gpu(built_lib):
         cb.poly_roots(np.ones((3, 6), dtype=np.complex128))
     with pytest.raises(CausticsError):
         cb.mag_point_source(np.zeros(4, dtype=np.complex128) + 0.1, nlenses=2, s=0.9, q=0.2)
+    with pytest.raises(CausticsError):
+        cb.mag_point_source_map(-1.5, -1.5, 1e-3, 1e-3, 10, 10, s=0.9, q=0.2)
+    with pytest.raises(ValueError):          # argument errors come before the device check
+        cb.mag_point_source_map(-1.5, -1.5, 1e-3, 1e-3, 10, 10, nlenses=1)
 
 
 def test_product_never_imports_oracle():
