@@ -68,6 +68,17 @@ SIGNATURES = {
     "caustics_mag_point_source": (_i, [_vp, _vp, _vp, _i64, _LP, _i, _i, _i, _vp]),
     "caustics_mag_point_source_grid": (_i, [_d, _d, _d, _d, _i64, _i64, _i64, _vp, _LP, _i, _i, _i, _vp]),
     "caustics_mag_point_source_host": (_i, [_vp, _vp, _i64, _LP, _i, _i, _i]),
+    "caustics_mag_point_source_grid_host": (_i, [_d, _d, _d, _d, _i64, _i64, _i64, _vp, _LP, _i, _i, _i]),
+    "caustics_peer_alloc": (_i, [ctypes.POINTER(_vp), ctypes.c_size_t]),
+    "caustics_peer_free": (_i, [_vp]),
+    "caustics_peer_export": (_i, [_vp, _vp]),
+    "caustics_peer_open": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "caustics_peer_close": (_i, [_vp]),
+    "caustics_peer_enable": (_i, [_i]),
+    "caustics_set_tuning": (_i, [ctypes.c_char_p, _i]),
+    "caustics_mag_workspace_bytes": (ctypes.c_size_t, [_i64, _i64, _i, _i, _i, _i]),
+    "caustics_mag_extended_source_list": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _LP, _i, _i, _d, _i, _i, _i, _vp,
+                                               ctypes.c_size_t, _vp]),
     "caustics_bench_fp64_peak": (_i, [_vp, _i, _i, _vp]),
     "caustics_bench_fp64_peak3": (_i, [_vp, _i, _i, _vp]),
     "caustics_mag_gate": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _d, _LP, _d, _i, _i, _vp]),

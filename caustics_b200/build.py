@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcaustics_b200.so")
-SOURCES = ["kernels.cu", "host_pipeline.cu", "extended.cu", "lightcurve.cu"]
+SOURCES = ["kernels.cu", "host_pipeline.cu", "extended.cu", "lightcurve.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

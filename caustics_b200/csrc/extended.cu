@@ -23,12 +23,13 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/caustics_b200.h"
 #include "extended_core.cuh"
 #include "extended_host.h"
+#include "nvtx_range.h"
+#include "tuning.h"
 
 using namespace cb200;
 
@@ -36,30 +37,20 @@ namespace {
 
 constexpr int NT = 128;
 constexpr int64_t SMALL_BATCH = 16384;
-// Small batches can run the limb walk as several concurrent chains (limb_walk_chain_body).  It cuts the
-// walk's latency ~3x but relabels roots at the chain joins by nearest neighbour instead of by warm
-// start, which moves ~5 % of caustic-crossing results by ~1e-5 (inside the 1e-4 bar, but no longer the
-// reference's exact path), so it is opt-in: CAUSTICS_B200_LIMB_CHAINS=4.
-inline int limb_chains() {
-  static int k = -1;
-  if (k < 0) { const char* e = getenv("CAUSTICS_B200_LIMB_CHAINS"); k = e ? atoi(e) : 1; if (k < 1 || k > 16) k = 1; }
-  return k;
-}   // below this many sources the warp-per-source selection is used
-
 // Phase-variant mask: 1 warp-per-source selection, 2 stitching on a shared-memory copy of the tracks,
 // 4 warp-per-source limb-darkened sum, 8 lane-per-root limb walk, 16 lane-per-root refinement solves.
 // The batch-size rules below were measured on one B200 (npts_limb = 200): the lane-per-root walk wins
 // up to ~8192 (binary) / ~4096 (triple) sources, the lane-per-root refinement up to ~2048 / ~128.
 // `scale` = 16 for gated binary light curves, where only a few per cent of the points are integrated.
-// CAUSTICS_B200_SMALL_MASK overrides the rules (experiments only).
-inline int small_mask(int64_t n, int nlenses, int64_t scale) {
-  static int k = -2;
-  if (k == -2) { const char* e = getenv("CAUSTICS_B200_SMALL_MASK"); k = e ? atoi(e) : -1; }
+// `n` is the number of sources that are integrated (a gated call passes its estimate).
+// caustics_set_tuning("ext_variants", mask) overrides the rules (tests, experiments).
+inline int small_mask(int64_t n, int nlenses) {
+  const int k = tuning_get(TUNE_EXT_VARIANTS);
   if (k >= 0) return k & 31;
   int m = 0;
-  if (n <= scale * SMALL_BATCH) m |= 7;
-  if (n <= scale * (nlenses == 2 ? 8192 : 4096)) m |= 8;
-  if (n <= scale * (nlenses == 2 ? 2048 : 128)) m |= 16;
+  if (n <= SMALL_BATCH) m |= 7;
+  if (n <= (nlenses == 2 ? 8192 : 4096)) m |= 8;
+  if (n <= (nlenses == 2 ? 2048 : 128)) m |= 16;
   return m;
 }
 
@@ -79,15 +70,6 @@ __global__ void __launch_bounds__(NT) k_limb_walk_group(ExtCfg cfg, ExtBuf b, Le
 template <int NL>
 __global__ void __launch_bounds__(NT) k_refine_solve_group(ExtCfg cfg, ExtBuf b, LensConst L, int round) {
   refine_solve_group_body<NL>(cfg, b, L, round, threadIdx.x, (int64_t)blockIdx.x * (NT / 32) + threadIdx.x / 32);
-}
-template <int NL>
-__global__ void __launch_bounds__(NT) k_limb_walk_chains(ExtCfg cfg, ExtBuf b, LensConst L) {
-  __shared__ EASmem<NL * NL + 1, false, NT> sm;
-  limb_walk_chain_body<NL, NT>(cfg, b, L, sm, threadIdx.x, (int64_t)blockIdx.x * NT + threadIdx.x);
-}
-template <int D>
-__global__ void __launch_bounds__(NT) k_align_chains(ExtCfg cfg, ExtBuf b) {
-  align_chains_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
 __global__ void __launch_bounds__(NT) k_limb_walk_single(ExtCfg cfg, ExtBuf b, LensConst L) {
   limb_walk_single_body(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
@@ -182,8 +164,7 @@ __global__ void __launch_bounds__(NT) k_ld_sum_warp(ExtCfg cfg, ExtBuf b) {
     total += acc * b.cpar[(int64_t)c * cfg.S + s];
   }
   if (lane == 0) {
-    const int64_t out_idx = b.list ? (int64_t)b.list[s] : s;
-    b.mag[out_idx] = fabs(total) / (3.14159265358979323846 * cfg.rho * cfg.rho);
+    b.mag[src_index(b, s)] = fabs(total) / (3.14159265358979323846 * cfg.rho * cfg.rho);
   }
 }
 template <bool COMP>
@@ -213,10 +194,7 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
   const unsigned gs = (unsigned)((cfg.S + NT - 1) / NT);
   const unsigned gr = (unsigned)(((int64_t)cfg.nadd * cfg.S + NT - 1) / NT);
   if (NL == 1) k_limb_walk_single<<<gs, NT, 0, st>>>(cfg, b, L);
-  else if (cfg.chains > 1) {
-    k_limb_walk_chains<(NL == 1 ? 2 : NL)><<<(unsigned)(((int64_t)cfg.chains * cfg.S + NT - 1) / NT), NT, 0, st>>>(cfg, b, L);
-    k_align_chains<D><<<gs, NT, 0, st>>>(cfg, b);
-  } else if (cfg.small & 8) {
+  else if (cfg.small & 8) {
     constexpr int G = 32 / (NL == 1 ? 5 : NL * NL + 1);   // sources per warp
     const int64_t warps = (cfg.S + G - 1) / G;
     k_limb_walk_group<(NL == 1 ? 2 : NL)><<<(unsigned)((warps + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, L);
@@ -265,26 +243,65 @@ size_t caustics_ext_workspace_bytes(int64_t n, int nlenses, int npts_limb, int l
   return make_layout(c).total;
 }
 
-// Shared driver: `gate` != 0 runs the lightcurve.py dispatch (hexadecapole where valid), else every
-// point gets the full contour integration (mag_extended_source).
-static int ext_driver(const void* w, double* mag, uint8_t* test_out, int64_t n, double rho, const caustics_lens* lens,
-                      double q_for_gate, int gate, int npts_limb, int limb_darkening, double u1, int npts_ld,
-                      int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream) {
+size_t caustics_mag_workspace_bytes(int64_t n, int64_t max_full, int nlenses, int npts_limb, int limb_darkening,
+                                    int npts_ld) {
+  if (max_full > n) max_full = n;
+  if (max_full < 1) max_full = 1;
+  ExtCfg c;
+  if (n < 0 || make_cfg(max_full, 1.0, nlenses, npts_limb, limb_darkening, 0.0, npts_ld, 1, 0, &c)) return 0;
+  return make_layout(c, n).total;
+}
+
+}  // extern "C"
+
+namespace {
+
+// The largest number of sources (<= n) whose per-source arrays fit `bytes` next to a compact list of n
+// points; 0 when not even one fits.  The layout is monotone in S, so bisect.
+int64_t capacity_for(const ExtCfg& proto, int64_t n, size_t bytes) {
+  auto fits = [&](int64_t S) { ExtCfg c = proto; c.S = S; return make_layout(c, n).total <= bytes; };
+  if (fits(n)) return n;
+  if (!fits(1)) return 0;
+  int64_t lo = 1, hi = n;               // fits(lo), !fits(hi)
+  while (hi - lo > 1) { const int64_t mid = lo + (hi - lo) / 2; (fits(mid) ? lo : hi) = mid; }
+  return lo;
+}
+
+// Shared driver.
+//   gate == 0  every point of w gets the full contour integration (mag_extended_source)
+//   gate == 1  lightcurve.py dispatch: hexadecapole where the reference's tests pass, else integration
+//   gate == 2  the caller supplies the compact list of points to integrate (ext_list, ext_count on the
+//              device, at most n entries): second half of the two-call form caustics_mag_gate -> here
+// Gated calls integrate at most `cap` sources at a time, cap = what the workspace holds; with cap < n the
+// integration phases are enqueued ceil(n / cap) times over consecutive windows of the list and a window
+// past the device-side count exits at once (the count never visits the host).
+int ext_driver(const void* w, double* mag, uint8_t* test_out, int64_t n, double rho, const caustics_lens* lens,
+               double q_for_gate, int gate, const int32_t* ext_list, const int32_t* ext_count, int npts_limb,
+               int limb_darkening, double u1, int npts_ld, int itmax, int compensated, void* workspace,
+               size_t workspace_bytes, void* stream) {
   if (!lens || n < 0) return CAUSTICS_ERR_BAD_ARG;
   ExtCfg cfg;
   int rc = make_cfg(n, rho, lens->nlenses, npts_limb, limb_darkening, u1, npts_ld, itmax, compensated, &cfg);
   if (rc) return rc;
   if (n == 0) return CAUSTICS_OK;
-  // small-batch (warp-per-source / staged) phase variants: few sources to integrate.  With the gate on
-  // only the points that fail it are integrated (a few per cent of a light curve), so the bound on n is
-  // 16x higher there.
-  const int64_t scale = gate && lens->nlenses == 2 ? 16 : 1;
-  cfg.small = small_mask(n, lens->nlenses, scale);
-  if (n <= scale * SMALL_BATCH && cfg.N0 >= 32) cfg.chains = limb_chains();
-  if (n > 0x7fffffffLL / (cfg.VMAX > NADD_MAX ? cfg.VMAX : NADD_MAX)) return CAUSTICS_ERR_BAD_ARG;  // index range of one call
   if (!w || !mag || !workspace) return CAUSTICS_ERR_BAD_ARG;
-  const Layout lay = make_layout(cfg);
+  if (gate == 2 && (!ext_list || !ext_count)) return CAUSTICS_ERR_BAD_ARG;
+  if (n > 0x7fffffffLL) return CAUSTICS_ERR_BAD_ARG;
+  const int64_t idx_cap = 0x7fffffffLL / (cfg.VMAX > NADD_MAX ? cfg.VMAX : NADD_MAX);   // index range of one pass
+  int64_t cap = n;
+  if (gate) {
+    cap = capacity_for(cfg, n, workspace_bytes);
+    if (cap > idx_cap) cap = idx_cap;
+    if (cap < 1) return CAUSTICS_ERR_BAD_ARG;
+  } else if (n > idx_cap) return CAUSTICS_ERR_BAD_ARG;
+  cfg.S = cap;
+  const Layout lay = make_layout(cfg, gate ? n : -1);
   if (workspace_bytes < lay.total) return CAUSTICS_ERR_BAD_ARG;
+  // Phase variants by the number of sources that are integrated.  A binary-lens gate sends a few per
+  // cent of a light curve to the integration (measured rule of round 1: the small-batch bounds apply to
+  // 16x the point count); a caller-supplied list is sized by its capacity.
+  const int64_t n_int = gate == 1 && lens->nlenses == 2 ? (n + 15) / 16 : (cap < n ? cap : n);
+  cfg.small = small_mask(n_int, lens->nlenses);
   LensConst L;
   memset(&L, 0, sizeof(L));
   if (lens->nlenses == 1) { L.nlenses = 1; L.x_cm = 0.0; L.eps[0] = 1.0; }
@@ -311,7 +328,7 @@ static int ext_driver(const void* w, double* mag, uint8_t* test_out, int64_t n, 
       k_store_table<<<1, TabChunk::N, 0, st>>>(c, (double*)(base + lay.gl) + off, m);
     }
   }
-  if (gate && lens->nlenses == 2) {
+  if (gate == 1 && lens->nlenses == 2) {
     cudaError_t e = cudaMemsetAsync(count, 0, 4, st);
     if (e != cudaSuccess) return cuda_rc(e);
     if (compensated)
@@ -319,23 +336,44 @@ static int ext_driver(const void* w, double* mag, uint8_t* test_out, int64_t n, 
     else
       k_gate<false><<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>((const double2*)w, mag, test_out, list, count, n, L, rho, q_for_gate, itmax);
     b.list = list; b.count = count;
-  } else if (gate) {
+  } else if (gate == 1) {
     k_iota<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(list, count, n);
     if (test_out) { cudaError_t e = cudaMemsetAsync(test_out, 0, (size_t)n, st); if (e != cudaSuccess) return cuda_rc(e); }
     b.list = list; b.count = count;
+  } else if (gate == 2) {
+    b.list = ext_list; b.count = ext_count;
   }
-  switch (lens->nlenses) {
-    case 1: return run_pipeline<1>(cfg, b, L, st);
-    case 2: return run_pipeline<2>(cfg, b, L, st);
-    default: return run_pipeline<3>(cfg, b, L, st);
+  for (int64_t off = 0; off < n; off += cap) {
+    b.list_off = off;
+    switch (lens->nlenses) {
+      case 1: rc = run_pipeline<1>(cfg, b, L, st); break;
+      case 2: rc = run_pipeline<2>(cfg, b, L, st); break;
+      default: rc = run_pipeline<3>(cfg, b, L, st); break;
+    }
+    if (rc || !gate) break;
   }
+  return rc;
 }
+
+}  // namespace
+
+extern "C" {
 
 int caustics_mag_extended_source(const void* w, double* mag, int64_t n, double rho, const caustics_lens* lens,
                                  int npts_limb, int limb_darkening, double u1, int npts_ld, int itmax,
                                  int compensated, void* workspace, size_t workspace_bytes, void* stream) {
-  return ext_driver(w, mag, nullptr, n, rho, lens, 0.0, 0, npts_limb, limb_darkening, u1, npts_ld, itmax,
-                    compensated, workspace, workspace_bytes, stream);
+  CB200_NVTX("caustics_mag_extended_source");
+  return ext_driver(w, mag, nullptr, n, rho, lens, 0.0, 0, nullptr, nullptr, npts_limb, limb_darkening, u1, npts_ld,
+                    itmax, compensated, workspace, workspace_bytes, stream);
+}
+
+int caustics_mag_extended_source_list(const void* w, double* mag, const int32_t* list, const int32_t* count,
+                                      int64_t max_count, double rho, const caustics_lens* lens, int npts_limb,
+                                      int limb_darkening, double u1, int npts_ld, int itmax, int compensated,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  CB200_NVTX("caustics_mag_extended_source_list");
+  return ext_driver(w, mag, nullptr, max_count, rho, lens, 0.0, 2, list, count, npts_limb, limb_darkening, u1,
+                    npts_ld, itmax, compensated, workspace, workspace_bytes, stream);
 }
 
 int caustics_ext_contour_capacity(int nlenses, int npts_limb, int* vmax, int* cmax) {
@@ -351,13 +389,13 @@ int caustics_ext_contours(const void* w, double* mag, int64_t n, double rho, con
                           int npts_limb, int itmax, int compensated, void* workspace, size_t workspace_bytes,
                           void* vz, double* vtheta, uint8_t* vcid, int32_t* vcount, double* cpar,
                           int32_t* cstart, int32_t* ncont, void* stream) {
+  CB200_NVTX("caustics_ext_contours");
   if (!lens || n < 0) return CAUSTICS_ERR_BAD_ARG;
   ExtCfg cfg;
   int rc = make_cfg(n, rho, lens->nlenses, npts_limb, 0, 0.0, 100, itmax, compensated, &cfg);
   if (rc) return rc;
   if (n == 0) return CAUSTICS_OK;
-  cfg.small = small_mask(n, lens->nlenses, 1);
-  if (n <= SMALL_BATCH && cfg.N0 >= 32) cfg.chains = limb_chains();
+  cfg.small = small_mask(n, lens->nlenses);
   if (n > 0x7fffffffLL / cfg.VMAX) return CAUSTICS_ERR_BAD_ARG;
   if (!w || !workspace || !vz || !vtheta || !vcid || !vcount || !cpar || !cstart || !ncont) return CAUSTICS_ERR_BAD_ARG;
   const Layout lay = make_layout(cfg);
@@ -383,6 +421,7 @@ int caustics_ext_contours(const void* w, double* mag, int64_t n, double rho, con
 int caustics_mag_gate(const void* w, double* mag, uint8_t* used_hexadecapole, int32_t* list, int32_t* count,
                       int64_t n, double rho, const caustics_lens* lens, double q, int itmax, int compensated,
                       void* stream) {
+  CB200_NVTX("caustics_mag_gate");
   if (!lens || lens->nlenses != 2 || n < 0 || !(rho > 0.0) || itmax < 0) return CAUSTICS_ERR_BAD_ARG;
   if (n == 0) return CAUSTICS_OK;
   if (n > 0x7fffffffLL || !w || !mag || !list || !count) return CAUSTICS_ERR_BAD_ARG;
@@ -402,8 +441,9 @@ int caustics_mag_gate(const void* w, double* mag, uint8_t* used_hexadecapole, in
 int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t n, double rho,
                  const caustics_lens* lens, double q, int npts_limb, int limb_darkening, double u1, int npts_ld,
                  int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream) {
-  return ext_driver(w, mag, used_hexadecapole, n, rho, lens, q, 1, npts_limb, limb_darkening, u1, npts_ld, itmax,
-                    compensated, workspace, workspace_bytes, stream);
+  CB200_NVTX("caustics_mag");
+  return ext_driver(w, mag, used_hexadecapole, n, rho, lens, q, 1, nullptr, nullptr, npts_limb, limb_darkening, u1,
+                    npts_ld, itmax, compensated, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -33,15 +33,6 @@ constexpr int NITER = 10;          // refinement rounds, extended_source.py:71
 constexpr int MAXSEG = 30;         // 3 * (nlenses^2 + 1), extended_source.py:279-280
 constexpr int MAXPARTS = 10;       // per track, extended_source.py:202-203
 constexpr double JIT_RE = 3.1e-7, JIT_IM = -5.3e-7;  // fixed stand-ins for U(+-1e-6) (:83-85)
-#ifndef CB200_EXT_PREDICT
-#define CB200_EXT_PREDICT 0
-#endif
-#ifndef CB200_EXT_PREDICT_MAXSTEP2
-#define CB200_EXT_PREDICT_MAXSTEP2 1e-2
-#endif
-#ifndef CB200_EXT_PREDICT_SEP
-#define CB200_EXT_PREDICT_SEP 1e300   /* predict a root only if (its step)^2 < SEP * (distance to the nearest other root)^2 */
-#endif
 constexpr double DUP_JIT = 7.0e-10;                  // stand-in for U(+-1e-9) (:146)
 
 struct ExtCfg {
@@ -49,7 +40,6 @@ struct ExtCfg {
   double rho;
   int itmax, comp, ld, n1, n2, VMAX, CMAX;
   int small;        // mask of small-batch phase variants: 1 warp select, 2 staged contours, 4 warp LD sum, 8 lane-per-root walk
-  int chains;       // limb walk split into this many independently started chains (small batches)
   int emit;         // 1: k_contours also writes the contour vertex lists (z, theta, contour id) for the host
   double u1;
   int64_t S;        // capacity (stride) of the source axis
@@ -58,7 +48,8 @@ struct ExtCfg {
 struct ExtBuf {
   const cb200_d2* w;       // source positions (all points of the call)
   const int32_t* list;     // optional: indices into w of the sources to integrate (else identity)
-  const int32_t* count;    // optional: device-side number of sources (else S)
+  const int32_t* count;    // optional: device-side number of listed sources (else S)
+  int64_t list_off;        // this pass integrates list[list_off .. list_off + S) (gated calls with a small workspace)
   double* theta;           // [NP][S]   by arrival slot
   double* zre; double* zim; uint8_t* flg;   // [NP][D][S] by arrival slot; flg bit0 real, bit1 det>0
   uint16_t* order;         // [NP][S]   arrival slot of the p-th point in theta order
@@ -75,14 +66,18 @@ struct ExtBuf {
 };
 
 __device__ __forceinline__ int64_t nsrc(const ExtCfg& c, const ExtBuf& b) {
-  return b.count ? (int64_t)*b.count : c.S;
+  if (!b.count) return c.S;
+  const int64_t left = (int64_t)*b.count - b.list_off;
+  return left < 0 ? 0 : (left < c.S ? left : c.S);
+}
+__device__ __forceinline__ int64_t src_index(const ExtBuf& b, int64_t s) {
+  return b.list ? (int64_t)b.list[b.list_off + s] : s;
 }
 #define I2(p, s) ((int64_t)(p) * cfg.S + (s))
 #define I3(p, j, s) (((int64_t)(p) * cfg.D + (j)) * cfg.S + (s))
 
 __device__ __forceinline__ cd source_centre(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s) {
-  const int64_t k = b.list ? (int64_t)b.list[s] : s;
-  const cb200_d2 v = b.w[k];
+  const cb200_d2 v = b.w[src_index(b, s)];
   return mk(v.x + L.x_cm, v.y);
 }
 __device__ __forceinline__ cd limb_point(cd w0, double rho, double theta) {
@@ -144,29 +139,9 @@ template <int NL, int NT>
 __device__ void limb_walk_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, EASmem<NL * NL + 1, false, NT>& sm, int tid, int64_t s) {
   const bool active = s < nsrc(cfg, b);
   const cd w0 = active ? source_centre(cfg, b, L, s) : mk(0.3, 0.2);
-#if CB200_EXT_PREDICT
-  double ppr[NL * NL + 1], ppi[NL * NL + 1];   // experiment: roots of the limb point before the previous one
-#endif
   for (int k = 0; k < cfg.N0; ++k) {
     const double th = theta_init(k, cfg.N0);
     const cd w = limb_point(w0, cfg.rho, th);
-#if CB200_EXT_PREDICT
-    if (active && k >= 1 && k < cfg.N0 - 1) {   // (the last point repeats theta = -pi: no extrapolation)
-      constexpr int D_ = NL * NL + 1;
-      double cr[D_], ci[D_];
-      for (int j = 0; j < D_; ++j) { cr[j] = sm.zre[j][tid]; ci[j] = sm.zim[j][tid]; }
-      for (int j = 0; j < D_; ++j) {
-        const double dr = cr[j] - ppr[j], di = ci[j] - ppi[j];
-        double sep2 = 1e300;   // squared distance to the nearest other root
-        for (int i = 0; i < D_; ++i)
-          if (i != j) sep2 = fmin(sep2, (cr[j] - cr[i]) * (cr[j] - cr[i]) + (ci[j] - ci[i]) * (ci[j] - ci[i]));
-        if (k >= 2 && dr * dr + di * di < CB200_EXT_PREDICT_MAXSTEP2 && dr * dr + di * di < CB200_EXT_PREDICT_SEP * sep2) {
-          sm.zre[j][tid] = cr[j] + dr; sm.zim[j][tid] = ci[j] + di;
-        }
-        ppr[j] = cr[j]; ppi[j] = ci[j];
-      }
-    }
-#endif
     // roots_compensated is not forwarded to the sequential walk (extended_source.py:104-106)
     solve_and_store<NL, false, NT>(cfg, b, L, sm, tid, active, w, k > 0, k, s);
     if (active) {
@@ -222,82 +197,6 @@ __device__ void limb_walk_group_body(const ExtCfg& cfg, const ExtBuf& b, const L
   }
 }
 #endif
-
-// Small batches: the limb walk is a chain of N0 dependent solves per source, pure latency when there
-// are only a few hundred sources.  It is cut into cfg.chains chains that start cold and run
-// concurrently (thread per (chain, source)); align_chains_body then relabels each chain's roots so
-// that row i continues row i of the previous chain's last point -- greedy nearest neighbour, the same
-// rule the reference applies along the whole limb (utils.py:15-40) -- which restores the continuity
-// along rows that the sequential warm start provides and the refinement step relies on.
-template <int NL, int NT>
-__device__ void limb_walk_chain_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,
-                                     EASmem<NL * NL + 1, false, NT>& sm, int tid, int64_t g) {
-  const int c = (int)(g / cfg.S);
-  const int64_t s = g - (int64_t)c * cfg.S;
-  const int len = (cfg.N0 + cfg.chains - 1) / cfg.chains;
-  const int k0 = c * len, k1 = (k0 + len < cfg.N0) ? k0 + len : cfg.N0;
-  const bool active = c < cfg.chains && s < nsrc(cfg, b);
-  const cd w0 = active ? source_centre(cfg, b, L, s) : mk(0.3, 0.2);
-  for (int k = k0; k < k0 + len; ++k) {      // uniform trip count across the warp
-    const bool act = active && k < k1;
-    const double th = theta_init(k < cfg.N0 ? k : cfg.N0 - 1, cfg.N0);
-    const cd w = limb_point(w0, cfg.rho, th);
-    solve_and_store<NL, false, NT>(cfg, b, L, sm, tid, act, w, k > k0, k, s);
-    if (act) {
-      b.theta[I2(k, s)] = th;
-      b.order[I2(k, s)] = (uint16_t)k;
-    }
-  }
-}
-
-template <int D>
-__device__ void align_chains_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
-  if (s >= nsrc(cfg, b)) return;
-  const int len = (cfg.N0 + cfg.chains - 1) / cfg.chains;
-  for (int c = 1; c < cfg.chains; ++c) {
-    const int k0 = c * len, k1 = (k0 + len < cfg.N0) ? k0 + len : cfg.N0;
-    if (k0 >= cfg.N0) break;
-    double pr[D], pi_[D], zr[D], zi[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-      pr[j] = b.zre[I3(k0 - 1, j, s)]; pi_[j] = b.zim[I3(k0 - 1, j, s)];
-      zr[j] = b.zre[I3(k0, j, s)]; zi[j] = b.zim[I3(k0, j, s)];
-    }
-    int perm[D];
-    unsigned used = 0;
-    bool ident = true;
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      double bd = 1e300; int best = -1;
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        const double dx = zr[k] - pr[i], dy = zi[k] - pi_[i];
-        const double d2 = dx * dx + dy * dy;
-        if (!((used >> k) & 1u) && d2 < bd) { bd = d2; best = k; }
-      }
-      if (best < 0) {
-#pragma unroll
-        for (int k = D - 1; k >= 0; --k) if (!((used >> k) & 1u)) best = k;
-      }
-      used |= 1u << best;
-      perm[i] = best;
-      ident = ident && best == i;
-    }
-    if (ident) continue;
-    for (int k = k0; k < k1; ++k) {
-      double cr[D], ci[D]; uint8_t cf[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) { cr[j] = b.zre[I3(k, j, s)]; ci[j] = b.zim[I3(k, j, s)]; cf[j] = b.flg[I3(k, j, s)]; }
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        double vr = 0, vi = 0; uint8_t vf = 0;
-#pragma unroll
-        for (int j = 0; j < D; ++j) if (j == perm[i]) { vr = cr[j]; vi = ci[j]; vf = cf[j]; }
-        b.zre[I3(k, i, s)] = vr; b.zim[I3(k, i, s)] = vi; b.flg[I3(k, i, s)] = vf;
-      }
-    }
-  }
-}
 
 __device__ void limb_walk_single_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s) {
   if (s >= nsrc(cfg, b)) return;
@@ -525,27 +424,6 @@ __device__ void refine_solve_body(const ExtCfg& cfg, const ExtBuf& b, const Lens
       sm.zre[j][tid] = b.zre[I3(lf, j, s)] + JIT_RE;
       sm.zim[j][tid] = b.zim[I3(lf, j, s)] + JIT_IM;
     }
-#if CB200_EXT_PREDICT
-    {   // experiment: interpolate between the two ends of the interval the new point splits
-      const int rt = b.right[I2(r, s)];
-      const double tl = b.theta[I2(lf, s)], tr = b.theta[I2(rt, s)], tn = b.theta[I2(slot, s)];
-      const double t = (tn - tl) / (tr - tl);
-      for (int j = 0; j < D; ++j) {
-        const double lr = b.zre[I3(lf, j, s)], li = b.zim[I3(lf, j, s)];
-        const double dr = b.zre[I3(rt, j, s)] - lr, di = b.zim[I3(rt, j, s)] - li;
-        double sep2 = 1e300;
-        for (int i = 0; i < D; ++i)
-          if (i != j) {
-            const double er = lr - b.zre[I3(lf, i, s)], ei = li - b.zim[I3(lf, i, s)];
-            sep2 = fmin(sep2, er * er + ei * ei);
-          }
-        if (dr * dr + di * di < CB200_EXT_PREDICT_MAXSTEP2 && dr * dr + di * di < CB200_EXT_PREDICT_SEP * sep2) {
-          sm.zre[j][tid] += t * dr;
-          sm.zim[j][tid] += t * di;
-        }
-      }
-    }
-#endif
   }
   solve_and_store<NL, COMP, NT>(cfg, b, L, sm, tid, active, w, true, slot, s);
   if (active) update_widths<D>(cfg, b, r, slot, s);
@@ -795,7 +673,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
   const Tracks T{cfg, b, s, stage};
   const int NP = cfg.NP;
   const double norm = 1.0 / (3.14159265358979323846 * cfg.rho * cfg.rho);
-  const int64_t out_idx = b.list ? (int64_t)b.list[s] : s;
+  const int64_t out_idx = src_index(b, s);
   double total = 0.0;
   const bool emit = cfg.ld || cfg.emit;
   LdEmit E{cfg, b, s, 0, 0};
@@ -1046,7 +924,7 @@ __device__ void ld_sum_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
     }
     total += acc * b.cpar[(int64_t)c * cfg.S + s];
   }
-  const int64_t out_idx = b.list ? (int64_t)b.list[s] : s;
+  const int64_t out_idx = src_index(b, s);
   b.mag[out_idx] = fabs(total) / (3.14159265358979323846 * cfg.rho * cfg.rho);
 }
 

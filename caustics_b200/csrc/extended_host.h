@@ -37,9 +37,12 @@ struct Layout {
 };
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-inline Layout make_layout(const ExtCfg& c) {
+// `npoints`: capacity of the gate's compact list (all points of the call); the per-source arrays are
+// sized by c.S, the number of sources integrated at a time.
+inline Layout make_layout(const ExtCfg& c, int64_t npoints = -1) {
   Layout l; size_t o = 0;
   const size_t S = (size_t)c.S, NP = c.NP, D = c.D;
+  const size_t NL = npoints > (int64_t)S ? (size_t)npoints : S;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
   l.theta = take(NP * S * 8);
   l.zre = take(NP * D * S * 8); l.zim = take(NP * D * S * 8); l.flg = take(NP * D * S);
@@ -51,7 +54,7 @@ inline Layout make_layout(const ExtCfg& c) {
     l.cz0 = take((size_t)c.CMAX * S * 16); l.cpar = take((size_t)c.CMAX * S * 8); l.cstart = take((size_t)(c.CMAX + 1) * S * 4);
     l.gl = take((size_t)(c.n1 + c.n2) * 16);
   } else { l.vz = l.vP = l.vQ = l.vcid = l.vcount = l.ncont = l.cz0 = l.cpar = l.cstart = l.gl = 0; }
-  l.list = take(S * 4); l.count = take(256);
+  l.list = take(NL * 4); l.count = take(256);
   l.total = o;
   return l;
 }
@@ -72,7 +75,6 @@ inline int make_cfg(int64_t S, double rho, int nlenses, int npts_limb, int limb_
   c.CMAX = c.D + 3;
   c.VMAX = c.D * c.NP + c.CMAX;
   c.S = S > 0 ? S : 1;
-  c.chains = 1;
   *out = c;
   return CAUSTICS_OK;
 }

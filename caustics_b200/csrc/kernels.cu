@@ -11,7 +11,9 @@
 #include "ea_core.cuh"
 #include "lens_core.cuh"
 #include "ps_walk.cuh"
-#include <stdlib.h>
+#include "nvtx_range.h"
+#include "tuning.h"
+#include <atomic>
 
 using namespace cb200;
 
@@ -285,9 +287,9 @@ ps_path_walk_kernel(const double* __restrict__ w, double* __restrict__ mag, int6
 }
 
 // rows per walk: 32 when the map is large enough to fill the machine several times over, shorter walks
-// (more CTAs) for small maps; CAUSTICS_B200_GRID_RUN overrides (experiments)
+// (more CTAs) for small maps; caustics_set_tuning("grid_run", v) overrides (tests, experiments)
 int grid_walk_run(int64_t ncolblk, int64_t nrows) {
-  if (const char* e = getenv("CAUSTICS_B200_GRID_RUN")) { const int v = atoi(e); if (v >= 1 && v <= 4096) return v; }
+  { const int v = cb200::tuning_get(cb200::TUNE_GRID_RUN); if (v >= 1 && v <= 4096) return v; }
   int run = 32;
   while (run > 4 && ncolblk * ((nrows + run - 1) / run) < 148 * 16) run >>= 1;
   return run;
@@ -296,7 +298,7 @@ int grid_walk_run(int64_t ncolblk, int64_t nrows) {
 // elements per thread of a path walk: long enough to amortise the cold first solve, short enough that
 // the batch still fills the machine (>= ~16 warps per SM)
 int path_walk_run(int64_t n) {
-  if (const char* e = getenv("CAUSTICS_B200_PATH_RUN")) { const int v = atoi(e); if (v >= 1 && v <= 4096) return v; }
+  { const int v = cb200::tuning_get(cb200::TUNE_PATH_RUN); if (v >= 1 && v <= 4096) return v; }
   int run = 32;
   while (run > 1 && n / run < 148 * 16 * 32) run >>= 1;
   return run;
@@ -309,8 +311,7 @@ int launch_path_walk(const void* w, double* mag, int64_t n, const LensConst& L, 
   const int64_t nthreads = (n + run - 1) / run;
   const int64_t nblk = (nthreads + NTW - 1) / NTW;
   if (nblk > 0x7fffffffLL) return CAUSTICS_ERR_BAD_ARG;
-  const char* e = getenv("CAUSTICS_B200_GRID_EXTRAP");
-  const int extrap = e ? atoi(e) : 1;
+  const int extrap = cb200::tuning_get(cb200::TUNE_GRID_EXTRAP) == 0 ? 0 : 1;   // default (unset = -1): on
   if (compensated) ps_path_walk_kernel<NL, true><<<(unsigned)nblk, NTW, 0, st>>>((const double*)w, mag, n, run, L, itmax, extrap);
   else ps_path_walk_kernel<NL, false><<<(unsigned)nblk, NTW, 0, st>>>((const double*)w, mag, n, run, L, itmax, extrap);
   return cuda_rc(cudaGetLastError());
@@ -323,8 +324,7 @@ int launch_grid_walk(GridSpec g, double* mag, int64_t nrows, const LensConst& L,
   const int run = grid_walk_run(ncolblk, nrows);
   const int64_t nblk = ncolblk * ((nrows + run - 1) / run);
   if (nblk > 0x7fffffffLL) return CAUSTICS_ERR_BAD_ARG;
-  const char* e = getenv("CAUSTICS_B200_GRID_EXTRAP");
-  const int extrap = e ? atoi(e) : 1;
+  const int extrap = cb200::tuning_get(cb200::TUNE_GRID_EXTRAP) == 0 ? 0 : 1;   // default (unset = -1): on
   if (compensated) ps_grid_walk_kernel<NL, true><<<(unsigned)nblk, NTW, 0, st>>>(g, mag, nrows, run, ncolblk, L, itmax, extrap);
   else ps_grid_walk_kernel<NL, false><<<(unsigned)nblk, NTW, 0, st>>>(g, mag, nrows, run, ncolblk, L, itmax, extrap);
   return cuda_rc(cudaGetLastError());
@@ -397,7 +397,14 @@ int launch_ps(const double2* w, GridSpec g, const double2* z_init, double2* z, u
   return cuda_rc(cudaGetLastError());
 }
 
-thread_local int g_last_xla_error = 0;
+// Sticky status of the XLA custom calls, process-wide: XLA runs custom calls on its own launcher
+// thread, the Python side that wants to know reads from another one.  The FIRST error sticks until read.
+std::atomic<int> g_last_xla_error{0};
+inline void set_xla_error(int rc) {
+  if (rc == 0) return;
+  int expected = 0;
+  g_last_xla_error.compare_exchange_strong(expected, rc);
+}
 
 
 // Same, but every DFMA reads three DISTINCT, changing register pairs (no constant or repeated
@@ -476,6 +483,7 @@ extern "C" {
 
 int caustics_ea_jvp(const void* coeffs, const void* roots, const void* dcoeffs, void* droots, int64_t size, int deg,
                     void* stream) {
+  CB200_NVTX("caustics_ea_jvp");
   if (size < 0 || deg < 1 || deg > 32) return CAUSTICS_ERR_BAD_ARG;
   if (size == 0) return CAUSTICS_OK;
   if (!coeffs || !roots || !dcoeffs || !droots) return CAUSTICS_ERR_BAD_ARG;
@@ -486,6 +494,7 @@ int caustics_ea_jvp(const void* coeffs, const void* roots, const void* dcoeffs, 
 
 int caustics_ea_vjp(const void* coeffs, const void* roots, const void* groots, void* gcoeffs, int64_t size, int deg,
                     void* stream) {
+  CB200_NVTX("caustics_ea_vjp");
   if (size < 0 || deg < 1 || deg > 32) return CAUSTICS_ERR_BAD_ARG;
   if (size == 0) return CAUSTICS_OK;
   if (!coeffs || !roots || !groots || !gcoeffs) return CAUSTICS_ERR_BAD_ARG;
@@ -501,6 +510,7 @@ int caustics_bench_fp64_peak3(double* sink, int blocks, int iters, void* stream)
 }
 
 int caustics_match_tracks(const void* z, void* out, int64_t nsets, int npts, int deg, void* stream) {
+  CB200_NVTX("caustics_match_tracks");
   if (nsets < 0 || npts < 0 || deg < 1 || deg > 16) return CAUSTICS_ERR_BAD_ARG;
   if (nsets == 0 || npts == 0) return CAUSTICS_OK;
   if (!z || !out) return CAUSTICS_ERR_BAD_ARG;
@@ -514,7 +524,9 @@ int caustics_bench_fp64_peak(double* sink, int blocks, int iters, void* stream) 
   return cuda_rc(cudaGetLastError());
 }
 
-const char* caustics_version(void) { return "caustics_b200 0.1 (sm_100a)"; }
+const char* caustics_version(void) { return "caustics_b200 0.2 (sm_100a)"; }
+
+int caustics_set_tuning(const char* key, int value) { return cb200::tuning_set(key, value) ? CAUSTICS_OK : CAUSTICS_ERR_BAD_ARG; }
 
 int caustics_device_count(void) {
   int n = 0;
@@ -539,6 +551,7 @@ const char* caustics_error_string(int code) {
 int caustics_ea_solve(const void* coeffs, const void* roots_init, void* roots, int32_t* sweeps,
                       int64_t size, int deg, int itmax, int compensated, int custom_init,
                       int flags, void* stream) {
+  CB200_NVTX("caustics_ea_solve");
   if (size < 0 || itmax < 0) return CAUSTICS_ERR_BAD_ARG;
   if (!caustics_ea_degree_supported(deg)) return CAUSTICS_ERR_UNSUPPORTED_DEGREE;
   if (size == 0) return CAUSTICS_OK;
@@ -566,17 +579,17 @@ size_t caustics_ea_make_descriptor(caustics_ea_descriptor* out, int64_t size, in
   return sizeof(caustics_ea_descriptor);
 }
 
-int caustics_last_xla_error(void) { return g_last_xla_error; }
+int caustics_last_xla_error(void) { return g_last_xla_error.exchange(0); }
 
 void caustics_ea_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len) {
   if (opaque_len != sizeof(caustics_ea_descriptor) || !opaque || !buffers) {
-    g_last_xla_error = CAUSTICS_ERR_BAD_DESCRIPTOR;  // the reference throws here (kernel_helpers.h:37-42)
+    set_xla_error(CAUSTICS_ERR_BAD_DESCRIPTOR);  // the reference throws here (kernel_helpers.h:37-42)
     return;
   }
   caustics_ea_descriptor d;
   memcpy(&d, opaque, sizeof(d));
-  g_last_xla_error = caustics_ea_solve(buffers[0], buffers[1], buffers[2], nullptr, d.size, d.deg, d.itmax,
-                                       d.compensated, d.custom_init, d.flags, stream);
+  set_xla_error(caustics_ea_solve(buffers[0], buffers[1], buffers[2], nullptr, d.size, d.deg, d.itmax,
+                                  d.compensated, d.custom_init, d.flags, stream));
 }
 
 static_assert(sizeof(caustics_mag_ps_descriptor) == 72 && sizeof(caustics_mag_ext_descriptor) == 112 &&
@@ -585,34 +598,35 @@ static_assert(sizeof(caustics_mag_ps_descriptor) == 72 && sizeof(caustics_mag_ex
 
 void caustics_mag_ps_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len) {
   if (opaque_len != sizeof(caustics_mag_ps_descriptor) || !opaque || !buffers) {
-    g_last_xla_error = CAUSTICS_ERR_BAD_DESCRIPTOR;
+    set_xla_error(CAUSTICS_ERR_BAD_DESCRIPTOR);
     return;
   }
   caustics_mag_ps_descriptor d;
   memcpy(&d, opaque, sizeof(d));
-  g_last_xla_error = caustics_mag_point_source(buffers[0], (double*)buffers[1], nullptr, d.n, &d.lens, d.itmax,
-                                               d.compensated, d.flags, stream);
+  set_xla_error(caustics_mag_point_source(buffers[0], (double*)buffers[1], nullptr, d.n, &d.lens, d.itmax,
+                                          d.compensated, d.flags, stream));
 }
 
 void caustics_mag_ext_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len) {
   if (opaque_len != sizeof(caustics_mag_ext_descriptor) || !opaque || !buffers) {
-    g_last_xla_error = CAUSTICS_ERR_BAD_DESCRIPTOR;
+    set_xla_error(CAUSTICS_ERR_BAD_DESCRIPTOR);
     return;
   }
   caustics_mag_ext_descriptor d;
   memcpy(&d, opaque, sizeof(d));
-  g_last_xla_error =
+  set_xla_error(
       d.gate ? caustics_mag(buffers[0], (double*)buffers[1], nullptr, d.n, d.rho, &d.lens, d.q, d.npts_limb,
                             d.limb_darkening, d.u1, d.npts_ld, d.itmax, d.compensated, buffers[2],
                             (size_t)d.workspace_bytes, stream)
              : caustics_mag_extended_source(buffers[0], (double*)buffers[1], d.n, d.rho, &d.lens, d.npts_limb,
                                             d.limb_darkening, d.u1, d.npts_ld, d.itmax, d.compensated, buffers[2],
-                                            (size_t)d.workspace_bytes, stream);
+                                            (size_t)d.workspace_bytes, stream));
 }
 
 int caustics_images_point_source(const void* w, const void* z_init, void* z, uint8_t* mask,
                                  int64_t n, const caustics_lens* lens, int itmax, int compensated,
                                  int custom_init, int flags, void* stream) {
+  CB200_NVTX("caustics_images_point_source");
   LensConst L;
   int rc = make_lens_const(lens, &L);
   if (rc) return rc;
@@ -628,6 +642,7 @@ int caustics_images_point_source(const void* w, const void* z_init, void* z, uin
 
 int caustics_images_point_source_sequential(const void* w, void* z, uint8_t* mask, int64_t npaths, int64_t n,
                                             const caustics_lens* lens, int itmax, int compensated, void* stream) {
+  CB200_NVTX("caustics_images_point_source_sequential");
   LensConst L;
   int rc = make_lens_const(lens, &L);
   if (rc) return rc;
@@ -648,6 +663,7 @@ int caustics_images_point_source_sequential(const void* w, void* z, uint8_t* mas
 int caustics_mag_point_source(const void* w, double* mag, uint8_t* nimages, int64_t n,
                               const caustics_lens* lens, int itmax, int compensated, int flags,
                               void* stream) {
+  CB200_NVTX("caustics_mag_point_source");
   LensConst L;
   int rc = make_lens_const(lens, &L);
   if (rc) return rc;
@@ -668,6 +684,7 @@ int caustics_mag_point_source_grid(double x0, double y0, double dx, double dy, i
                                    int64_t row_begin, int64_t row_end, double* mag,
                                    const caustics_lens* lens, int itmax, int compensated,
                                    int flags, void* stream) {
+  CB200_NVTX("caustics_mag_point_source_grid");
   LensConst L;
   int rc = make_lens_const(lens, &L);
   if (rc) return rc;

@@ -59,24 +59,41 @@ def _run(w, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax, r
     if n == 0:
         return (restore(mag), restore(test.bool())) if return_test else restore(mag)
     rho = float(rho)
-    chunk = _chunk_len(L, n, nlenses, npts_limb, limb_darkening, npts_ld)
+    ld, comp = int(bool(limb_darkening)), int(bool(roots_compensated))
+    cfg = (int(npts_limb), ld, float(u1), int(npts_ld), int(roots_itmax), comp)
     with torch.cuda.device(flat.device):
         st = torch.cuda.current_stream().cuda_stream
-        nbytes = L.caustics_ext_workspace_bytes(chunk, nlenses, npts_limb, int(limb_darkening), npts_ld)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
-        for off in range(0, n, chunk):
-            m = min(chunk, n - off)
-            wp = flat.data_ptr() + 16 * off
-            mp = mag.data_ptr() + 8 * off
-            if gate:
-                _lib.check(L.caustics_mag(wp, mp, test.data_ptr() + off, m, rho, lens, float(q), int(npts_limb),
-                                          int(bool(limb_darkening)), float(u1), int(npts_ld), int(roots_itmax),
-                                          int(bool(roots_compensated)), ws.data_ptr(), nbytes, st))
-            else:
-                _lib.check(L.caustics_mag_extended_source(wp, mp, m, rho, lens, int(npts_limb),
-                                                          int(bool(limb_darkening)), float(u1), int(npts_ld),
-                                                          int(roots_itmax), int(bool(roots_compensated)),
-                                                          ws.data_ptr(), nbytes, st))
+        if gate and nlenses == 2 and n < 2**31 and not torch.cuda.is_current_stream_capturing():
+            # Two-call form: the gate alone, then the workspace is sized by the points that FAILED it
+            # (a few per cent of a light curve; one 4-byte read-back) instead of by n.
+            lst = torch.empty(n, dtype=torch.int32, device=flat.device)
+            cnt = torch.empty(1, dtype=torch.int32, device=flat.device)
+            _lib.check(L.caustics_mag_gate(flat.data_ptr(), mag.data_ptr(), test.data_ptr(), lst.data_ptr(),
+                                           cnt.data_ptr(), n, rho, lens, float(q), cfg[4], comp, st))
+            nfull = int(cnt.item())
+            if nfull:
+                chunk = _chunk_len(L, nfull, nlenses, npts_limb, limb_darkening, npts_ld)
+                nbytes = L.caustics_mag_workspace_bytes(nfull, chunk, nlenses, cfg[0], ld, cfg[3])
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
+                _lib.check(L.caustics_mag_extended_source_list(flat.data_ptr(), mag.data_ptr(), lst.data_ptr(),
+                                                               cnt.data_ptr(), nfull, rho, lens, *cfg,
+                                                               ws.data_ptr(), nbytes, st))
+        elif gate:
+            # one stream-ordered call (CUDA-graph capturable; triple lens: every point is integrated):
+            # the survivor count stays on the device, the workspace holds `chunk` sources at a time
+            chunk = _chunk_len(L, n, nlenses, npts_limb, limb_darkening, npts_ld)
+            nbytes = L.caustics_mag_workspace_bytes(n, chunk, nlenses, cfg[0], ld, cfg[3])
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
+            _lib.check(L.caustics_mag(flat.data_ptr(), mag.data_ptr(), test.data_ptr(), n, rho, lens, float(q),
+                                      *cfg, ws.data_ptr(), nbytes, st))
+        else:
+            chunk = _chunk_len(L, n, nlenses, npts_limb, limb_darkening, npts_ld)
+            nbytes = L.caustics_ext_workspace_bytes(chunk, nlenses, cfg[0], ld, cfg[3])
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
+            for off in range(0, n, chunk):
+                m = min(chunk, n - off)
+                _lib.check(L.caustics_mag_extended_source(flat.data_ptr() + 16 * off, mag.data_ptr() + 8 * off, m,
+                                                          rho, lens, *cfg, ws.data_ptr(), nbytes, st))
     if return_test:
         return restore(mag), restore(test.bool())
     return restore(mag)

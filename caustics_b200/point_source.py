@@ -270,14 +270,18 @@ GRID_WALK = 4   # CAUSTICS_FLAG_GRID_WALK (include/caustics_b200.h)
 
 
 def mag_point_source_map(x0, y0, dx, dy, nx, ny, nlenses=2, rows=None, walk=True, roots_itmax=2500,
-                         roots_compensated=False, device=None, **params):
+                         roots_compensated=False, device=None, out=None, **params):
     """Point-source magnification map (BASELINE config C5): `mag_point_source` on the regular grid
     w[iy, ix] = (x0 + ix dx) + i (y0 + iy dy) without materialising w (the reference's user would build
     the grid with jnp.meshgrid and call mag_point_source, point_source.py:1762-1830).  `rows = (begin,
     end)` computes a row block (how a multi-GPU driver shards the map).  `walk=True` solves each column
     segment as a warm-started walk (csrc/ps_walk.cuh: ~3x fewer root updates; agrees with the cold
     solves to rounding x conditioning), `walk=False` solves every pixel from cold, bit-identical to
-    `mag_point_source` on the explicit grid.  Returns a (rows, nx) float64 CUDA tensor."""
+    `mag_point_source` on the explicit grid.  Returns a (rows, nx) float64 CUDA tensor.
+    `out`: a C-contiguous float64 HOST array of shape (rows, nx) (NumPy, e.g. a slice of a shared-memory map
+    several ranks fill) -- the row block is then computed in chunks whose device-to-host copies overlap the
+    kernels (caustics_mag_point_source_grid_host) and `out` is returned; or an int, the DEVICE address the
+    block is written to (e.g. `PeerGather.ptr(...)`: another GPU's buffer), in which case nothing is returned."""
     if nlenses not in (2, 3):
         raise ValueError("mag_point_source_map supports nlenses = 2 or 3")
     _lib.require_cuda()
@@ -287,6 +291,21 @@ def mag_point_source_map(x0, y0, dx, dy, nx, ny, nlenses=2, rows=None, walk=True
     p, x_cm = lens_params(nlenses, **params)
     lens = _c_lens(nlenses, x_cm, **p)
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    fl = GRID_WALK if walk else 0
+    if isinstance(out, np.ndarray):
+        if out.dtype != np.float64 or out.shape != (r1 - r0, int(nx)) or not out.flags.c_contiguous:
+            raise ValueError("`out` has to be a C-contiguous float64 array of shape (rows, nx)")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().caustics_mag_point_source_grid_host(
+                float(x0), float(y0), float(dx), float(dy), int(nx), r0, r1, out.ctypes.data, lens, int(roots_itmax),
+                int(bool(roots_compensated)), fl))
+        return out
+    if isinstance(out, int):
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().caustics_mag_point_source_grid(
+                float(x0), float(y0), float(dx), float(dy), int(nx), r0, r1, out, lens, int(roots_itmax),
+                int(bool(roots_compensated)), fl, torch.cuda.current_stream().cuda_stream))
+        return None
     mag = torch.empty((r1 - r0, int(nx)), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().caustics_mag_point_source_grid(

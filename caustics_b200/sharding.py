@@ -7,7 +7,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "sharded_apply", "balanced_order", "row_block", "sharded_rows"]
+__all__ = ["shard_bounds", "sharded_apply", "balanced_order", "row_block", "sharded_rows", "PeerGather",
+           "HostGather"]
 
 
 def shard_bounds(n, world, rank):
@@ -90,3 +91,132 @@ def sharded_rows(fn, nrows, group=None, gather=True, align=1):
     out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return out[:nrows]
+
+
+class _RawCuda:
+    """a raw device pointer as a __cuda_array_interface__ object (-> torch.as_tensor without a copy)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerGather:
+    """The final result gather WITHOUT a collective (include/caustics_b200.h, caustics_peer_*).
+
+    Rank `dst` owns one device buffer of `nbytes`; every other rank maps it over NVLink (CUDA IPC) and
+    passes `ptr(offset)` as the result pointer of a launcher, so the kernels' own stores land in the
+    destination while they compute -- there is no gather phase to wait for, only `finish()`: stream
+    synchronise + barrier, after which `tensor(dtype, shape)` on the destination holds everyone's slice.
+    Setup (allocation, handle exchange, mapping) happens once, outside any timed region; the buffer is
+    reused across calls.  Without an initialised process group it degrades to a plain local buffer."""
+
+    def __init__(self, nbytes, dst=0, group=None):
+        import ctypes
+        from . import _lib
+        self._L, self._lib = _lib.lib(), _lib
+        self.nbytes, self.dst, self.group = int(nbytes), dst, group
+        self.dist = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.dist else 0
+        self.world = dist.get_world_size(group) if self.dist else 1
+        self.owner = self.rank == dst or not self.dist
+        self._base = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        if self.owner:
+            _lib.check(self._L.caustics_peer_alloc(ctypes.byref(self._base), self.nbytes))
+            if self.dist:
+                _lib.check(self._L.caustics_peer_export(self._base, handle))
+        if self.dist:
+            box = [bytes(handle) if self.owner else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst,
+                                       group=group)
+            if not self.owner:
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(box[0])
+                _lib.check(self._L.caustics_peer_open(buf, ctypes.byref(self._base)))
+        self._open = True
+
+    def ptr(self, offset_bytes=0):
+        """device address of byte `offset_bytes` of the destination buffer, valid on THIS rank"""
+        if not (0 <= offset_bytes <= self.nbytes):
+            raise ValueError("offset outside the peer buffer")
+        return self._base.value + int(offset_bytes)
+
+    def tensor(self, dtype=torch.float64, shape=None):
+        """the destination buffer as a torch tensor (no copy); meaningful on the owner after finish()"""
+        t = torch.as_tensor(_RawCuda(self._base.value, self.nbytes), device="cuda").view(dtype)
+        return t if shape is None else t[: int(np.prod(shape))].reshape(shape)
+
+    def finish(self):
+        """every rank's stores are complete and visible on the destination when this returns"""
+        torch.cuda.current_stream().synchronize()
+        if self.dist:
+            dist.barrier(group=self.group)
+
+    def close(self):
+        if not self._open:
+            return
+        self._open = False
+        if self.dist:
+            dist.barrier(group=self.group)          # nobody is still writing
+        if self.owner:
+            self._L.caustics_peer_free(self._base)
+        else:
+            self._L.caustics_peer_close(self._base)
+
+    def __del__(self):
+        try:
+            if self._open and not self.dist:
+                self._L.caustics_peer_free(self._base)
+        except Exception:
+            pass
+
+
+class HostGather:
+    """The same for HOST results (the end-to-end path of a one-process-per-GPU driver): rank `dst` creates
+    one POSIX shared-memory segment, every rank maps and page-locks it (cudaHostRegister), and the *_host
+    entry points write their slices into it with their own D2H copies -- eight PCIe links in parallel
+    instead of a device-side gather followed by one 800 MB copy over a single link."""
+
+    def __init__(self, nbytes, dst=0, group=None):
+        from multiprocessing import shared_memory
+        self.nbytes, self.dst, self.group = int(nbytes), dst, group
+        self.dist = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.dist else 0
+        self.owner = self.rank == dst or not self.dist
+        box = [None]
+        if self.owner:
+            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+            box[0] = self.shm.name
+        if self.dist:
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst,
+                                       group=group)
+            if not self.owner:
+                self.shm = shared_memory.SharedMemory(name=box[0])
+        self.array = np.ndarray((self.nbytes,), dtype=np.uint8, buffer=self.shm.buf)
+        self.array[self.rank::4096] = 0            # fault the pages in before pinning
+        self._registered = False
+        if torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, self.nbytes, 0)
+            self._registered = int(rc) == 0
+        if self.dist:
+            dist.barrier(group=group)
+
+    def view(self, dtype=np.float64, shape=None):
+        a = self.array.view(dtype)
+        return a if shape is None else a[: int(np.prod(shape))].reshape(shape)
+
+    def finish(self):
+        if self.dist:
+            dist.barrier(group=self.group)
+
+    def close(self):
+        if getattr(self, "shm", None) is None:
+            return
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+        if self.dist:
+            dist.barrier(group=self.group)
+        self.array = None
+        shm, self.shm = self.shm, None
+        shm.close()
+        if self.owner:
+            shm.unlink()

@@ -139,6 +139,8 @@ void caustics_release_workspace(void);
  * buffers = [coeffs, roots_init, roots]; opaque = caustics_ea_descriptor bytes.  On a bad descriptor
  * nothing is launched and the sticky error is readable with caustics_last_xla_error(). */
 void caustics_ea_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+/* returns the first error recorded since the last call and clears it (process-wide, atomic: XLA runs
+ * custom calls on its own thread) */
 int caustics_last_xla_error(void);
 /* buffers = [w (n) complex128, mag (n) float64]; opaque = caustics_mag_ps_descriptor bytes */
 void caustics_mag_ps_xla(void* stream, void** buffers, const char* opaque, size_t opaque_len);
@@ -188,6 +190,14 @@ int caustics_mag_point_source_grid(double x0, double y0, double dx, double dy, i
                                    int flags, void* stream);
 int caustics_mag_point_source_host(const void* w, double* mag, int64_t n, const caustics_lens* lens,
                                    int itmax, int compensated, int flags);
+/* the map entry with a HOST result buffer (rows [row_begin, row_end) -> mag[(iy-row_begin)*nx + ix]):
+ * row blocks (multiples of 32 rows, so walked maps are cut on walk boundaries) flow through the
+ * internal workspace as kernel -> D2H, the copy of block k overlapping the kernel of block k+1.
+ * Synchronous.  `mag` may be pinned, pageable, or a shared-memory segment several ranks write
+ * disjoint row blocks of (how a one-process-per-GPU driver assembles the map on the host). */
+int caustics_mag_point_source_grid_host(double x0, double y0, double dx, double dy, int64_t nx,
+                                        int64_t row_begin, int64_t row_end, double* mag,
+                                        const caustics_lens* lens, int itmax, int compensated, int flags);
 
 /* ---- kernel family 3: extended-source magnification by contour integration ------------------
  * w (n) complex128 source-disk centres, rho the source radius, npts_limb / limb_darkening / u1 /
@@ -198,12 +208,29 @@ int caustics_mag_point_source_host(const void* w, double* mag, int64_t n, const 
  * against 0.01 for the planetary-caustic test) and full integration elsewhere; used_hexadecapole
  * (n) uint8, optional, records the decision.  Limits: npts_limb <= 1280, n * (D*npts_limb) < 2^31. */
 size_t caustics_ext_workspace_bytes(int64_t n, int nlenses, int npts_limb, int limb_darkening, int npts_ld);
+/* workspace of a GATED call (caustics_mag, caustics_mag_extended_source_list) over n points that
+ * integrates at most max_full sources at a time: per-source arrays for max_full sources + the compact
+ * list of n points.  caustics_mag accepts any workspace >= caustics_mag_workspace_bytes(n, 1, ...): the
+ * points that fail the gate are integrated in windows of as many sources as the workspace holds, the
+ * window loop is enqueued without reading the device-side count back (a window past the count exits at
+ * once).  A light curve sends a few per cent of its points to the integration, so a workspace for
+ * n / 8 sources is ample and 8x smaller than caustics_ext_workspace_bytes(n, ...). */
+size_t caustics_mag_workspace_bytes(int64_t n, int64_t max_full, int nlenses, int npts_limb, int limb_darkening,
+                                    int npts_ld);
 int caustics_mag_extended_source(const void* w, double* mag, int64_t n, double rho, const caustics_lens* lens,
                                  int npts_limb, int limb_darkening, double u1, int npts_ld, int itmax,
                                  int compensated, void* workspace, size_t workspace_bytes, void* stream);
 int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t n, double rho,
                  const caustics_lens* lens, double q, int npts_limb, int limb_darkening, double u1, int npts_ld,
                  int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Second half of the two-call form  caustics_mag_gate -> (host reads *count, sizes the workspace) ->
+ * here: full contour integration of the points w[list[k]], k < *count (device int32, <= max_count),
+ * results to mag[list[k]].  workspace >= caustics_mag_workspace_bytes(max_count, m, ...) for any m >= 1. */
+int caustics_mag_extended_source_list(const void* w, double* mag, const int32_t* list, const int32_t* count,
+                                      int64_t max_count, double rho, const caustics_lens* lens, int npts_limb,
+                                      int limb_darkening, double u1, int npts_ld, int itmax, int compensated,
+                                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* The gate alone (binary lens, lightcurve.py:202-225): hexadecapole magnification of every point in
  * mag (n), the validity decision in used_hexadecapole (n, optional), and the compacted indices of
@@ -245,6 +272,29 @@ int caustics_ext_contours(const void* w, double* mag, int64_t n, double rho, con
  * z (nsets, npts, deg) complex128 -> out, same shape: every row re-ordered so that entry i continues
  * entry i of the previous row (greedy nearest neighbour without reuse, utils.py:15-40). deg <= 16. */
 int caustics_match_tracks(const void* z, void* out, int64_t nsets, int npts, int deg, void* stream);
+
+/* ---- multi-GPU: the final result gather without a collective ---------------------
+ * Source positions are independent (lightcurve.py:245-254, point_source.py:1762-1830,
+ * cpu_ops.cc:45-72), so the only inter-GPU traffic is the gather of the results.  Instead of a
+ * collective after the kernels, the destination rank exports one buffer and every other rank passes
+ * `opened base + its slice offset` as the result pointer of the launchers above: the kernels' own
+ * stores travel over NVLink while they compute.  alloc/export on the destination, open/close on the
+ * writers (one process per GPU, CUDA IPC; handle = CAUSTICS_PEER_HANDLE_BYTES opaque bytes moved by
+ * any host-side means); a single process driving several GPUs calls caustics_peer_enable(owner
+ * device) on each writer device instead and uses the owner's pointer as is.  After the writers have
+ * synchronised their streams and a host-side barrier, the destination reads the assembled result. */
+#define CAUSTICS_PEER_HANDLE_BYTES 64
+int caustics_peer_alloc(void** ptr, size_t bytes);
+int caustics_peer_free(void* ptr);
+int caustics_peer_export(void* ptr, void* handle);
+int caustics_peer_open(const void* handle, void** ptr);
+int caustics_peer_close(void* ptr);
+int caustics_peer_enable(int peer_device);
+
+/* ---- launch-shape overrides for tests and experiments ---------------------------------------
+ * key in {"grid_run", "path_run", "grid_extrap", "ext_variants"}; value -1 restores the launcher's own
+ * rule.  (These replace environment variables: nothing in the library calls getenv.) */
+int caustics_set_tuning(const char* key, int value);
 
 /* ---- measurement aid -----------------------------------------------------------------------
  * Launches blocks x 256 threads, each running 8 independent chains of `iters` double-precision

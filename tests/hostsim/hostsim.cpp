@@ -138,13 +138,8 @@ static void ext_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, int64_
   constexpr int NLS = NL == 1 ? 2 : NL;   // solver instantiation (unused for the single lens)
   static EASmem<NLS * NLS + 1, false, 1> sm0;
   static EASmem<NLS * NLS + 1, true, 1> sm1;
-  if (NL != 1 && cfg.chains > 1) {
-    for (int64_t g = 0; g < (int64_t)cfg.chains * cfg.S; ++g) limb_walk_chain_body<NLS, 1>(cfg, b, L, sm0, 0, g);
-    for (int64_t s = 0; s < ns; ++s) align_chains_body<D>(cfg, b, s);
-  } else {
-    for (int64_t s = 0; s < ns; ++s) {
-      if (NL == 1) limb_walk_single_body(cfg, b, L, s); else limb_walk_body<NLS, 1>(cfg, b, L, sm0, 0, s);
-    }
+  for (int64_t s = 0; s < ns; ++s) {
+    if (NL == 1) limb_walk_single_body(cfg, b, L, s); else limb_walk_body<NLS, 1>(cfg, b, L, sm0, 0, s);
   }
   for (int r = 0; r < NITER; ++r) {
     for (int64_t s = 0; s < ns; ++s) {
@@ -165,8 +160,6 @@ static void ext_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, int64_
   }
 }
 
-static int g_hostsim_chains = 1;
-extern "C" void hostsim_set_chains(int k) { g_hostsim_chains = k; }
 
 extern "C" int hostsim_mag_extended(const double* w, double* mag, uint8_t* test_out, int64_t n, double rho, int nlenses,
                                     const double* eps, const double* r, const double* H, const double* G, double x_cm,
@@ -175,7 +168,6 @@ extern "C" int hostsim_mag_extended(const double* w, double* mag, uint8_t* test_
   ExtCfg cfg;
   int rc = make_cfg(n, rho, nlenses, npts_limb, ld, u1, npts_ld, itmax, comp, &cfg);
   if (rc) return rc;
-  if (g_hostsim_chains > 1 && cfg.N0 >= 32) cfg.chains = g_hostsim_chains;
   Layout lay = make_layout(cfg);
   std::vector<char> ws(lay.total + 256, 0);
   LensConst L;

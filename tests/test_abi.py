@@ -102,3 +102,32 @@ def test_jvp_rule_host():
     assert np.allclose(cb.roots_jvp(c, z, dc), fd, rtol=1e-4, atol=1e-4)
     zt = cb.roots_jvp(torch.from_numpy(c), torch.from_numpy(z), torch.from_numpy(dc))
     assert np.allclose(zt.numpy(), cb.roots_jvp(c, z, dc))
+
+
+def test_round2_entry_points_without_compute(built_lib):
+    """the round-2 additions: tuning overrides (no getenv anywhere in the library), the gated workspace
+    sizes, and the peer-buffer entry points' argument checks / loud failure without a device"""
+    L = built_lib
+    assert L.caustics_set_tuning(b"path_run", 8) == 0 and L.caustics_set_tuning(b"path_run", -1) == 0
+    assert L.caustics_set_tuning(b"no_such_knob", 1) == 1 and L.caustics_set_tuning(None, 1) == 1
+    for f in os.listdir(os.path.join(ROOT, "caustics_b200", "csrc")):
+        assert "getenv" not in open(os.path.join(ROOT, "caustics_b200", "csrc", f)).read().replace("no getenv", ""), f
+    # a gated call's workspace: per-source arrays for max_full sources + a list of n points
+    full = L.caustics_ext_workspace_bytes(1_000_000, 2, 200, 1, 100)
+    small = L.caustics_mag_workspace_bytes(1_000_000, 60_000, 2, 200, 1, 100)
+    one = L.caustics_mag_workspace_bytes(1_000_000, 1, 2, 200, 1, 100)
+    assert one < small < full and small < 4 << 30 and one >= 4_000_000
+    assert L.caustics_mag_workspace_bytes(1000, 5000, 2, 200, 0, 100) == L.caustics_ext_workspace_bytes(1000, 2, 200, 0, 100)
+    assert L.caustics_mag_workspace_bytes(1000, 10, 7, 200, 0, 100) == 0          # bad nlenses
+    # peer buffers
+    p = ctypes.c_void_p()
+    assert L.caustics_peer_alloc(None, 16) == 1 and L.caustics_peer_alloc(ctypes.byref(p), 0) == 1
+    assert L.caustics_peer_export(None, None) == 1 and L.caustics_peer_open(None, None) == 1
+    assert L.caustics_peer_free(None) == 0 and L.caustics_peer_close(None) == 0
+    if not torch.cuda.is_available():
+        assert L.caustics_peer_alloc(ctypes.byref(p), 1024) >= 1000            # 1000 + cudaError: no CPU stand-in
+        lens = __import__("caustics_b200")._lib.Lens(); lens.nlenses = 2; lens.a = 0.45; lens.e1 = 0.8
+        out = np.zeros(64)
+        assert L.caustics_mag_point_source_grid_host(0.0, 0.0, 0.1, 0.1, 8, 0, 8, out.ctypes.data, ctypes.byref(lens),
+                                                     100, 0, 0) >= 1000
+    assert L.caustics_mag_point_source_grid_host(0.0, 0.0, 0.1, 0.1, 0, 0, 8, None, None, 100, 0, 0) == 1

@@ -261,17 +261,21 @@ def test_path_walk(cb):
         assert torch.equal(cb.mag_point_source(short, nlenses=nl, flags=8, **hp), cb.mag_point_source(short, nlenses=nl, **hp))
 
 
-def test_path_walk_small_forced(cb, monkeypatch):
-    """the path-walk kernel on arrays whose length the run does not divide (CAUSTICS_B200_PATH_RUN forces the
-    kernel for a batch that would otherwise take the default one), plus run lengths longer than the array"""
+def test_path_walk_small_forced(cb):
+    """the path-walk kernel on arrays whose length the run does not divide (caustics_set_tuning("path_run")
+    forces the kernel for a batch that would otherwise take the default one), plus run lengths longer than
+    the array"""
+    from caustics_b200 import _lib
+    tune = _lib.lib().caustics_set_tuning
     hp = dict(s=0.9, q=0.2)
     for n, run in ((1003, 8), (130, 32), (5, 16), (1, 4), (4097, 3)):
-        monkeypatch.setenv("CAUSTICS_B200_PATH_RUN", str(run))
         w = torch.from_numpy(np.linspace(-0.5, 0.5, n) + 0.1j).cuda()
         for nl, h in ((2, hp), (3, TRIPLE_HP)):
-            walk = cb.mag_point_source(w, nlenses=nl, flags=8, **h)
-            monkeypatch.delenv("CAUSTICS_B200_PATH_RUN")
+            assert tune(b"path_run", run) == 0
+            try:
+                walk = cb.mag_point_source(w, nlenses=nl, flags=8, **h)
+            finally:
+                tune(b"path_run", -1)
             cold = cb.mag_point_source(w, nlenses=nl, **h)
-            monkeypatch.setenv("CAUSTICS_B200_PATH_RUN", str(run))
             assert walk.shape == cold.shape and torch.allclose(walk, cold, rtol=1e-7, atol=0), (n, run, nl)
             assert ((walk - cold).abs() / cold).median().item() < 1e-13

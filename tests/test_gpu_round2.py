@@ -1,0 +1,181 @@
+"""GPU tier, round-2 additions: the gather without a collective (PeerGather / HostGather, the map entry with a
+host result buffer), gated calls whose workspace is sized by the gate's survivors, and -- on a box with two
+GPUs -- the one-process-per-GPU path itself (NCCL for the rendezvous, kernel stores over NVLink for the data)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+HP2 = dict(s=0.9, q=0.2)
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import caustics_b200
+    return caustics_b200
+
+
+def test_map_into_peer_buffer_and_host_buffer(cb):
+    """the map written straight into a PeerGather buffer (single process: a plain local allocation) and into
+    a host array through caustics_mag_point_source_grid_host equals the ordinary map bit for bit, cold and
+    walked (host chunks are cut on 32-row walk boundaries)"""
+    from caustics_b200.sharding import PeerGather
+    nx, ny = 3000, 1100
+    x0, y0, dx = -1.2, -0.5, 1e-3
+    for walk in (False, True):
+        want = cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, walk=walk, **HP2)
+        pg = PeerGather(nx * ny * 8)
+        # two row blocks, like two ranks would write them (32-row aligned so the walked map is the same walks)
+        for lo, hi in ((0, 544), (544, ny)):
+            assert cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, rows=(lo, hi), walk=walk, out=pg.ptr(lo * nx * 8), **HP2) is None
+        pg.finish()
+        assert torch.equal(pg.tensor(torch.float64, (ny, nx)), want)
+        pg.close()
+        host = np.empty((ny, nx))
+        assert cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, walk=walk, out=host, **HP2) is host
+        assert np.array_equal(host, want.cpu().numpy())
+        part = np.full((100, nx), -1.0)
+        cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, rows=(64, 164), walk=walk, out=part, **HP2)
+        assert np.array_equal(part, want[64:164].cpu().numpy())
+    with pytest.raises(ValueError):
+        cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, out=np.empty((ny, nx), dtype=np.float32), **HP2)
+
+
+def test_gated_workspace_sized_by_survivors(cb):
+    """caustics_mag with a workspace for a fraction of the points integrates the gate's survivors in windows
+    (no host read-back) and gives the same bits as the full-size workspace; the two-call form
+    caustics_mag_gate -> caustics_mag_extended_source_list likewise"""
+    from caustics_b200 import _lib
+    L = _lib.lib()
+    n = 20_000
+    w = torch.from_numpy(np.linspace(-2, 2, n) + 0.1j).cuda()
+    p, x_cm = cb.lens_params(2, **HP2)
+    lens = cb.point_source._c_lens(2, x_cm, **p)
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for ld in (0, 1):
+        for cap in (n, 700, 97):
+            nb = L.caustics_mag_workspace_bytes(n, cap, 2, 200, ld, 100)
+            assert nb > 0
+            ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+            mag = torch.full((n,), -1.0, dtype=torch.float64, device="cuda")
+            used = torch.empty(n, dtype=torch.uint8, device="cuda")
+            L.caustics_set_tuning(b"ext_variants", 31)        # same phase variants whatever the window size
+            try:
+                _lib.check(L.caustics_mag(w.data_ptr(), mag.data_ptr(), used.data_ptr(), n, 1e-2, lens, 0.2, 200, ld, 0.7,
+                                          100, 2500, 0, ws.data_ptr(), nb, st))
+            finally:
+                L.caustics_set_tuning(b"ext_variants", -1)
+            torch.cuda.synchronize()
+            res[(ld, cap)] = (mag, used)
+        nfull = int((res[(ld, n)][1] == 0).sum().item())
+        assert 1000 < nfull < 1400                  # several windows of 700, many of 97
+        for cap in (700, 97):
+            assert torch.equal(res[(ld, cap)][0], res[(ld, n)][0]) and torch.equal(res[(ld, cap)][1], res[(ld, n)][1])
+        # the public call (gate -> count -> exact workspace -> list integration)
+        m, t = cb.mag(w, 1e-2, nlenses=2, npts_limb=200, limb_darkening=bool(ld), u1=0.7, npts_ld=100, return_test=True, **HP2)
+        assert torch.equal(t, res[(ld, n)][1].bool())
+        assert torch.allclose(m, res[(ld, n)][0], rtol=1e-9, atol=0)
+    # too small for one source + the list: a clean argument error, nothing launched
+    ws = torch.empty(1000, dtype=torch.uint8, device="cuda")
+    mag = torch.empty(n, dtype=torch.float64, device="cuda")
+    assert L.caustics_mag(w.data_ptr(), mag.data_ptr(), None, n, 1e-2, lens, 0.2, 200, 0, 0.0, 100, 2500, 0, ws.data_ptr(), 1000, st) == 1
+
+
+def test_million_point_gated_light_curve_fits_4gb(cb):
+    """a 10^6-point gated binary light curve (limb-darkened) needs < 4 GB of device memory: the workspace is
+    sized by the points that fail the gate, not by the length of the light curve"""
+    n = 1_000_000
+    w = torch.from_numpy(np.linspace(-2, 2, n) + 0.1j).cuda()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    m, t = cb.mag(w, 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7, npts_ld=100, return_test=True, **HP2)
+    torch.cuda.synchronize()
+    assert torch.cuda.max_memory_allocated() - base < 4 << 30
+    assert bool(torch.isfinite(m).all()) and 0.03 < float((~t).double().mean()) < 0.09
+    # every 100th point is a point of the 10^4-point light curve C3 (same linspace ends): same values
+    sub = cb.mag(w[::100].contiguous(), 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7, npts_ld=100, **HP2)
+    assert torch.allclose(m[::100], sub, rtol=1e-9, atol=0)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _two_gpu_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import caustics_b200 as cb
+    from caustics_b200 import _lib, sharding
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ok = True
+    # C5-like map: every rank's kernel stores its row block into rank 0's buffer over NVLink
+    nx, ny = 2000, 1024
+    x0, y0, dx = -1.2, -0.5, 1.5e-3
+    pg = sharding.PeerGather(nx * ny * 8, dst=0)
+    lo, hi = sharding.row_block(ny, world, rank, align=32)
+    for walk in (False, True):
+        cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, rows=(lo, hi), walk=walk, out=pg.ptr(lo * nx * 8), **HP2)
+        pg.finish()
+        if rank == 0:
+            want = cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, walk=walk, **HP2)
+            ok = ok and bool(torch.equal(pg.tensor(torch.float64, (ny, nx)), want))
+        dist.barrier()
+    pg.close()
+    # the host-side assembly: both ranks' D2H copies into one shared, page-locked map
+    hg = sharding.HostGather(nx * ny * 8, dst=0)
+    v = hg.view(np.float64, (ny, nx))
+    cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, rows=(lo, hi), walk=False, out=v[lo:hi], **HP2)
+    hg.finish()
+    want = cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, walk=False, **HP2).cpu().numpy()
+    ok = ok and bool(np.array_equal(v, want))
+    del v
+    hg.close()
+    # extended sources sharded, results into rank 0's buffer
+    n = 600
+    w_all = np.linspace(-0.4, 0.4, n) + 0.05j
+    L = _lib.lib()
+    p, x_cm = cb.lens_params(2, **HP2)
+    lens = cb.point_source._c_lens(2, x_cm, **p)
+    slo, shi = sharding.shard_bounds(n, world, rank)
+    w = torch.from_numpy(w_all[slo:shi]).cuda()
+    nb = L.caustics_ext_workspace_bytes(shi - slo, 2, 200, 0, 100)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    pg = sharding.PeerGather(n * 8, dst=0)
+    _lib.check(L.caustics_mag_extended_source(w.data_ptr(), pg.ptr(slo * 8), shi - slo, 1e-2, lens, 200, 0, 0.0, 100, 2500, 0,
+                                              ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream))
+    pg.finish()
+    if rank == 0:
+        want = cb.mag_extended_source(torch.from_numpy(w_all).cuda(), 1e-2, nlenses=2, npts_limb=200, **HP2)
+        ok = ok and bool(torch.allclose(pg.tensor(torch.float64, (n,)), want, rtol=1e-9, atol=0))
+    pg.close()
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one box")
+def test_two_process_gather_over_nvlink():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert res == [(0, True), (1, True)]

@@ -108,22 +108,6 @@ def test_other_geometries_and_radii(hs, hp):
     assert (t_got == t_want).all() and np.allclose(got, want, rtol=1e-7)
 
 
-def test_chain_split_limb_walk(hs, g):
-    """opt-in small-batch variant (CAUSTICS_B200_LIMB_CHAINS): concurrent limb chains joined by
-    nearest-neighbour relabelling stay inside the 1e-4 bar and agree exactly away from caustic crossings"""
-    hs.hostsim_set_chains(4)
-    try:
-        w = g["b_w_0.01"][:20]
-        want = np.array([extended.mag_extended_source(x, 1e-2, 2, 200, **HP2) for x in w])
-        got = hs_ext(hs, w, 1e-2, 2, HP2)
-        assert np.allclose(got, want, rtol=1e-4) and (np.abs(got / want - 1) < 1e-8).mean() >= 0.8
-        wl = g["lc_w"]
-        want = extended.mag(wl, 1e-2, 2, 200, **HP2)
-        assert np.allclose(hs_ext(hs, wl, 1e-2, 2, HP2, gate=True)[0], want, rtol=1e-4)
-    finally:
-        hs.hostsim_set_chains(1)
-
-
 def hs_grid_walk(lib, x0, y0, dx, dy, nx, r0, r1, nl, hp, run=32, extrap=1, comp=False):
     p, xcm = lens.lens_params(nl, **hp)
     eps, r, H, G = lens_const(nl, **p)

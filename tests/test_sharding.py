@@ -108,3 +108,44 @@ def test_row_block_alignment():
                 assert spans[0][0] == 0 and spans[-1][1] == nrows
                 assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
                 assert all(lo % align == 0 or lo == nrows for lo, _ in spans)
+
+
+def _host_gather_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    from caustics_b200.sharding import HostGather, shard_bounds
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 1001
+    hg = HostGather(n * 8, dst=0)
+    v = hg.view(np.float64, (n,))
+    lo, hi = shard_bounds(n, world, rank)
+    v[lo:hi] = np.arange(lo, hi) * 0.5          # what a *_host entry point's D2H copies do
+    hg.finish()
+    ok = bool(np.array_equal(v, np.arange(n) * 0.5))   # every rank sees the assembled result
+    del v
+    hg.close()
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_host_gather_gloo_world2():
+    """HostGather: the ranks' slices land in ONE shared host buffer without a collective (the end-to-end
+    path of a one-process-per-GPU driver); page-locking is skipped where there is no CUDA device"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_host_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert res == [(0, True), (1, True)]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_peer_gather_needs_a_device():
+    from caustics_b200._lib import CausticsError
+    from caustics_b200.sharding import PeerGather
+    with pytest.raises(CausticsError):
+        PeerGather(1 << 20)
