@@ -17,6 +17,7 @@ from .point_source import _c_lens, lens_params
 __all__ = ["mag_extended_source", "mag", "mag_gate"]
 
 _MAX_WS_BYTES = 24 << 30      # per-call workspace budget; larger batches are processed in chunks
+_MAX_GATED_WS_BYTES = 3 << 30  # gated light curves: the survivors are integrated in windows of this much state
 
 
 def _to_device(w):
@@ -35,7 +36,7 @@ def _to_device(w):
     return flat, lambda m: m.cpu().numpy().reshape(shape)
 
 
-def _chunk_len(L, n, nlenses, npts_limb, ld, npts_ld):
+def _chunk_len(L, n, nlenses, npts_limb, ld, npts_ld, budget=None):
     per1 = L.caustics_ext_workspace_bytes(1, nlenses, npts_limb, int(ld), npts_ld)
     if per1 == 0:
         raise ValueError("unsupported extended-source configuration "
@@ -43,7 +44,7 @@ def _chunk_len(L, n, nlenses, npts_limb, ld, npts_ld):
     per = (L.caustics_ext_workspace_bytes(1024, nlenses, npts_limb, int(ld), npts_ld) + 1023) // 1024
     deg = 2 if nlenses == 1 else nlenses**2 + 1
     cap_idx = (2**31 - 1) // (deg * (npts_limb + 4) + 16)
-    return max(1, min(n, _MAX_WS_BYTES // per, cap_idx))
+    return max(1, min(n, (budget or _MAX_WS_BYTES) // per, cap_idx))
 
 
 def _run(w, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax, roots_compensated,
@@ -72,7 +73,7 @@ def _run(w, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax, r
                                            cnt.data_ptr(), n, rho, lens, float(q), cfg[4], comp, st))
             nfull = int(cnt.item())
             if nfull:
-                chunk = _chunk_len(L, nfull, nlenses, npts_limb, limb_darkening, npts_ld)
+                chunk = _chunk_len(L, nfull, nlenses, npts_limb, limb_darkening, npts_ld, _MAX_GATED_WS_BYTES)
                 nbytes = L.caustics_mag_workspace_bytes(nfull, chunk, nlenses, cfg[0], ld, cfg[3])
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
                 _lib.check(L.caustics_mag_extended_source_list(flat.data_ptr(), mag.data_ptr(), lst.data_ptr(),

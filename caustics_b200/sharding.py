@@ -191,6 +191,11 @@ class HostGather:
                                        group=group)
             if not self.owner:
                 self.shm = shared_memory.SharedMemory(name=box[0])
+                try:        # Python < 3.13 registers attached segments for unlinking too: only the owner unlinks
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(self.shm._name, "shared_memory")
+                except Exception:
+                    pass
         self.array = np.ndarray((self.nbytes,), dtype=np.uint8, buffer=self.shm.buf)
         self.array[self.rank::4096] = 0            # fault the pages in before pinning
         self._registered = False

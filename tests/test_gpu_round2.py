@@ -24,9 +24,13 @@ def test_map_into_peer_buffer_and_host_buffer(cb):
     """the map written straight into a PeerGather buffer (single process: a plain local allocation) and into
     a host array through caustics_mag_point_source_grid_host equals the ordinary map bit for bit, cold and
     walked (host chunks are cut on 32-row walk boundaries)"""
+    from caustics_b200 import _lib
     from caustics_b200.sharding import PeerGather
     nx, ny = 3000, 1100
     x0, y0, dx = -1.2, -0.5, 1e-3
+    # maps this small would get shorter walks the smaller the row block: pin the walk length, as a map large
+    # enough to fill the GPU has it (sharding.row_block(align=32) documents the condition)
+    _lib.lib().caustics_set_tuning(b"grid_run", 32)
     for walk in (False, True):
         want = cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, walk=walk, **HP2)
         pg = PeerGather(nx * ny * 8)
@@ -42,6 +46,7 @@ def test_map_into_peer_buffer_and_host_buffer(cb):
         part = np.full((100, nx), -1.0)
         cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, rows=(64, 164), walk=walk, out=part, **HP2)
         assert np.array_equal(part, want[64:164].cpu().numpy())
+    _lib.lib().caustics_set_tuning(b"grid_run", -1)
     with pytest.raises(ValueError):
         cb.mag_point_source_map(x0, y0, dx, dx, nx, ny, out=np.empty((ny, nx), dtype=np.float32), **HP2)
 
@@ -126,6 +131,7 @@ def _two_gpu_worker(rank, world, port, q):
     # C5-like map: every rank's kernel stores its row block into rank 0's buffer over NVLink
     nx, ny = 2000, 1024
     x0, y0, dx = -1.2, -0.5, 1.5e-3
+    _lib.lib().caustics_set_tuning(b"grid_run", 32)       # see test_map_into_peer_buffer_and_host_buffer
     pg = sharding.PeerGather(nx * ny * 8, dst=0)
     lo, hi = sharding.row_block(ny, world, rank, align=32)
     for walk in (False, True):
