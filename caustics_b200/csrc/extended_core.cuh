@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "ea_core.cuh"
+#include "jax_prng.cuh"
 #include "lens_core.cuh"
 #include "multipole.cuh"
 
@@ -32,8 +33,7 @@ constexpr int NADD_MAX = 64;       // new limb points per refinement round (npts
 constexpr int NITER = 10;          // refinement rounds, extended_source.py:71
 constexpr int MAXSEG = 30;         // 3 * (nlenses^2 + 1), extended_source.py:279-280
 constexpr int MAXPARTS = 10;       // per track, extended_source.py:202-203
-constexpr double JIT_RE = 3.1e-7, JIT_IM = -5.3e-7;  // fixed stand-ins for U(+-1e-6) (:83-85)
-constexpr double DUP_JIT = 7.0e-10;                  // stand-in for U(+-1e-9) (:146)
+// warm-start and duplicate jitters: the reference's own values, jax_prng.cuh (limb_jitter, duplicate_jitter)
 
 struct ExtCfg {
   int nl, D, N0, nadd, NP;
@@ -109,6 +109,23 @@ __device__ __forceinline__ void solve_and_store(const ExtCfg& cfg, const ExtBuf&
   lens_poly<NL>(L, w, p);
   ea_normalise<D>(p);
   ea_solve_thread<D, COMP, NT, CB200_EXT_STRAIGHT != 0>(p, sm, tid, active, warm, EA_INIT_REFERENCE, cfg.itmax);
+  if (warm) {
+    // Coinciding warm-start values make an Aberth term 0 * inf = NaN, and a NaN root passes the stopping
+    // test (|h| > eps b is false): the image would silently vanish.  Redo such a solve from the default
+    // initial estimates, as the point-source walks do (ps_walk.cuh).  Warp-uniform branch.
+    double chk = 0.0;
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) chk += fabs(sm.zre[j][tid]) + fabs(sm.zim[j][tid]);
+    }
+    const bool bad = active && !(chk < 1e300);
+#ifndef CB200_HOSTSIM
+    if (__any_sync(0xffffffffu, bad))
+#else
+    if (bad)
+#endif
+      ea_solve_thread<D, COMP, NT, CB200_EXT_STRAIGHT != 0>(p, sm, tid, bad, false, EA_INIT_REFERENCE, cfg.itmax);
+  }
   if (!active) return;
 #pragma unroll
   for (int j = 0; j < D; ++j) {
@@ -421,8 +438,9 @@ __device__ void refine_solve_body(const ExtCfg& cfg, const ExtBuf& b, const Lens
     const int lf = b.left[I2(r, s)];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-      sm.zre[j][tid] = b.zre[I3(lf, j, s)] + JIT_RE;
-      sm.zim[j][tid] = b.zim[I3(lf, j, s)] + JIT_IM;
+      const cd jit = limb_jitter(j, r, D, cfg.nadd);      // extended_source.py:83-85
+      sm.zre[j][tid] = b.zre[I3(lf, j, s)] + jit.re;
+      sm.zim[j][tid] = b.zim[I3(lf, j, s)] + jit.im;
     }
   }
   solve_and_store<NL, COMP, NT>(cfg, b, L, sm, tid, active, w, true, slot, s);
@@ -445,7 +463,8 @@ __device__ void refine_solve_group_body(const ExtCfg& cfg, const ExtBuf& b, cons
   if (valid) {
     w = limb_point(source_centre(cfg, b, L, s), cfg.rho, b.theta[I2(slot, s)]);
     const int lf = b.left[I2(r, s)];
-    z = mk(b.zre[I3(lf, j, s)] + JIT_RE, b.zim[I3(lf, j, s)] + JIT_IM);
+    const cd jit = limb_jitter(j, r, D, cfg.nadd);
+    z = mk(b.zre[I3(lf, j, s)] + jit.re, b.zim[I3(lf, j, s)] + jit.im);
   }
   cd p[D + 1];
   lens_poly<NL>(L, w, p);
@@ -507,7 +526,7 @@ __device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
         if (k < j && zr[k] == zr[j] && zi[k] == zi[j]) dup = true;
         if (p > 0 && cre[k] == zr[j] && cim[k] == zi[j]) dup = true;
       }
-      if (dup) zr[j] += DUP_JIT;
+      if (dup) zr[j] += duplicate_jitter(j, p, D, cfg.NP);   // extended_source.py:144-148
     }
     unsigned used = 0;
     double nre[D], nim[D];

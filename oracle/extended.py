@@ -28,9 +28,7 @@ import numpy as np
 from . import lens as _lens
 from . import solver as _solver
 
-JIT_RE = 3.1e-7   # stands in for U(-1e-6, 1e-6), extended_source.py:83-85
-JIT_IM = -5.3e-7
-DUP_JIT = 7.0e-10  # stands in for U(-1e-9, 1e-9), extended_source.py:146
+from . import jaxprng as _prng   # the reference's own jitter stream (fixed jax.random keys), :76-85,146
 
 
 def _solve_images(w, nlenses, p, z_init=None, compensated=False, itmax=2500):
@@ -81,7 +79,7 @@ def images_of_source_limb(w0, rho, nlenses=2, npts=300, niter=10, roots_itmax=25
         if nlenses == 1:
             z_new, m_new = _lens.images_point_source(w_new, 1)
         else:
-            z_new, m_new = _solve_images(w_new, nlenses, p, z_init=z[:, idc] + (JIT_RE + 1j * JIT_IM),
+            z_new, m_new = _solve_images(w_new, nlenses, p, z_init=z[:, idc] + _prng.limb_jitters(z.shape[0], n),
                                          compensated=roots_compensated, itmax=roots_itmax)
         p_new = np.sign(_lens.lens_eq_det_jac(z_new, nlenses, **p))
         theta = np.insert(theta, idc + 1, th_new)
@@ -95,7 +93,7 @@ def images_of_source_limb(w0, rho, nlenses=2, npts=300, niter=10, roots_itmax=25
     dup = np.ones(flat.shape, bool)
     dup[first] = False
     if dup.any():
-        z = np.where(dup.reshape(z.shape), z + DUP_JIT, z)
+        z = np.where(dup.reshape(z.shape), z + _prng.duplicate_jitters(*z.shape), z)
 
     # order every column so that row i continues row i of the previous column (:34-53)
     carry = z[:, 0].copy()

@@ -14,9 +14,10 @@ Differences from real jax that can matter, all replicated or documented:
   * out-of-range integer indexing is clamped like XLA gather (utils.py:93-94 reads x[tail+1]);
   * ``lax.dynamic_slice`` clamps its start index;
   * argsort is stable (XLA's sort is);
-  * ``jax.random.uniform`` is NOT threefry: the reference only uses it for 1e-6 / 1e-9 jitters
-    of initial guesses and duplicate roots (extended_source.py:76-85,146), which do not change
-    converged results beyond the solver tolerance.
+  * ``jax.random`` IS JAX's default threefry2x32 generator (oracle/jaxprng.py, float64 as under
+    jax_enable_x64): the reference's jitters of warm starts and duplicate roots come from fixed keys
+    (extended_source.py:76-85,146) and decide which limb intervals get refined at caustic crossings, so
+    they are reproduced exactly rather than stood in for.
 
 This module only works where /root/reference is mounted; it exists to generate tests/golden/*
 (see tests/golden/make_golden.py) and to pin oracle/lens.py and oracle/extended.py.
@@ -28,6 +29,8 @@ import types
 
 import numpy as np
 import scipy.special
+
+from . import jaxprng as _prng
 
 REF_SRC = "/root/reference/src"
 
@@ -252,21 +255,18 @@ def _jit(f=None, **kw):
     return f
 
 
-class _Key(int):
-    pass
-
-
+# jax.random: JAX's default threefry2x32 generator restated in oracle/jaxprng.py (pinned to the Random123 and
+# JAX known answers), so the reference draws exactly the jitters it draws under real JAX with x64 enabled
 def _prng_key(seed):
-    return _Key(int(seed) * 7919 + 13)
+    return _prng.prng_key(seed)
 
 
 def _split(key, num=2):
-    return tuple(_Key(int(key) * 104729 + 31 * (i + 1)) for i in range(num))
+    return tuple(_prng.split(np.asarray(key, dtype=np.uint32), num))
 
 
 def _uniform(key, shape=(), dtype=np.float64, minval=0.0, maxval=1.0):
-    rng = np.random.default_rng(int(key) % (2**63))
-    return _wrap(rng.uniform(minval, maxval, size=shape))
+    return _wrap(_prng.uniform(np.asarray(key, dtype=np.uint32), tuple(shape), np.float64, minval, maxval))
 
 
 def install():

@@ -216,3 +216,15 @@ extern "C" void hostsim_counters(long long* out, int reset) {
   if (reset) { cb200::g_ea_evals = 0; cb200::g_ea_updates = 0; }
 }
 #endif
+
+// the device code's jitter stream (csrc/jax_prng.cuh): limb (deg, n) complex, dup (deg, npts) real
+extern "C" void hostsim_jitters(int deg, int n, int npts, double* limb, double* dup) {
+  for (int j = 0; j < deg; ++j) {
+    for (int r = 0; r < n; ++r) {
+      const cd v = limb_jitter(j, r, deg, n);
+      limb[2 * (j * n + r)] = v.re;
+      limb[2 * (j * n + r) + 1] = v.im;
+    }
+    for (int p = 0; p < npts; ++p) dup[j * npts + p] = duplicate_jitter(j, p, deg, npts);
+  }
+}

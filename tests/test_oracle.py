@@ -132,3 +132,28 @@ def test_sequential_images_match_reference(seq_golden, k):
     assert np.abs(z - seq_golden[f"{k}_z"]).max() < 1e-9
     if k == "b":
         assert np.abs(z - seq_golden[f"{k}_z"])[seq_golden[f"{k}_mask"]].max() < 1e-12
+
+
+def test_jax_prng_known_answers():
+    """oracle/jaxprng.py (the reference's jitter stream, extended_source.py:76-85,146) against the published
+    known answers: the Random123 test vectors of threefry2x32 (Salmon et al., SC'11 -- also JAX's own
+    tests/random_test.py::testThreefry2x32), JAX's documented `random.split(PRNGKey(0))` and
+    `random.uniform(PRNGKey(0))`"""
+    from oracle import jaxprng as J
+    u = lambda *v: np.array(v, dtype=np.uint32)
+    for key, ctr, want in (((0, 0), (0, 0), (0x6b200159, 0x99ba4efe)),
+                           ((0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff), (0x1cb996fc, 0xbb002be7)),
+                           ((0x13198a2e, 0x03707344), (0x243f6a88, 0x85a308d3), (0xc4923a9c, 0x483df7a0))):
+        y0, y1 = J.threefry2x32(key[0], key[1], u(ctr[0]), u(ctr[1]))
+        assert (int(y0[0]), int(y1[0])) == want
+    assert J.prng_key(0).tolist() == [0, 0] and J.prng_key(2**32 + 5).tolist() == [1, 5]
+    assert J.split(J.prng_key(0)).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    assert abs(float(J.uniform(J.prng_key(0), (), np.float32)) - 0.41845703) < 1e-8
+    # float64 draws: in range, reproducible, a different stream per key, C-order element i is a pure function
+    # of (key, i, N)
+    t = J.limb_jitters(5, 10)
+    assert t.shape == (5, 10) and (np.abs(t.real) <= 1e-6).all() and (np.abs(t.imag) <= 1e-6).all()
+    assert np.array_equal(t, J.limb_jitters(5, 10)) and not np.array_equal(t.real, t.imag)
+    assert len(np.unique(t)) == 50 and 2e-7 < np.abs(t.real).mean() < 8e-7
+    d = J.duplicate_jitters(10, 200)
+    assert d.shape == (10, 200) and (np.abs(d) <= 1e-9).all() and abs(d.mean()) < 1e-10
