@@ -427,6 +427,22 @@ def bench_c4(cx, steps):
 
     ms_local = cx.time_device(lambda: launch(local.data_ptr()), steps, warmup=2)
     ms_gather = cx.time_device(lambda: launch(peer.ptr(lo * 8)), steps, warmup=2)
+    # forward value AND tangent w.r.t. (a, e1, e2, r3, w, rho) in one pass (C4 = "jax.grad through ...")
+    grad = torch.empty((8, m), dtype=torch.float64, device="cuda")
+    ms_grad = cx.time_device(lambda: _lib.check(L.caustics_mag_extended_source_grad(
+        w.data_ptr(), local.data_ptr(), grad.data_ptr(), m, 1e-2, lens3, 200, 2500, 0, ws.data_ptr(), nbytes, cx.stream)),
+        steps, warmup=2)
+    grad_finite = bool(torch.isfinite(grad).all().item())
+    del grad
+    # weak scaling beside the strong-scaled figure: every rank its own 10^5 sources
+    ms_weak = None
+    if cx.world > 1:
+        nbw = L.caustics_ext_workspace_bytes(n, 3, 200, 0, 100)
+        wsw = torch.empty(nbw, dtype=torch.uint8, device="cuda")
+        ww = torch.from_numpy(w_all).cuda()
+        mw = torch.empty(n, dtype=torch.float64, device="cuda")
+        ms_weak = cx.time_device(lambda: launch(mw.data_ptr(), ww, n, wsw, nbw), max(3, steps // 2), warmup=2)
+        del wsw, ww, mw
     launch(peer.ptr(lo * 8))
     peer.finish()
     same, dev = None, None
@@ -466,6 +482,12 @@ def bench_c4(cx, steps):
             "n_gpus": cx.world, "value": n / (ms_gather * 1e-3), "ms_per_step": ms_gather,
             "value_no_gather": n / (ms_local * 1e-3), "ms_no_gather": ms_local, "gather_ms": ms_gather - ms_local,
             "matches_single_gpu": same, "max_rel_dev_vs_single_gpu": dev,
+            "gradient": {"value": n / (ms_grad * 1e-3), "unit": "evals/s", "ms_per_step": ms_grad, "finite": grad_finite,
+                         "what": "caustics_mag_extended_source_grad: magnification + d mag/d(a, e1, e2, Re r3, Im r3, "
+                                 "Re w, Im w, rho) per source in one pass (tangent accumulated while the contours are "
+                                 "walked), device resident, no gather"},
+            "weak_scaling": None if ms_weak is None else {"value": cx.world * n / (ms_weak * 1e-3), "ms_per_step": ms_weak,
+                                                          "what": "every rank its own 10^5 sources, no gather"},
             "matches_note": "shards below 16 384 sources take the small-batch phase variants (other summation order "
                             "inside an Aberth sum): bitwise only when the shard stays on the same variants",
             "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "evals/s", "ms_per_step": e2e_ms,

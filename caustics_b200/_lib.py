@@ -79,6 +79,7 @@ SIGNATURES = {
     "caustics_mag_workspace_bytes": (ctypes.c_size_t, [_i64, _i64, _i, _i, _i, _i]),
     "caustics_mag_extended_source_list": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _LP, _i, _i, _d, _i, _i, _i, _vp,
                                                ctypes.c_size_t, _vp]),
+    "caustics_mag_extended_source_grad": (_i, [_vp, _vp, _vp, _i64, _d, _LP, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
     "caustics_bench_fp64_peak": (_i, [_vp, _i, _i, _vp]),
     "caustics_bench_fp64_peak3": (_i, [_vp, _i, _i, _vp]),
     "caustics_mag_gate": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _d, _LP, _d, _i, _i, _vp]),

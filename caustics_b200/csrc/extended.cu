@@ -36,20 +36,20 @@ using namespace cb200;
 namespace {
 
 constexpr int NT = 128;
-constexpr int64_t SMALL_BATCH = 16384;
 // Phase-variant mask: 1 warp-per-source selection, 2 stitching on a shared-memory copy of the tracks,
 // 4 warp-per-source limb-darkened sum, 8 lane-per-root limb walk, 16 lane-per-root refinement solves.
-// The batch-size rules below were measured on one B200 (npts_limb = 200): the lane-per-root walk wins
-// up to ~8192 (binary) / ~4096 (triple) sources, the lane-per-root refinement up to ~2048 / ~128.
-// `scale` = 16 for gated binary light curves, where only a few per cent of the points are integrated.
+// The batch-size rules below were measured on one B200 (npts_limb = 200): warp-per-source selection wins
+// up to ~32 Ki sources, staged stitching and the lane-per-root walk up to ~16 Ki (binary) / ~8 Ki (triple),
+// the lane-per-root refinement up to ~2048 / ~128.
 // `n` is the number of sources that are integrated (a gated call passes its estimate).
 // caustics_set_tuning("ext_variants", mask) overrides the rules (tests, experiments).
 inline int small_mask(int64_t n, int nlenses) {
   const int k = tuning_get(TUNE_EXT_VARIANTS);
   if (k >= 0) return k & 31;
+  // measured on one B200 at npts_limb = 200 (profiles/r02_variant_sweep.jsonl, batches of 3 000 ... 100 000)
   int m = 0;
-  if (n <= SMALL_BATCH) m |= 7;
-  if (n <= (nlenses == 2 ? 8192 : 4096)) m |= 8;
+  if (n <= 32768) m |= 1;
+  if (n <= (nlenses == 2 ? 16384 : 8192)) m |= 6 | 8;
   if (n <= (nlenses == 2 ? 2048 : 128)) m |= 16;
   return m;
 }
@@ -97,13 +97,13 @@ template <int D>
 __global__ void __launch_bounds__(NT) k_tracks(ExtCfg cfg, ExtBuf b) {
   tracks_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
-template <int D>
+template <int D, bool GRAD>
 __global__ void __launch_bounds__(NT) k_contours(ExtCfg cfg, ExtBuf b, LensConst L) {
-  contours_body<D>(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
+  contours_body<D, GRAD>(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
 // small batches: one warp per source; the lanes copy the source's tracks into shared memory, lane 0
 // runs the (scalar) stitching logic on the copy
-template <int D>
+template <int D, bool GRAD>
 __global__ void __launch_bounds__(32) k_contours_staged(ExtCfg cfg, ExtBuf b, LensConst L) {
   extern __shared__ double stage_mem[];
   const int64_t s = blockIdx.x;
@@ -117,13 +117,13 @@ __global__ void __launch_bounds__(32) k_contours_staged(ExtCfg cfg, ExtBuf b, Le
     const int64_t g = (int64_t)k * cfg.S + s;    // k = p * D + track, same order as the global planes
     re[k] = b.sre[g]; im[k] = b.sim[g]; f[k] = b.sflg[g];
   }
-  if (b.vth)
+  if (b.vth || b.grad)
     for (int pth = threadIdx.x; pth < cfg.NP; pth += 32)
       th[pth] = b.theta[(int64_t)b.order[(int64_t)pth * cfg.S + s] * cfg.S + s];
   __syncwarp();
   if (threadIdx.x == 0) {
     const TrackStage st{re, im, f, th};
-    contours_body<D>(cfg, b, L, s, &st);
+    contours_body<D, GRAD>(cfg, b, L, s, &st);
   }
 }
 template <int NL>
@@ -181,6 +181,10 @@ __global__ void k_store_table(TabChunk c, double* dst, int m) {
   if ((int)threadIdx.x < m) dst[threadIdx.x] = c.v[threadIdx.x];
 }
 
+__global__ void k_jitter_table(int D, int nadd, double* out) {
+  jitter_table_body(D, nadd, out, (int)(blockIdx.x * blockDim.x + threadIdx.x));
+}
+
 // fills list = 0..n-1 and count = n (nlenses != 2: full integration everywhere, lightcurve.py:226-227)
 __global__ void k_iota(int32_t* list, int32_t* count, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,6 +197,8 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
   constexpr int D = NL == 1 ? 2 : NL * NL + 1;
   const unsigned gs = (unsigned)((cfg.S + NT - 1) / NT);
   const unsigned gr = (unsigned)(((int64_t)cfg.nadd * cfg.S + NT - 1) / NT);
+  if (NL != 1 && b.list_off == 0)      // the same table serves every window of a gated call
+    k_jitter_table<<<(D * cfg.nadd + 127) / 128, 128, 0, st>>>(D, cfg.nadd, const_cast<double*>(b.jit));
   if (NL == 1) k_limb_walk_single<<<gs, NT, 0, st>>>(cfg, b, L);
   else if (cfg.small & 8) {
     constexpr int G = 32 / (NL == 1 ? 5 : NL * NL + 1);   // sources per warp
@@ -214,11 +220,15 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
   k_tracks<D><<<gs, NT, 0, st>>>(cfg, b);
   const size_t stage_bytes = (size_t)cfg.NP * D * 17 + (size_t)cfg.NP * 8 + 64;
   if ((cfg.small & 2) && stage_bytes <= 200 * 1024) {
-    if (stage_bytes > 48 * 1024)
-      cudaFuncSetAttribute(k_contours_staged<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
-    k_contours_staged<D><<<(unsigned)cfg.S, 32, stage_bytes, st>>>(cfg, b, L);
+    if (stage_bytes > 48 * 1024) {
+      cudaFuncSetAttribute(k_contours_staged<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+      cudaFuncSetAttribute(k_contours_staged<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+    }
+    if (b.grad) k_contours_staged<D, true><<<(unsigned)cfg.S, 32, stage_bytes, st>>>(cfg, b, L);
+    else k_contours_staged<D, false><<<(unsigned)cfg.S, 32, stage_bytes, st>>>(cfg, b, L);
   } else {
-    k_contours<D><<<gs, NT, 0, st>>>(cfg, b, L);
+    if (b.grad) k_contours<D, true><<<gs, NT, 0, st>>>(cfg, b, L);
+    else k_contours<D, false><<<gs, NT, 0, st>>>(cfg, b, L);
   }
   if (cfg.ld) {
     const int64_t gv_all = ((int64_t)cfg.VMAX * cfg.S + NT - 1) / NT;
@@ -275,7 +285,7 @@ int64_t capacity_for(const ExtCfg& proto, int64_t n, size_t bytes) {
 // Gated calls integrate at most `cap` sources at a time, cap = what the workspace holds; with cap < n the
 // integration phases are enqueued ceil(n / cap) times over consecutive windows of the list and a window
 // past the device-side count exits at once (the count never visits the host).
-int ext_driver(const void* w, double* mag, uint8_t* test_out, int64_t n, double rho, const caustics_lens* lens,
+int ext_driver(const void* w, double* mag, double* grad, uint8_t* test_out, int64_t n, double rho, const caustics_lens* lens,
                double q_for_gate, int gate, const int32_t* ext_list, const int32_t* ext_count, int npts_limb,
                int limb_darkening, double u1, int npts_ld, int itmax, int compensated, void* workspace,
                size_t workspace_bytes, void* stream) {
@@ -310,6 +320,8 @@ int ext_driver(const void* w, double* mag, uint8_t* test_out, int64_t n, double 
   ExtBuf b = bind(cfg, lay, workspace);
   b.w = (const double2*)w;
   b.mag = mag;
+  b.grad = cfg.ld ? nullptr : grad;
+  cfg.ngrad_stride = n;
   char* base = (char*)workspace;
   int32_t* list = (int32_t*)(base + lay.list);
   int32_t* count = (int32_t*)(base + lay.count);
@@ -363,8 +375,17 @@ int caustics_mag_extended_source(const void* w, double* mag, int64_t n, double r
                                  int npts_limb, int limb_darkening, double u1, int npts_ld, int itmax,
                                  int compensated, void* workspace, size_t workspace_bytes, void* stream) {
   CB200_NVTX("caustics_mag_extended_source");
-  return ext_driver(w, mag, nullptr, n, rho, lens, 0.0, 0, nullptr, nullptr, npts_limb, limb_darkening, u1, npts_ld,
+  return ext_driver(w, mag, nullptr, nullptr, n, rho, lens, 0.0, 0, nullptr, nullptr, npts_limb, limb_darkening, u1, npts_ld,
                     itmax, compensated, workspace, workspace_bytes, stream);
+}
+
+int caustics_mag_extended_source_grad(const void* w, double* mag, double* grad, int64_t n, double rho,
+                                      const caustics_lens* lens, int npts_limb, int itmax, int compensated,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  CB200_NVTX("caustics_mag_extended_source_grad");
+  if (!grad) return CAUSTICS_ERR_BAD_ARG;
+  return ext_driver(w, mag, grad, nullptr, n, rho, lens, 0.0, 0, nullptr, nullptr, npts_limb, 0, 0.0, 100, itmax,
+                    compensated, workspace, workspace_bytes, stream);
 }
 
 int caustics_mag_extended_source_list(const void* w, double* mag, const int32_t* list, const int32_t* count,
@@ -372,7 +393,7 @@ int caustics_mag_extended_source_list(const void* w, double* mag, const int32_t*
                                       int limb_darkening, double u1, int npts_ld, int itmax, int compensated,
                                       void* workspace, size_t workspace_bytes, void* stream) {
   CB200_NVTX("caustics_mag_extended_source_list");
-  return ext_driver(w, mag, nullptr, max_count, rho, lens, 0.0, 2, list, count, npts_limb, limb_darkening, u1,
+  return ext_driver(w, mag, nullptr, nullptr, max_count, rho, lens, 0.0, 2, list, count, npts_limb, limb_darkening, u1,
                     npts_ld, itmax, compensated, workspace, workspace_bytes, stream);
 }
 
@@ -442,7 +463,7 @@ int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t
                  const caustics_lens* lens, double q, int npts_limb, int limb_darkening, double u1, int npts_ld,
                  int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream) {
   CB200_NVTX("caustics_mag");
-  return ext_driver(w, mag, used_hexadecapole, n, rho, lens, q, 1, nullptr, nullptr, npts_limb, limb_darkening, u1,
+  return ext_driver(w, mag, nullptr, used_hexadecapole, n, rho, lens, q, 1, nullptr, nullptr, npts_limb, limb_darkening, u1,
                     npts_ld, itmax, compensated, workspace, workspace_bytes, stream);
 }
 

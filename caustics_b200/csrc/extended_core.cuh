@@ -43,6 +43,7 @@ struct ExtCfg {
   int emit;         // 1: k_contours also writes the contour vertex lists (z, theta, contour id) for the host
   double u1;
   int64_t S;        // capacity (stride) of the source axis
+  int64_t ngrad_stride;   // number of points of the call (row length of ExtBuf::grad)
 };
 
 struct ExtBuf {
@@ -62,7 +63,9 @@ struct ExtBuf {
   int32_t* ncont;          // [S] number of contours emitted
   cb200_d2* cz0; double* cpar; int32_t* cstart;   // [CMAX(+1)][S] per contour: centroid, parity, first vertex
   const double* glx; const double* glw;          // Gauss-Legendre nodes/weights, n1 then n2
+  const double* jit;       // [D][nadd][2] the reference's warm-start jitters (jitter_table_body), same for every source
   double* mag;             // result, indexed like w (through list)
+  double* grad;            // optional (uniform disk): [NGRAD][cfg.ngrad_stride] d mag / d(a, e1, e2, Re r3, Im r3, Re w, Im w, rho)
 };
 
 __device__ __forceinline__ int64_t nsrc(const ExtCfg& c, const ExtBuf& b) {
@@ -438,9 +441,9 @@ __device__ void refine_solve_body(const ExtCfg& cfg, const ExtBuf& b, const Lens
     const int lf = b.left[I2(r, s)];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-      const cd jit = limb_jitter(j, r, D, cfg.nadd);      // extended_source.py:83-85
-      sm.zre[j][tid] = b.zre[I3(lf, j, s)] + jit.re;
-      sm.zim[j][tid] = b.zim[I3(lf, j, s)] + jit.im;
+      const double* jt = b.jit + 2 * (j * cfg.nadd + r);  // extended_source.py:83-85
+      sm.zre[j][tid] = b.zre[I3(lf, j, s)] + jt[0];
+      sm.zim[j][tid] = b.zim[I3(lf, j, s)] + jt[1];
     }
   }
   solve_and_store<NL, COMP, NT>(cfg, b, L, sm, tid, active, w, true, slot, s);
@@ -463,8 +466,8 @@ __device__ void refine_solve_group_body(const ExtCfg& cfg, const ExtBuf& b, cons
   if (valid) {
     w = limb_point(source_centre(cfg, b, L, s), cfg.rho, b.theta[I2(slot, s)]);
     const int lf = b.left[I2(r, s)];
-    const cd jit = limb_jitter(j, r, D, cfg.nadd);
-    z = mk(b.zre[I3(lf, j, s)] + jit.re, b.zim[I3(lf, j, s)] + jit.im);
+    const double* jt = b.jit + 2 * (j * cfg.nadd + r);
+    z = mk(b.zre[I3(lf, j, s)] + jt[0], b.zim[I3(lf, j, s)] + jt[1]);
   }
   cd p[D + 1];
   lens_poly<NL>(L, w, p);
@@ -490,6 +493,19 @@ __device__ void refine_solve_single_body(const ExtCfg& cfg, const ExtBuf& b, con
   const int slot = cfg.N0 + round * cfg.nadd + r;
   store_single(cfg, b, limb_point(source_centre(cfg, b, L, s), cfg.rho, b.theta[I2(slot, s)]), slot, s);
   update_widths<2>(cfg, b, r, slot, s);
+}
+
+// The (deg, nadd) jitter table is the same for every source and every round: one tiny launch fills it
+// (entry t = j * nadd + r) instead of ~20 threefry blocks per refinement solve.
+__device__ __forceinline__ void jitter_table_body(int D, int nadd, double* out, int t) {
+  if (t >= D * nadd) return;
+  const cd v = limb_jitter(t / nadd, t % nadd, D, nadd);
+  out[2 * t] = v.re;
+  out[2 * t + 1] = v.im;
+}
+// duplicates are rare: keep the generator out of line so it does not cost the matching loop registers
+__device__ __noinline__ double duplicate_jitter_cold(int j, int p, int deg, int npts) {
+  return duplicate_jitter(j, p, deg, npts);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -526,7 +542,7 @@ __device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
         if (k < j && zr[k] == zr[j] && zi[k] == zi[j]) dup = true;
         if (p > 0 && cre[k] == zr[j] && cim[k] == zi[j]) dup = true;
       }
-      if (dup) zr[j] += duplicate_jitter(j, p, D, cfg.NP);   // extended_source.py:144-148
+      if (dup) zr[j] += duplicate_jitter_cold(j, p, D, cfg.NP);   // extended_source.py:144-148
     }
     unsigned used = 0;
     double nre[D], nim[D];
@@ -577,7 +593,7 @@ struct Tracks {
     return mk(b.sre[(((int64_t)p * cfg.D + track) * cfg.S + s)], b.sim[(((int64_t)p * cfg.D + track) * cfg.S + s)]);
   }
   __device__ __forceinline__ double th(int p) const {
-    if (!b.vth) return 0.0;
+    if (!b.vth && !b.grad) return 0.0;
     if (st) return st->th[p];
     return b.theta[(int64_t)b.order[(int64_t)p * cfg.S + s] * cfg.S + s];
   }
@@ -659,6 +675,84 @@ struct GreenAcc {
   __device__ double close() { if (any) add(first); return sum; }
 };
 
+// Tangent of the uniform-disk area with respect to the low-level parameters, accumulated while the
+// contour is walked (the rule is the reference's implicit-function JVP,
+// ehrlich_aberth_primitive.py:290-324, written on the lens equation: every contour vertex is a zero of
+// F(z) = z - sum_j eps_j / (conj z - conj r_j) - w,  w = wc + rho e^{i theta}, so
+//   dz/dt = (-F_t + g conj(F_t)) / (1 - |g|^2),   g = dF/d(conj z) = sum_j eps_j / (conj z - conj r_j)^2,
+// with the sampling theta, the masks and the contour topology constants -- exactly what jax.grad sees).
+// Parameters t, in the order of the C ABI: a, e1, e2, Re r3, Im r3, Re wc, Im wc, rho.
+// The area 1/2 sum_i (x_i y_{i+1} - x_{i+1} y_i) of a closed polygon has the tangent
+//   1/2 sum_i [ dx_i (y_{i+1} - y_{i-1}) - dy_i (x_{i+1} - x_{i-1}) ]   (cyclic),
+// so a vertex's tangent meets only the POSITIONS of its neighbours: no tangent is carried along the walk.
+constexpr int NGRAD = 8;
+template <int NL>
+struct GreenTangent {
+  const LensConst& L;
+  double rho;
+  double d[NGRAD];          // tangent of the current contour's area
+  cd z0, z1, zp, zc;        // first two vertices; previous and current vertex
+  double th0, th1, thc;
+  int cnt;
+  __device__ GreenTangent(const LensConst& L_, double rho_) : L(L_), rho(rho_) {}
+  __device__ void start() {
+#pragma unroll
+    for (int k = 0; k < NGRAD; ++k) d[k] = 0.0;
+    cnt = 0;
+  }
+  // vertex z (limb angle th) with neighbours zprev, znext
+  __device__ void vertex(cd z, double th, cd zprev, cd znext) {
+    const cd zb = conj(z);
+    cd u[3], g = mk(0, 0);
+    constexpr int M = NL == 1 ? 1 : NL;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      u[j] = crecip(NL == 1 ? zb : zb - conj(L.r[j]));
+      g = g + (NL == 1 ? 1.0 : L.eps[j]) * (u[j] * u[j]);
+    }
+    const double den = 1.0 / (1.0 - norm2(g));
+    const double wy = 0.5 * (znext.im - zprev.im), wx = 0.5 * (znext.re - zprev.re);
+    auto acc = [&](int k, cd Ft) {
+      const cd dz = den * (g * conj(Ft) - Ft);
+      d[k] += dz.re * wy - dz.im * wx;
+    };
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    acc(5, mk(-1.0, 0.0));
+    acc(6, mk(0.0, -1.0));
+    acc(7, mk(-cs, -sn));
+    if (NL >= 2) {
+      const cd q0 = L.eps[0] * (u[0] * u[0]), q1 = L.eps[1] * (u[1] * u[1]);
+      acc(0, q1 - q0);                                        // r_1 = a, r_2 = -a
+      if (NL == 2) acc(1, u[1] - u[0]);                       // eps = (e1, 1 - e1)
+      else {
+        const cd q2 = L.eps[2] * (u[2] * u[2]);
+        acc(1, u[2] - u[0]);                                  // eps = (e1, e2, 1 - e1 - e2)
+        acc(2, u[2] - u[1]);
+        acc(3, -q2);                                          // r_3 = r3: F_t = -eps_3 u_3^2 conj(dr3/dt)
+        acc(4, mk(0.0, 1.0) * q2);
+      }
+    }
+  }
+  __device__ void add(cd z, double th) {
+    if (cnt == 0) { z0 = z; th0 = th; }
+    else if (cnt == 1) { z1 = z; th1 = th; }
+    else vertex(zc, thc, zp, z);
+    zp = cnt == 0 ? z : zc;
+    zc = z; thc = th;
+    ++cnt;
+  }
+  // closes the polygon (the reference appends the first point again, :724-725) and adds parity * tangent to out
+  __device__ void close(double par, double (&out)[NGRAD]) {
+    if (cnt >= 2) {
+      vertex(zc, thc, zp, z0);        // last vertex: neighbours (previous, first)
+      vertex(z0, th0, zc, z1);        // first vertex: neighbours (last, second)
+    }
+#pragma unroll
+    for (int k = 0; k < NGRAD; ++k) out[k] += par * d[k];
+  }
+};
+
 // limb-darkening vertex emitter: appends the vertices of one closed contour (closing point included)
 struct LdEmit {
   const ExtCfg& cfg; const ExtBuf& b; int64_t s; int nv, nc; cd first, csum; int cnt0; bool any; double first_th;
@@ -685,10 +779,17 @@ struct LdEmit {
   }
 };
 
-template <int D>
+template <int D, bool GRAD = false>
 __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s,
                               const TrackStage* stage = nullptr) {
   if (s >= nsrc(cfg, b)) return;
+  constexpr int NLG = D == 2 ? 1 : (D == 5 ? 2 : 3);
+  GreenTangent<NLG> GT(L, cfg.rho);
+  double dtot[NGRAD];
+  if (GRAD) {
+#pragma unroll
+    for (int k = 0; k < NGRAD; ++k) dtot[k] = 0.0;
+  }
   const Tracks T{cfg, b, s, stage};
   const int NP = cfg.NP;
   const double norm = 1.0 / (3.14159265358979323846 * cfg.rho * cfg.rho);
@@ -719,6 +820,11 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
 #pragma unroll 8
       for (int p = 0; p < NP; ++p) G.add(T.pt(i, p));
       total += par * G.close();
+      if (GRAD) {
+        GT.start();
+        for (int p = 0; p < NP; ++p) GT.add(T.pt(i, p), T.th(p));
+        GT.close(par, dtot);
+      }
     }
   }
 
@@ -834,6 +940,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
       const double par = chain_parity(parts, act);
       if (emit) E.start();
       G.start();
+      if (GRAD) GT.start();
       for (int q = act.head; q < act.tail; ++q) {
         const Seg& g = parts[act.seg[q]];
         const int n = seg_n(g);
@@ -842,10 +949,12 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
           const cd z = T.pt(g.track, pidx);
           if (emit) E.add(z, T.th(pidx));
           G.add(z);
+          if (GRAD) GT.add(z, T.th(pidx));
         }
       }
       if (emit) E.close(par);
       total += par * G.close();
+      if (GRAD) GT.close(par, dtot);
     }
   }
   if (emit) {
@@ -854,6 +963,14 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
     b.ncont[s] = E.nc < cfg.CMAX ? E.nc : cfg.CMAX;
   }
   if (!cfg.ld && b.mag) b.mag[out_idx] = fabs(total) * norm;
+  if (GRAD) {
+    // mag = |A| / (pi rho^2): d mag = sign(A) dA / (pi rho^2), and -2 mag / rho more for rho itself
+    const double sg = total < 0.0 ? -norm : norm;
+    const int64_t n = cfg.ngrad_stride;
+#pragma unroll
+    for (int k = 0; k < NGRAD; ++k)
+      b.grad[(int64_t)k * n + out_idx] = sg * dtot[k] - (k == 7 ? 2.0 * fabs(total) * norm / cfg.rho : 0.0);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ inline void leggauss(int n, double* x, double* w) {
 }
 
 struct Layout {
-  size_t theta, zre, zim, flg, order, left, right, dval, sre, sim, sflg, vz, vP, vQ, vcid, vcount, ncont, cz0, cpar, cstart, gl, list, count, total;
+  size_t theta, zre, zim, flg, order, left, right, dval, sre, sim, sflg, vz, vP, vQ, vcid, vcount, ncont, cz0, cpar, cstart, gl, jit, list, count, total;
 };
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -54,6 +54,7 @@ inline Layout make_layout(const ExtCfg& c, int64_t npoints = -1) {
     l.cz0 = take((size_t)c.CMAX * S * 16); l.cpar = take((size_t)c.CMAX * S * 8); l.cstart = take((size_t)(c.CMAX + 1) * S * 4);
     l.gl = take((size_t)(c.n1 + c.n2) * 16);
   } else { l.vz = l.vP = l.vQ = l.vcid = l.vcount = l.ncont = l.cz0 = l.cpar = l.cstart = l.gl = 0; }
+  l.jit = take((size_t)NADD_MAX * 10 * 16);
   l.list = take(NL * 4); l.count = take(256);
   l.total = o;
   return l;
@@ -92,6 +93,7 @@ inline ExtBuf bind(const ExtCfg& c, const Layout& l, void* ws) {
     b.cz0 = (cb200_d2*)(base + l.cz0); b.cpar = (double*)(base + l.cpar); b.cstart = (int32_t*)(base + l.cstart);
     b.glx = (const double*)(base + l.gl); b.glw = b.glx + (c.n1 + c.n2);
   }
+  b.jit = (const double*)(base + l.jit);
   return b;
 }
 

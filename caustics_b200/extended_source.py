@@ -226,14 +226,77 @@ def _mag_from_contours(cont, wf, rho, nlenses, params, newton_steps=1, ld=None):
     return (torch.abs(total) / (np.pi * rho_t**2)).reshape(cont["shape"])
 
 
+class _UniformMagGrad(torch.autograd.Function):
+    """Uniform-disk magnification whose backward pass is the tangent the kernels emit alongside the forward
+    pass (caustics_mag_extended_source_grad: d mag / d(a, e1, e2, r3, w + x_cm, rho) per source, the
+    implicit-function rule on every contour vertex pushed through the trapezoid sum on the device).  The
+    chain from the low-level to the user's (s, q, q3, r3, psi) parameters is ordinary torch autograd around
+    this Function (`lens_params`), i.e. the JVP rule itself stays in Python."""
+
+    @staticmethod
+    def forward(ctx, wf, rho, a, e1, e2, r3, x_cm, nlenses, npts_limb, itmax, comp):
+        L = _lib.lib()
+        lens = _lib.Lens()
+        lens.nlenses, lens.x_cm = nlenses, float(x_cm)
+        if nlenses >= 2:
+            lens.a, lens.e1 = float(a), float(e1)
+        if nlenses == 3:
+            lens.e2, lens.r3_re, lens.r3_im = float(e2), float(r3.real), float(r3.imag)
+        wd = wf.detach().to(torch.complex128).resolve_conj().resolve_neg().contiguous()
+        n = wd.numel()
+        mag = torch.empty(n, dtype=torch.float64, device=wd.device)
+        chunk = _chunk_len(L, n, nlenses, npts_limb, False, 100)
+        parts = []
+        with torch.cuda.device(wd.device):
+            st = torch.cuda.current_stream().cuda_stream
+            nbytes = L.caustics_ext_workspace_bytes(chunk, nlenses, int(npts_limb), 0, 100)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=wd.device)
+            for off in range(0, n, chunk):
+                m = min(chunk, n - off)
+                g = torch.empty((8, m), dtype=torch.float64, device=wd.device)
+                _lib.check(L.caustics_mag_extended_source_grad(wd.data_ptr() + 16 * off, mag.data_ptr() + 8 * off,
+                                                               g.data_ptr(), m, float(rho), lens, int(npts_limb),
+                                                               int(itmax), int(bool(comp)), ws.data_ptr(), nbytes, st))
+                parts.append(g)
+        ctx.save_for_backward(parts[0] if len(parts) == 1 else torch.cat(parts, dim=1))
+        return mag
+
+    @staticmethod
+    def backward(ctx, gout):
+        G, = ctx.saved_tensors
+        t = G * gout[None, :]
+        s = t.sum(dim=1)
+        # complex inputs: torch's convention for a real loss is dL/dRe + i dL/dIm
+        return (torch.complex(t[5], t[6]), s[7], s[0], s[1], s[2], torch.complex(s[3], s[4]), s[5],
+                None, None, None, None)
+
+
+def _mag_uniform_kernel_grad(w0, rho, nlenses, npts_limb, roots_itmax, roots_compensated, params):
+    """differentiable uniform-disk magnification through the fused forward + tangent kernel"""
+    _lib.require_cuda()
+    dev = w0.device if isinstance(w0, torch.Tensor) and w0.is_cuda else torch.device("cuda")
+    w0t = (w0.to(dev, torch.complex128) if isinstance(w0, torch.Tensor)
+           else torch.as_tensor(w0, dtype=torch.complex128, device=dev))
+    p, x_cm = lens_params(nlenses, **params) if nlenses > 1 else ({}, 0.0)
+    R = lambda v: v.to(dev, torch.float64) if isinstance(v, torch.Tensor) else torch.tensor(float(v), dtype=torch.float64, device=dev)
+    C = lambda v: v.to(dev, torch.complex128) if isinstance(v, torch.Tensor) else torch.tensor(complex(v), dtype=torch.complex128, device=dev)
+    out = _UniformMagGrad.apply(w0t.reshape(-1), R(rho), R(p.get("a", 0.0)), R(p.get("e1", 0.0)), R(p.get("e2", 0.0)),
+                                C(p.get("r3", 0.0)), R(x_cm), int(nlenses), int(npts_limb), int(roots_itmax),
+                                bool(roots_compensated))
+    return out.reshape(tuple(w0t.shape))
+
+
 def _mag_uniform_differentiable(w0, rho, nlenses, npts_limb, roots_itmax, roots_compensated, params, ld=None):
-    """Magnification with gradients w.r.t. w0, rho, u1 and the lens parameters: contours from the
-    kernels, gradient by the implicit-function rule (sampling, masks and contour topology are
-    constants, exactly as in the reference's jax.grad).  `ld` = (u1, npts_ld) for limb darkening.
-    Sources are processed in slices so the (vertex, source, node) quadrature tensors stay small."""
-    cont = _get_contours(w0, rho, nlenses, npts_limb, roots_itmax, roots_compensated, params)
+    """Magnification with gradients w.r.t. w0, rho, u1 and the lens parameters (sampling, masks and
+    contour topology are constants, exactly as in the reference's jax.grad).
+    Uniform disk: forward value and tangent come out of ONE kernel pass (`_UniformMagGrad`).
+    `ld` = (u1, npts_ld), limb darkening: contours from the kernels, the Dominik P/Q quadrature and its
+    gradient in torch on those vertices (`_mag_from_contours`, which is also the executable specification the
+    kernel tangent is tested against); sources are processed in slices so the (vertex, source, node)
+    quadrature tensors stay small."""
     if ld is None:
-        return _mag_from_contours(cont, cont["wf"], rho, nlenses, params)
+        return _mag_uniform_kernel_grad(w0, rho, nlenses, npts_limb, roots_itmax, roots_compensated, params)
+    cont = _get_contours(w0, rho, nlenses, npts_limb, roots_itmax, roots_compensated, params)
     n = cont["wf"].numel()
     outs = []
     for lo in range(0, n, 16):

@@ -224,6 +224,18 @@ int caustics_mag(const void* w, double* mag, uint8_t* used_hexadecapole, int64_t
                  const caustics_lens* lens, double q, int npts_limb, int limb_darkening, double u1, int npts_ld,
                  int itmax, int compensated, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Uniform-disk magnification AND its tangent in one pass: grad (8, n) float64 =
+ * d mag / d(a, e1, e2, Re r3, Im r3, Re w, Im w, rho) per source, low-level lens parameters as in
+ * caustics_lens (w is the source centre AFTER the x_cm shift; entries of parameters the lens does not have
+ * are 0).  The rule is the reference's implicit-function JVP (ehrlich_aberth_primitive.py:290-324) applied
+ * on the lens equation at every contour vertex and pushed through the trapezoid sum while the contour is
+ * walked; limb sampling, masks, gate decisions and contour topology are constants, which is what jax.grad
+ * differentiates in the reference (tests/test_extended_source.py:294-331).  The chain to the high-level
+ * (s, q, q3, r3, psi) parameters stays in Python (caustics_b200/extended_source.py). */
+int caustics_mag_extended_source_grad(const void* w, double* mag, double* grad, int64_t n, double rho,
+                                      const caustics_lens* lens, int npts_limb, int itmax, int compensated,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Second half of the two-call form  caustics_mag_gate -> (host reads *count, sizes the workspace) ->
  * here: full contour integration of the points w[list[k]], k < *count (device int32, <= max_count),
  * results to mag[list[k]].  workspace >= caustics_mag_workspace_bytes(max_count, m, ...) for any m >= 1. */

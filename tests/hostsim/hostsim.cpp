@@ -153,13 +153,19 @@ static void ext_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, int64_
     }
   }
   for (int64_t s = 0; s < ns; ++s) tracks_body<D>(cfg, b, s);
-  for (int64_t s = 0; s < ns; ++s) contours_body<D>(cfg, b, L, s);
+  for (int64_t s = 0; s < ns; ++s) {
+    if (b.grad) contours_body<D, true>(cfg, b, L, s); else contours_body<D>(cfg, b, L, s);
+  }
   if (cfg.ld) {
     for (int64_t g = 0; g < (int64_t)cfg.VMAX * cfg.S; ++g) ld_pq_body<NL>(cfg, b, L, g);
     for (int64_t s = 0; s < ns; ++s) ld_sum_body(cfg, b, s);
   }
 }
 
+
+// optional: where the next hostsim_mag_extended call writes d mag / d(a, e1, e2, Re r3, Im r3, Re w, Im w, rho), (8, n)
+static double* g_hostsim_grad = nullptr;
+extern "C" void hostsim_set_grad(double* out) { g_hostsim_grad = out; }
 
 extern "C" int hostsim_mag_extended(const double* w, double* mag, uint8_t* test_out, int64_t n, double rho, int nlenses,
                                     const double* eps, const double* r, const double* H, const double* G, double x_cm,
@@ -176,6 +182,9 @@ extern "C" int hostsim_mag_extended(const double* w, double* mag, uint8_t* test_
   ExtBuf b = bind(cfg, lay, ws.data());
   b.w = (const cb200_d2*)w;
   b.mag = mag;
+  b.grad = ld ? nullptr : g_hostsim_grad;
+  cfg.ngrad_stride = n;
+  for (int t = 0; t < cfg.D * cfg.nadd; ++t) jitter_table_body(cfg.D, cfg.nadd, (double*)(ws.data() + lay.jit), t);
   int32_t* list = (int32_t*)(ws.data() + lay.list);
   int32_t* count = (int32_t*)(ws.data() + lay.count);
   if (cfg.ld) {

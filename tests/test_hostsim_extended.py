@@ -255,3 +255,38 @@ def test_device_jitters_are_the_references(hs):
         hs.hostsim_jitters(deg, n, npts, limb.ctypes.data_as(vp), dup.ctypes.data_as(vp))
         assert np.array_equal(limb, jaxprng.limb_jitters(deg, n))
         assert np.array_equal(dup, jaxprng.duplicate_jitters(deg, npts))
+
+
+def test_fused_tangent_device_logic(hs):
+    """SURVEY 8 f2 on the CPU: the tangent accumulated inside contours_body (csrc/extended_core.cuh,
+    GreenTangent) against what does not depend on it -- the closed form of a source centred on a single lens,
+    d/d rho sqrt(1 + 4 / rho^2), and central differences of the forward pass for sources away from caustics
+    (w, rho, and s, q through the chain a = s/2, e1 = 1/(1+q), x_cm = a (1-q)/(1+q))"""
+    def with_grad(w, rho, nl, hp, **kw):
+        w = np.atleast_1d(np.asarray(w, complex))
+        gr = np.zeros((8, len(w)))
+        hs.hostsim_set_grad(gr.ctypes.data_as(vp))
+        try:
+            m = hs_ext(hs, w, rho, nl, hp, **kw)
+        finally:
+            hs.hostsim_set_grad(None)
+        return m, gr
+
+    rho = 0.1
+    m, gr = with_grad([1e-9 + 0j], rho, 1, {}, npts=300)
+    assert abs(gr[7, 0] / (-4 / (rho**3 * np.sqrt(1 + 4 / rho**2))) - 1) < 1e-3          # 300-gon vs circle
+    assert abs(gr[5, 0]) < 1e-3 and abs(gr[6, 0]) < 1e-3 and (gr[:5] == 0).all()          # symmetric; no lens parameters
+    w0 = np.array([0.8 + 0.6j, -1.2 + 0.3j, 0.1 + 1.1j])
+    s_, q_ = 0.9, 0.2
+    m, gr = with_grad(w0, 1e-2, 2, HP2)
+    assert np.array_equal(m, hs_ext(hs, w0, 1e-2, 2, HP2))                                # same forward value
+    h = 1e-5
+    fd = lambda f, x: (f(x + h) - f(x - h)) / (2 * h)
+    assert np.allclose(gr[5], fd(lambda x: hs_ext(hs, w0 + x, 1e-2, 2, HP2), 0.0), rtol=1e-5, atol=1e-7)
+    assert np.allclose(gr[6], fd(lambda x: hs_ext(hs, w0 + 1j * x, 1e-2, 2, HP2), 0.0), rtol=1e-5, atol=1e-7)
+    assert np.allclose(gr[7], (hs_ext(hs, w0, 1e-2 + 1e-6, 2, HP2) - hs_ext(hs, w0, 1e-2 - 1e-6, 2, HP2)) / 2e-6, rtol=2e-3)
+    ds = gr[0] * 0.5 + gr[5] * 0.5 * (1 - q_) / (1 + q_)
+    dq = gr[1] * (-1 / (1 + q_)**2) + gr[5] * (s_ / 2) * (-2) / (1 + q_)**2
+    assert np.allclose(ds, fd(lambda x: hs_ext(hs, w0, 1e-2, 2, dict(s=x, q=q_)), s_), rtol=1e-5, atol=1e-7)
+    assert np.allclose(dq, fd(lambda x: hs_ext(hs, w0, 1e-2, 2, dict(s=s_, q=x)), q_), rtol=1e-5, atol=1e-7)
+    assert (gr[2:5] == 0).all()                                                          # binary lens: no e2, r3
