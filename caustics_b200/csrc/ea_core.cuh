@@ -23,7 +23,10 @@
 //     (same sweep counts, same root order); results do not depend on the batch layout;
 //   * coefficients are normalised by a power of two on load (exact, roots unchanged) so that |.|^2
 //     comparisons can replace hypot() everywhere; reciprocals / square roots are branch-free
-//     (hardware seed + Newton);
+//     (hardware seed + Newton).  Supported range: the moduli of the coefficients, of the roots and of p'(root)
+//     may span ~1e+-150 around the largest coefficient (squares must stay inside the double range; the
+//     stopping test itself falls back to unsquared moduli, ea_exceeds).  The reference's hypot() and scaled
+//     complex division go further (z^10 - 1e-200); lens polynomials span < 1e10;
 //   * compensated kernels run the plain sweeps first and the polishing sweeps afterwards, with the
 //     per-step error terms summed plainly (see priest_sum4) -- same polished roots as the reference.
 // The FP64 pipe is the bound; a DFMA with three distinct register operands issues at 69 % of the
@@ -91,7 +94,10 @@ __device__ __forceinline__ void ea_normalise(cd (&p)[DEG + 1]) {
   int hi = __double2hiint(m);
   int ex = (hi >> 20) & 0x7ff;
   if (ex != 0 && ex != 0x7ff) {
-    double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex)
+    // 2^(1023-ex); for ex = 2046 (max |coefficient| >= 2^1023) that would be the exponent field 0, i.e. +0.0:
+    // scale by 2^-1022 instead (the largest coefficient ends up in [2, 4) -- still exact)
+    if (ex > 2045) ex = 2045;
+    double sc = __hiloint2double((2046 - ex) << 20, 0);
 #pragma unroll
     for (int i = 0; i <= DEG; ++i) { p[i].re *= sc; p[i].im *= sc; }
   }
@@ -264,6 +270,19 @@ template <int DEG, int NT> struct AlphaPick<DEG, NT, true> { typedef AlphaSmem<D
 template <int DEG, int NT> __device__ __forceinline__ void alpha_bind(AlphaRegs<DEG, NT>&, double*) {}
 template <int DEG, int NT> __device__ __forceinline__ void alpha_bind(AlphaSmem<DEG, NT>& a, double* base) { a.base = base; }
 
+// The stopping test |h| > thr (thr = EPS * b, ehrlich_aberth.h:109/:122) on squares, nh = |h|^2 -- except when
+// thr^2 would underflow (a polynomial whose coefficients span more than ~150 decades, e.g. z^10 - 1e-200:
+// |h| keeps shrinking far below sqrt(DBL_MIN) while the reference's hypot-based test is still unmet); there
+// the moduli are compared unsquared through a scaled hypot.  Rare path, inside the lazily evaluated block.
+__device__ __forceinline__ bool ea_exceeds(cd h, double nh, double thr) {
+  if (thr > 1e-150) return nh > __dmul_rn(thr, thr);
+  const double ar = fabs(h.re), ai = fabs(h.im);
+  const double m = fmax(ar, ai), q = fmin(ar, ai);
+  if (!(m > 0.0)) return false;
+  const double r = q / m;
+  return m * sqrt(fma(r, r, 1.0)) > thr;
+}
+
 // Value, derivative and the real bound polynomial in one unrolled Horner pass (horner.h:219-267).
 // MODE 0: every lane evaluates p at x (coefficients high->low); MODE 1: every lane evaluates the
 // reversed polynomial (coefficients from index 0, reference's rhorner_*); MODE 2: per-lane select.
@@ -371,12 +390,10 @@ __device__ __forceinline__ void ea_step_plain(const cd (&p)[DEG + 1], const ALPH
         ax = az2 * r0;
       }
       b = horner_bound<DEG, MODE, ALPHA>(al, ax, rev);
-      const double thr = EA_EPS * b;
-      big = nh > __dmul_rn(thr, thr);
+      big = ea_exceeds(h, nh, EA_EPS * b);
     }
   } else {
-    const double thr = EA_EPS * b;
-    big = nh > __dmul_rn(thr, thr);  // |h| > EPS*b, ehrlich_aberth.h:109/:122
+    big = ea_exceeds(h, nh, EA_EPS * b);  // |h| > EPS*b, ehrlich_aberth.h:109/:122
   }
   if (need && big) {
     zre[j * NT] = z.re - corr.re;
@@ -466,10 +483,14 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
   // through the Aberth sum, which steers but does not set the fixed point, so the polished roots are
   // the same -- golden vectors: identical to 5e-15 -- while the warp never executes the plain and
   // the compensated evaluation for the same root, and the plain stage runs the straight-line step.)
-  bool stage2 = false;
+  bool stage2 = false, spent = false;
   int s1 = 0, it2 = 0;   // own plain sweeps; polishing sweeps since the warp switched
   int it = 0;
-  for (; it < itmax; ++it) {
+  // Compensated kernels: a lane's budget is itmax of its OWN sweeps (plain + polishing); the sweeps it spends
+  // waiting for the other lanes of its warp to leave the plain stage are not charged, so whether a polynomial
+  // converges within itmax does not depend on its warp neighbours (the warp loop may run up to 2 itmax).
+  const int it_end = COMP ? (itmax > 0x3fffffff ? 0x7fffffff : 2 * itmax) : itmax;
+  for (; it < it_end; ++it) {
     if (COMP && !stage2 && __all_sync(0xffffffffu, c1 == FULL)) stage2 = true;
     const unsigned done_bits = COMP ? c2 : c1;
     if (__all_sync(0xffffffffu, done_bits == FULL)) break;
@@ -544,8 +565,7 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
             }
             b = horner_bound<DEG, 2, ALPHA>(al, ax, rev);
           }
-          const double thr = EA_EPS * b;
-          if (nh > thr * thr) upd = true;  // |h| > EPS*b, :109/:122
+          if (ea_exceeds(h, nh, EA_EPS * b)) upd = true;  // |h| > EPS*b, :109/:122
           else c1 |= (1u << j);
         }
       }
@@ -617,7 +637,7 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
         }
       }
     }
-    if (active && !res.converged) {
+    if (active && !res.converged && !spent) {
       if (!COMP) {
         res.sweeps = it + 1;
         if (c1 == FULL) res.converged = true;
@@ -626,6 +646,7 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
         if (s1 == 0 && c1 == FULL) s1 = it + 1;
         res.sweeps = (s1 ? s1 : it + 1) + it2;
         if (c2 == FULL) res.converged = true;
+        else if (res.sweeps >= itmax) { spent = true; c1 = FULL; c2 = FULL; }   // budget spent: stop, reported unconverged
       }
     }
   }
@@ -673,8 +694,7 @@ __device__ __forceinline__ int ea_solve_group(const cd (&p)[DEG + 1], cd& z, int
     cd h, hd;
     double b;
     horner_plain<DEG, 2, AlphaRegs<DEG, 1> >(p, al, x, ax, rev, h, hd, b);
-    const double thr = EA_EPS * b;
-    const bool upd = !conv && norm2(h) > thr * thr;
+    const bool upd = !conv && ea_exceeds(h, norm2(h), EA_EPS * b);
     conv = conv || !upd;
     cd num = h, den = hd;
     if (rev) {

@@ -329,10 +329,8 @@ int ext_driver(const void* w, double* mag, double* grad, uint8_t* test_out, int6
     // Gauss-Legendre tables: computed on the host and handed to the device as KERNEL ARGUMENTS, 256
     // doubles per launch.  (A cudaMemcpyAsync from this stack buffer would be fine eagerly, but a
     // captured CUDA graph would replay the copy from a dead host address.)
-    double tab[2 * 2048];
-    const int nn = cfg.n1 + cfg.n2;
-    leggauss(cfg.n1, tab, tab + nn);
-    leggauss(cfg.n2, tab + cfg.n1, tab + nn + cfg.n1);
+    double tab[2 * (2048 + 1024 + 512 + 8)];
+    const int nn = fill_gl_tables(cfg.n1, cfg.n2, tab);
     for (int off = 0; off < 2 * nn; off += TabChunk::N) {
       TabChunk c;
       const int m = 2 * nn - off < TabChunk::N ? 2 * nn - off : TabChunk::N;

@@ -12,6 +12,14 @@
 #include "lens_core.cuh"
 #include "multipole.cuh"
 
+// adaptive far-panel rule (two_panel): lengths in source radii below which the quarter / half order is used.
+// Measured on the golden sets (host build, npts_ld = 100): (0, 8) deviates <= 7e-5 from the reference's rule,
+// (2, 8) without the distance condition 4e-4, (0, 16) 2e-4 -- the integrand has square-root kinks wherever the
+// integration line leaves or enters an image, so low orders are only safe on short panels.
+#ifndef CB200_ADAPT_Q
+#define CB200_ADAPT_Q 0.0
+#define CB200_ADAPT_H 8.0
+#endif
 #ifndef CB200_EXT_STRAIGHT
 #define CB200_EXT_STRAIGHT 0   // warm-started limb solves: the branchy step (see ea_solve_thread)
 #endif
@@ -39,6 +47,7 @@ struct ExtCfg {
   int nl, D, N0, nadd, NP;
   double rho;
   int itmax, comp, ld, n1, n2, VMAX, CMAX;
+  int ld_adapt;     // opt-in: fewer Gauss-Legendre nodes on short far panels of the P/Q integrals (two_panel)
   int small;        // mask of small-batch phase variants: 1 warp select, 2 staged contours, 4 warp LD sum, 8 lane-per-root walk
   int emit;         // 1: k_contours also writes the contour vertex lists (z, theta, contour id) for the host
   double u1;
@@ -1007,7 +1016,18 @@ __device__ double two_panel(const ExtCfg& cfg, const ExtBuf& bf, const LensConst
   double tot = 0.0;
   for (int panel = 0; panel < 2; ++panel) {
     const double lo = panel == 0 ? a : split, hi = panel == 0 ? split : b;
-    const int n = panel == 0 ? cfg.n1 : cfg.n2, off = panel == 0 ? 0 : cfg.n1;
+    int n = panel == 0 ? cfg.n1 : cfg.n2, off = panel == 0 ? 0 : cfg.n1;
+    if (cfg.ld_adapt && panel == 0) {
+      // SURVEY 8 f4 (opt-in, default off so that parity with integrate.py:47-121 holds): the panel next to
+      // the vertex ends ON the limb, where the brightness has its square-root edge, and keeps its n2 nodes;
+      // a far panel that stays >= 2 rho away from the vertex and is only a few source radii long is
+      // integrated by the half-order rule.
+      const double len = fabs(split - a);
+      const int nh = cfg.n1 / 2 > 2 ? cfg.n1 / 2 : 2, nq = cfg.n1 / 4 > 2 ? cfg.n1 / 4 : 2;
+      const bool far = 0.5 * ad > 2.0 * rho;        // the far panel stays >= 2 rho away from the vertex
+      if (far && len <= CB200_ADAPT_Q * rho) { n = nq; off = cfg.n1 + cfg.n2 + nh; }
+      else if (far && len <= CB200_ADAPT_H * rho) { n = nh; off = cfg.n1 + cfg.n2; }
+    }
     const double hw = 0.5 * (hi - lo), mid = 0.5 * (hi + lo);
     double acc = 0.0;
     for (int k = 0; k < n; ++k) {

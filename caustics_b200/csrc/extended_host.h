@@ -32,6 +32,23 @@ inline void leggauss(int n, double* x, double* w) {
   }
 }
 
+// Gauss-Legendre tables of a limb-darkened call, nodes then weights, each laid out as
+// [n1 | n2 | nh = max(2, n1/2) | nq = max(2, n1/4)]: the two panels of integrate.py:56-75 and the two reduced
+// orders of the opt-in adaptive far panel (ExtCfg::ld_adapt).  Returns the number of nodes (= weights).
+inline int gl_table_nodes(int n1, int n2) {
+  const int nh = n1 / 2 > 2 ? n1 / 2 : 2, nq = n1 / 4 > 2 ? n1 / 4 : 2;
+  return n1 + n2 + nh + nq;
+}
+inline int fill_gl_tables(int n1, int n2, double* tab) {
+  const int nh = n1 / 2 > 2 ? n1 / 2 : 2, nq = n1 / 4 > 2 ? n1 / 4 : 2;
+  const int nn = n1 + n2 + nh + nq;
+  leggauss(n1, tab, tab + nn);
+  leggauss(n2, tab + n1, tab + nn + n1);
+  leggauss(nh, tab + n1 + n2, tab + nn + n1 + n2);
+  leggauss(nq, tab + n1 + n2 + nh, tab + nn + n1 + n2 + nh);
+  return nn;
+}
+
 struct Layout {
   size_t theta, zre, zim, flg, order, left, right, dval, sre, sim, sflg, vz, vP, vQ, vcid, vcount, ncont, cz0, cpar, cstart, gl, jit, list, count, total;
 };
@@ -52,7 +69,7 @@ inline Layout make_layout(const ExtCfg& c, int64_t npoints = -1) {
     l.vz = take((size_t)c.VMAX * S * 16); l.vP = take((size_t)c.VMAX * S * 8); l.vQ = take((size_t)c.VMAX * S * 8);
     l.vcid = take((size_t)c.VMAX * S); l.vcount = take(S * 4); l.ncont = take(S * 4);
     l.cz0 = take((size_t)c.CMAX * S * 16); l.cpar = take((size_t)c.CMAX * S * 8); l.cstart = take((size_t)(c.CMAX + 1) * S * 4);
-    l.gl = take((size_t)(c.n1 + c.n2) * 16);
+    l.gl = take((size_t)gl_table_nodes(c.n1, c.n2) * 16);
   } else { l.vz = l.vP = l.vQ = l.vcid = l.vcount = l.ncont = l.cz0 = l.cpar = l.cstart = l.gl = 0; }
   l.jit = take((size_t)NADD_MAX * 10 * 16);
   l.list = take(NL * 4); l.count = take(256);
@@ -71,6 +88,7 @@ inline int make_cfg(int64_t S, double rho, int nlenses, int npts_limb, int limb_
   if (c.N0 < 4 || c.nadd < 1 || c.nadd > NADD_MAX || c.NP > 4000) return CAUSTICS_ERR_BAD_ARG;
   c.rho = rho; c.itmax = itmax; c.comp = compensated ? 1 : 0;
   c.ld = limb_darkening ? 1 : 0; c.u1 = u1;
+  c.ld_adapt = (limb_darkening & 2) ? 1 : 0;
   c.n1 = npts_ld / 2; c.n2 = npts_ld - c.n1;
   if (c.ld && (c.n1 < 1 || npts_ld > 2048)) return CAUSTICS_ERR_BAD_ARG;
   c.CMAX = c.D + 3;
@@ -91,7 +109,7 @@ inline ExtBuf bind(const ExtCfg& c, const Layout& l, void* ws) {
     b.vz = (cb200_d2*)(base + l.vz); b.vP = (double*)(base + l.vP); b.vQ = (double*)(base + l.vQ);
     b.vcid = (uint8_t*)(base + l.vcid); b.vcount = (int32_t*)(base + l.vcount); b.ncont = (int32_t*)(base + l.ncont);
     b.cz0 = (cb200_d2*)(base + l.cz0); b.cpar = (double*)(base + l.cpar); b.cstart = (int32_t*)(base + l.cstart);
-    b.glx = (const double*)(base + l.gl); b.glw = b.glx + (c.n1 + c.n2);
+    b.glx = (const double*)(base + l.gl); b.glw = b.glx + gl_table_nodes(c.n1, c.n2);
   }
   b.jit = (const double*)(base + l.jit);
   return b;

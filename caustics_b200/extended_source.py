@@ -37,7 +37,8 @@ def _to_device(w):
 
 
 def _chunk_len(L, n, nlenses, npts_limb, ld, npts_ld, budget=None):
-    per1 = L.caustics_ext_workspace_bytes(1, nlenses, npts_limb, int(ld), npts_ld)
+    ld = int(bool(ld))
+    per1 = L.caustics_ext_workspace_bytes(1, nlenses, npts_limb, ld, npts_ld)
     if per1 == 0:
         raise ValueError("unsupported extended-source configuration "
                          "(need 8 <= npts_limb <= 1280, nlenses in 1..3, npts_ld <= 2048)")
@@ -60,7 +61,9 @@ def _run(w, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax, r
     if n == 0:
         return (restore(mag), restore(test.bool())) if return_test else restore(mag)
     rho = float(rho)
-    ld, comp = int(bool(limb_darkening)), int(bool(roots_compensated))
+    # limb_darkening = "adaptive": CAUSTICS_LD_ADAPTIVE (fewer quadrature nodes on short far panels, opt-in)
+    ld = (3 if limb_darkening == "adaptive" else 1) if limb_darkening else 0
+    comp = int(bool(roots_compensated))
     cfg = (int(npts_limb), ld, float(u1), int(npts_ld), int(roots_itmax), comp)
     with torch.cuda.device(flat.device):
         st = torch.cuda.current_stream().cuda_stream
@@ -310,7 +313,9 @@ def _mag_uniform_differentiable(w0, rho, nlenses, npts_limb, roots_itmax, roots_
 def mag_extended_source(w0, rho, nlenses=2, npts_limb=150, limb_darkening=False, u1=0.0, npts_ld=100,
                         roots_itmax=2500, roots_compensated=False, **params):
     """Magnification of a (limb-darkened) disk of radius `rho` centred on `w0` by contour
-    integration in the image plane; arguments as in the reference (extended_source.py:741-805)."""
+    integration in the image plane; arguments as in the reference (extended_source.py:741-805).
+    `limb_darkening="adaptive"` (no reference counterpart) integrates short far panels of the
+    Dominik P/Q integrals with a lower-order Gauss-Legendre rule; True is the reference's quadrature."""
     if nlenses not in (1, 2, 3):
         raise ValueError("`nlenses` has to be set to be <= 3.")
     if _requires_grad(w0, rho, u1, *params.values()):

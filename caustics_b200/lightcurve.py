@@ -52,13 +52,17 @@ class AnnualParallaxTrajectory:
         is_t = isinstance(t, torch.Tensor)
         td = _dev(t)
         w = torch.empty(td.shape, dtype=torch.complex128, device=td.device)
-        tabs = [None] * 5 if self.t_jpl is None else [x.to(td.device).data_ptr() for x in
-                                                      (self.t_jpl, self.s_e, self.s_n, self.s_e_dot, self.s_n_dot)]
+        # the tables moved to t's device stay referenced until after the launch (a temporary freed before the
+        # kernel is enqueued could be handed out again by the caching allocator)
+        moved = [] if self.t_jpl is None else [x.to(td.device) for x in
+                                               (self.t_jpl, self.s_e, self.s_n, self.s_e_dot, self.s_n_dot)]
+        tabs = [None] * 5 if self.t_jpl is None else [x.data_ptr() for x in moved]
         with torch.cuda.device(td.device):
             _lib.check(_lib.lib().caustics_trajectory(
                 td.data_ptr(), w.data_ptr(), td.numel(), float(params["t0"]), float(params["tE"]),
                 float(params["u0"]), psi, piE, *tabs, 0 if self.t_jpl is None else self.t_jpl.numel(),
                 torch.cuda.current_stream().cuda_stream))
+        del moved
         if is_t:
             return w if t.is_cuda else w.cpu()
         return w.cpu().numpy()

@@ -143,10 +143,12 @@ class _PolyRoots(torch.autograd.Function):
 
 
 def poly_roots(coeffs, itmax=2000, compensated=False, custom_init=False, roots_init=None, flags=0,
-               out=None):
+               out=None, check=False):
     """Roots of complex polynomials; the last axis of `coeffs` holds the coefficients starting from
     the HIGHEST order term (reference docstring, ehrlich_aberth_primitive.py:49-65).  Returns the
-    same shape with the last axis shrunk by one."""
+    same shape with the last axis shrunk by one.
+    `check=True` (no reference counterpart: the reference prints "not all roots converged" from C++) also
+    fetches the per-polynomial sweep counts and warns when a polynomial ran into `itmax`."""
     ncoeffs = coeffs.shape[-1]
     out_shape = tuple(coeffs.shape[:-1]) + (ncoeffs - 1,)
     flat = coeffs.reshape(-1, ncoeffs)
@@ -159,6 +161,15 @@ def poly_roots(coeffs, itmax=2000, compensated=False, custom_init=False, roots_i
         roots = _PolyRoots.apply(torch.flip(flat, dims=[1]), ri, itmax, compensated, custom_init, flags)
     else:
         # the kernel reads the rows back to front instead of materialising coeffs[:, ::-1]
-        roots = _solve_flat(flat, ri, itmax, compensated, custom_init,
-                            flags | _lib.FLAG_COEFFS_HIGH_FIRST, out=out)
+        if check and out is None:
+            roots, sweeps = _solve_flat(flat, ri, itmax, compensated, custom_init,
+                                        flags | _lib.FLAG_COEFFS_HIGH_FIRST, return_sweeps=True)
+            bad = int((sweeps < 0).sum())
+            if bad:
+                import warnings
+                warnings.warn(f"poly_roots: {bad} of {flat.shape[0]} polynomials did not converge within itmax={itmax}",
+                              RuntimeWarning, stacklevel=2)
+        else:
+            roots = _solve_flat(flat, ri, itmax, compensated, custom_init,
+                                flags | _lib.FLAG_COEFFS_HIGH_FIRST, out=out)
     return roots.reshape(out_shape)

@@ -206,7 +206,14 @@ int caustics_mag_point_source_grid_host(double x0, double y0, double dx, double 
  * caustics_mag is the light-curve entry (lightcurve.py:99-254): binary lenses use the hexadecapole
  * approximation wherever the reference's validity tests pass (q is the user's mass ratio, tested
  * against 0.01 for the planetary-caustic test) and full integration elsewhere; used_hexadecapole
- * (n) uint8, optional, records the decision.  Limits: npts_limb <= 1280, n * (D*npts_limb) < 2^31. */
+ * (n) uint8, optional, records the decision.  Limits: npts_limb <= 1280, n * (D*npts_limb) < 2^31.
+ * limb_darkening: 0 uniform disk, 1 linear limb darkening with the reference's quadrature
+ * (integrate.py:47-121: npts_ld/2 + npts_ld/2 Gauss-Legendre nodes per P and Q integral of every contour
+ * vertex), 1 | CAUSTICS_LD_ADAPTIVE the same with the half-order rule (npts_ld/4 nodes) on far panels that
+ * are at most 8 rho long and stay 2 rho away from the vertex (the panel that ends on the limb
+ * keeps its nodes).  Opt-in: it moves results by up to 7e-5, so the default stays the
+ * reference's rule. */
+#define CAUSTICS_LD_ADAPTIVE 2
 size_t caustics_ext_workspace_bytes(int64_t n, int nlenses, int npts_limb, int limb_darkening, int npts_ld);
 /* workspace of a GATED call (caustics_mag, caustics_mag_extended_source_list) over n points that
  * integrates at most max_full sources at a time: per-source arrays for max_full sources + the compact

@@ -188,10 +188,7 @@ extern "C" int hostsim_mag_extended(const double* w, double* mag, uint8_t* test_
   int32_t* list = (int32_t*)(ws.data() + lay.list);
   int32_t* count = (int32_t*)(ws.data() + lay.count);
   if (cfg.ld) {
-    const int nn = cfg.n1 + cfg.n2;
-    double* tab = (double*)(ws.data() + lay.gl);
-    leggauss(cfg.n1, tab, tab + nn);
-    leggauss(cfg.n2, tab + cfg.n1, tab + nn + cfg.n1);
+    fill_gl_tables(cfg.n1, cfg.n2, (double*)(ws.data() + lay.gl));
   }
   int64_t ns = n;
   if (gate && nlenses == 2) {

@@ -210,7 +210,7 @@ def test_fused_tangent_kernel_vs_python_rule(cb):
         kern = run(lambda w, rho, t: es._mag_uniform_kernel_grad(w, rho, nl, 200, 2500, False, t))
         spec = run(lambda w, rho, t: es._mag_from_contours(es._get_contours(w, rho, nl, 200, 2500, False, t),
                                                            w.reshape(-1), rho, nl, t))
-        assert torch.allclose(kern[0], spec[0], rtol=1e-12, atol=0)
+        assert torch.allclose(kern[0], spec[0], rtol=1e-10, atol=0)       # (another summation order)
         assert torch.allclose(kern[1], spec[1], rtol=1e-8, atol=1e-9 * spec[1].abs().max().item())
         assert abs(kern[2].item() - spec[2].item()) <= 1e-8 * abs(spec[2].item())
         for k in hp:

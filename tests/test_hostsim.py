@@ -114,3 +114,24 @@ def test_device_code_update_count_is_the_reference_algorithms(ea_golden):
     assert abs(updates - st[0]) <= 1e-4 * st[0]
     assert 95.0 < updates / len(c) < 95.4
     assert evals - updates == 10 * len(c)
+
+
+def test_extreme_dynamic_range(hs):
+    """ADVICE r1: (i) a polynomial whose largest coefficient is >= 2^1023 must not be scaled by +0.0;
+    (ii) when EPS*b is so small that its square underflows (z^10 - 1e-140: roots of modulus 1e-14, stopping
+    threshold ~1e-156) the stopping test compares unsquared moduli.  (Spans beyond ~1e+-150 between the
+    moduli involved, e.g. z^10 - 1e-200, overflow the squared moduli inside the complex divisions as well;
+    that range is documented as unsupported in ea_core.cuh -- lens polynomials are nowhere near it.)"""
+    big = np.zeros((1, 6), complex)
+    big[0] = [2.0**1023, -3 * 2.0**1020, 2.0**1000, 1.0, 0.5, 2.0**1023 * 0.75]     # low -> high
+    got, sw = hs_solve(hs, big)
+    want = np.roots((big[0] * 2.0**-1000)[::-1])[None, :]       # (the reference itself overflows on this input)
+    assert np.isfinite(got).all() and sw[0] > 0
+    assert set_distance(got, want).max() < 1e-10
+    c = np.zeros((1, 11), complex)
+    c[0, 0], c[0, 10] = -1e-140, 1.0
+    got, sw = hs_solve(hs, c)
+    exact = 1e-14 * np.exp(2j * np.pi * np.arange(10) / 10)
+    assert 0 < sw[0] < 100                          # (squared compare: thr^2 = 0, spins until |h|^2 underflows or itmax)
+    rel = np.abs(np.sort_complex(got[0]) - np.sort_complex(exact)) / 1e-14
+    assert rel.max() < 1e-12

@@ -290,3 +290,15 @@ def test_fused_tangent_device_logic(hs):
     assert np.allclose(ds, fd(lambda x: hs_ext(hs, w0, 1e-2, 2, dict(s=x, q=q_)), s_), rtol=1e-5, atol=1e-7)
     assert np.allclose(dq, fd(lambda x: hs_ext(hs, w0, 1e-2, 2, dict(s=s_, q=x)), q_), rtol=1e-5, atol=1e-7)
     assert (gr[2:5] == 0).all()                                                          # binary lens: no e2, r3
+
+
+def test_adaptive_limb_darkening_quadrature(hs, g):
+    """SURVEY 8 f4, opt-in (CAUSTICS_LD_ADAPTIVE): half-order Gauss-Legendre rule on short far panels of the P/Q
+    integrals stays within 1e-4 of the reference's rule on the caustic-crossing golden sources, and the default
+    (off) is untouched"""
+    for w, rho, nl, hp, u1 in ((g["b_w_0.01"][:16], 1e-2, 2, HP2, 0.7), (g["b_w_0.1"][:8], 1e-1, 2, HP2, 0.7),
+                               (g["t_w_0.01"][:4], 1e-2, 3, HP3, 0.3)):
+        ref = hs_ext(hs, w, rho, nl, hp, ld=1, u1=u1)
+        ada = hs_ext(hs, w, rho, nl, hp, ld=3, u1=u1)
+        assert np.abs(ada / ref - 1).max() < 1e-4 and not np.array_equal(ada, ref)
+    assert np.abs(hs_ext(hs, g["b_w_0.01"][:16], 1e-2, 2, HP2, ld=1, u1=0.7) / g["b_ld_0.01"] - 1).max() < 1e-9
