@@ -67,35 +67,58 @@ __global__ void __launch_bounds__(NT) k_limb_walk_group(ExtCfg cfg, ExtBuf b, Le
   __shared__ EASmem<NL * NL + 1, false, NT> sm;
   limb_walk_group_body<NL, NT>(cfg, b, L, sm, threadIdx.x, (int64_t)blockIdx.x * (NT / 32) + threadIdx.x / 32);
 }
-template <int NL>
-__global__ void __launch_bounds__(NT) k_refine_solve_group(ExtCfg cfg, ExtBuf b, LensConst L, int round) {
-  refine_solve_group_body<NL>(cfg, b, L, round, threadIdx.x, (int64_t)blockIdx.x * (NT / 32) + threadIdx.x / 32);
-}
 __global__ void __launch_bounds__(NT) k_limb_walk_single(ExtCfg cfg, ExtBuf b, LensConst L) {
   limb_walk_single_body(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
-template <int D>
-__global__ void __launch_bounds__(NT) k_refine_select(ExtCfg cfg, ExtBuf b, int round) {
-  refine_select_body<D>(cfg, b, round, (int64_t)blockIdx.x * NT + threadIdx.x);
-}
-// small batches: one warp per source (4 sources per 128-thread CTA)
-template <int D>
-__global__ void __launch_bounds__(NT) k_refine_select_warp(ExtCfg cfg, ExtBuf b, int round) {
-  const int64_t s = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-  if (s >= nsrc(cfg, b)) return;   // warp-uniform
-  refine_select_warp_body<D>(cfg, b, round, s, threadIdx.x & 31);
+// All NITER refinement rounds of G = 32 / nadd sources per warp; the warps of a CTA are independent
+// (no CTA barrier), a CTA is just RF_WPC private slices of dynamic shared memory.
+constexpr int RF_WPC = 2;
+inline size_t refine_warp_bytes(const ExtCfg& c, size_t solver_planes) {
+  const int lps = c.nadd < 32 ? c.nadd : 32, G = 32 / lps;
+  const size_t n = (size_t)G * c.NP * 8 + solver_planes + (size_t)G * c.NP * 2 + (size_t)G * 2 * NADD_MAX * 2;
+  return (n + 15) & ~(size_t)15;
 }
 template <int NL, bool COMP>
-__global__ void __launch_bounds__(NT) k_refine_solve(ExtCfg cfg, ExtBuf b, LensConst L, int round) {
-  __shared__ EASmem<NL * NL + 1, COMP, NT> sm;
-  refine_solve_body<NL, COMP, NT>(cfg, b, L, round, sm, threadIdx.x, (int64_t)blockIdx.x * NT + threadIdx.x);
+__global__ void __launch_bounds__(RF_WPC * 32) k_refine_fused(ExtCfg cfg, ExtBuf b, LensConst L, int warp_bytes) {
+  extern __shared__ __align__(16) unsigned char rf_smem[];
+  typedef EASmem<(NL == 1 ? 2 : NL * NL + 1), COMP, 32> Planes;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lps = cfg.nadd < 32 ? cfg.nadd : 32, G = 32 / lps;
+  unsigned char* base = rf_smem + (size_t)wid * warp_bytes;
+  double* s_dval = (double*)base;
+  Planes* sm = (Planes*)(base + (size_t)G * cfg.NP * 8);
+  uint16_t* s_order = (uint16_t*)(base + (size_t)G * cfg.NP * 8 + sizeof(Planes));
+  uint16_t* s_lr = s_order + (size_t)G * cfg.NP;
+  refine_fused_body<NL, COMP>(cfg, b, L, *sm, s_order, s_dval, s_lr, lane, (int64_t)blockIdx.x * RF_WPC + wid);
 }
-__global__ void __launch_bounds__(NT) k_refine_solve_single(ExtCfg cfg, ExtBuf b, LensConst L, int round) {
-  refine_solve_single_body(cfg, b, L, round, (int64_t)blockIdx.x * NT + threadIdx.x);
+template <int NL, bool COMP>
+int launch_refine(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, cudaStream_t st) {
+  typedef EASmem<(NL == 1 ? 2 : NL * NL + 1), COMP, 32> Planes;
+  const size_t wb = refine_warp_bytes(cfg, sizeof(Planes)), bytes = wb * RF_WPC;
+  if (bytes > 200 * 1024) return CAUSTICS_ERR_BAD_ARG;
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_refine_fused<NL, COMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return cuda_rc(e);
+  }
+  const int lps = cfg.nadd < 32 ? cfg.nadd : 32, G = 32 / lps;
+  const int64_t warps = (cfg.S + G - 1) / G;
+  k_refine_fused<NL, COMP><<<(unsigned)((warps + RF_WPC - 1) / RF_WPC), RF_WPC * 32, bytes, st>>>(cfg, b, L, (int)wb);
+  return CAUSTICS_OK;
 }
 template <int D>
 __global__ void __launch_bounds__(NT) k_tracks(ExtCfg cfg, ExtBuf b) {
   tracks_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+template <int D>
+__global__ void __launch_bounds__(NT) k_sweep(ExtCfg cfg, ExtBuf b) {
+  sweep_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
+}
+// the sources sweep_body listed: open tracks -> segments -> stitched contours, added to the closed-track sum
+template <int D>
+__global__ void __launch_bounds__(NT) k_open(ExtCfg cfg, ExtBuf b, LensConst L) {
+  const int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
+  if (g >= *b.open_count) return;
+  contours_body<D, false>(cfg, b, L, b.open_list[g], nullptr, true);
 }
 template <int D, bool GRAD>
 __global__ void __launch_bounds__(NT) k_contours(ExtCfg cfg, ExtBuf b, LensConst L) {
@@ -119,7 +142,7 @@ __global__ void __launch_bounds__(32) k_contours_staged(ExtCfg cfg, ExtBuf b, Le
   }
   if (b.vth || b.grad)
     for (int pth = threadIdx.x; pth < cfg.NP; pth += 32)
-      th[pth] = b.theta[(int64_t)b.order[(int64_t)pth * cfg.S + s] * cfg.S + s];
+      th[pth] = b.theta[s * cfg.NP + b.order[s * cfg.NP + pth]];
   __syncwarp();
   if (threadIdx.x == 0) {
     const TrackStage st{re, im, f, th};
@@ -196,7 +219,6 @@ template <int NL>
 int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t st) {
   constexpr int D = NL == 1 ? 2 : NL * NL + 1;
   const unsigned gs = (unsigned)((cfg.S + NT - 1) / NT);
-  const unsigned gr = (unsigned)(((int64_t)cfg.nadd * cfg.S + NT - 1) / NT);
   if (NL != 1 && b.list_off == 0)      // the same table serves every window of a gated call
     k_jitter_table<<<(D * cfg.nadd + 127) / 128, 128, 0, st>>>(D, cfg.nadd, const_cast<double*>(b.jit));
   if (NL == 1) k_limb_walk_single<<<gs, NT, 0, st>>>(cfg, b, L);
@@ -205,17 +227,17 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
     const int64_t warps = (cfg.S + G - 1) / G;
     k_limb_walk_group<(NL == 1 ? 2 : NL)><<<(unsigned)((warps + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, L);
   } else k_limb_walk<(NL == 1 ? 2 : NL)><<<gs, NT, 0, st>>>(cfg, b, L);
-  for (int r = 0; r < NITER; ++r) {
-    if (cfg.small & 1) k_refine_select_warp<D><<<(unsigned)((cfg.S + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, r);
-    else k_refine_select<D><<<gs, NT, 0, st>>>(cfg, b, r);
-    if (NL == 1) k_refine_solve_single<<<gr, NT, 0, st>>>(cfg, b, L, r);
-    else if ((cfg.small & 16) && !cfg.comp) {
-      constexpr int G = 32 / (NL == 1 ? 5 : NL * NL + 1);
-      const int64_t warps = ((int64_t)cfg.nadd * cfg.S + G - 1) / G;
-      k_refine_solve_group<(NL == 1 ? 2 : NL)><<<(unsigned)((warps + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, L, r);
-    }
-    else if (cfg.comp) k_refine_solve<(NL == 1 ? 2 : NL), true><<<gr, NT, 0, st>>>(cfg, b, L, r);
-    else k_refine_solve<(NL == 1 ? 2 : NL), false><<<gr, NT, 0, st>>>(cfg, b, L, r);
+  {
+    const int rc = cfg.comp && NL != 1 ? launch_refine<NL, true>(cfg, b, L, st) : launch_refine<NL, false>(cfg, b, L, st);
+    if (rc) return rc;
+  }
+  if (!cfg.ld && !cfg.tracks) {
+    // plain uniform-disk magnification: one pass (matching + closed tracks), then the caustic-crossing sources
+    cudaError_t e = cudaMemsetAsync(b.open_count, 0, 4, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    k_sweep<D><<<gs, NT, 0, st>>>(cfg, b);
+    k_open<D><<<gs, NT, 0, st>>>(cfg, b, L);
+    return cuda_rc(cudaGetLastError());
   }
   k_tracks<D><<<gs, NT, 0, st>>>(cfg, b);
   const size_t stage_bytes = (size_t)cfg.NP * D * 17 + (size_t)cfg.NP * 8 + 64;
@@ -249,7 +271,10 @@ extern "C" {
 
 size_t caustics_ext_workspace_bytes(int64_t n, int nlenses, int npts_limb, int limb_darkening, int npts_ld) {
   ExtCfg c;
-  if (make_cfg(n, 1.0, nlenses, npts_limb, limb_darkening, 0.0, npts_ld, 1, 0, &c)) return 0;
+  if (make_cfg(n, 1.0, nlenses, npts_limb, limb_darkening & 3, 0.0, npts_ld, 1, 0, &c)) return 0;
+  // a uniform-disk workspace serves the tangent and contour-export entry points too (they keep the image
+  // tracks as arrays) unless the caller says it will only ask for magnifications
+  c.tracks = (limb_darkening & CAUSTICS_WS_MAG_ONLY) ? 0 : 1;
   return make_layout(c).total;
 }
 
@@ -298,6 +323,7 @@ int ext_driver(const void* w, double* mag, double* grad, uint8_t* test_out, int6
   if (gate == 2 && (!ext_list || !ext_count)) return CAUSTICS_ERR_BAD_ARG;
   if (n > 0x7fffffffLL) return CAUSTICS_ERR_BAD_ARG;
   const int64_t idx_cap = 0x7fffffffLL / (cfg.VMAX > NADD_MAX ? cfg.VMAX : NADD_MAX);   // index range of one pass
+  cfg.tracks = grad ? 1 : 0;
   int64_t cap = n;
   if (gate) {
     cap = capacity_for(cfg, n, workspace_bytes);
@@ -305,6 +331,7 @@ int ext_driver(const void* w, double* mag, double* grad, uint8_t* test_out, int6
     if (cap < 1) return CAUSTICS_ERR_BAD_ARG;
   } else if (n > idx_cap) return CAUSTICS_ERR_BAD_ARG;
   cfg.S = cap;
+  cfg.tracks = grad ? 1 : 0;
   const Layout lay = make_layout(cfg, gate ? n : -1);
   if (workspace_bytes < lay.total) return CAUSTICS_ERR_BAD_ARG;
   // Phase variants by the number of sources that are integrated.  A binary-lens gate sends a few per
@@ -415,6 +442,7 @@ int caustics_ext_contours(const void* w, double* mag, int64_t n, double rho, con
   if (rc) return rc;
   if (n == 0) return CAUSTICS_OK;
   cfg.small = small_mask(n, lens->nlenses);
+  cfg.tracks = 1;
   if (n > 0x7fffffffLL / cfg.VMAX) return CAUSTICS_ERR_BAD_ARG;
   if (!w || !workspace || !vz || !vtheta || !vcid || !vcount || !cpar || !cstart || !ncont) return CAUSTICS_ERR_BAD_ARG;
   const Layout lay = make_layout(cfg);

@@ -49,6 +49,7 @@ struct ExtCfg {
   int itmax, comp, ld, n1, n2, VMAX, CMAX;
   int ld_adapt;     // opt-in: fewer Gauss-Legendre nodes on short far panels of the P/Q integrals (two_panel)
   int small;        // mask of small-batch phase variants: 1 warp select, 2 staged contours, 4 warp LD sum, 8 lane-per-root walk
+  int tracks;       // 1: the theta-ordered track arrays are materialised (tangent / contour export; always with ld)
   int emit;         // 1: k_contours also writes the contour vertex lists (z, theta, contour id) for the host
   double u1;
   int64_t S;        // capacity (stride) of the source axis
@@ -60,13 +61,20 @@ struct ExtBuf {
   const int32_t* list;     // optional: indices into w of the sources to integrate (else identity)
   const int32_t* count;    // optional: device-side number of listed sources (else S)
   int64_t list_off;        // this pass integrates list[list_off .. list_off + S) (gated calls with a small workspace)
-  double* theta;           // [NP][S]   by arrival slot
-  double* zre; double* zim; uint8_t* flg;   // [NP][D][S] by arrival slot; flg bit0 real, bit1 det>0
-  uint16_t* order;         // [NP][S]   arrival slot of the p-th point in theta order
-  uint16_t* left;          // [NADD][S] warm-start slot of each new point of the current round
-  uint16_t* right;         // [NADD][S] slot of the right end of the interval each new point splits
-  double* dval;            // [NP][S]   by arrival slot: squared width of the interval that STARTS at this slot
-  double* sre; double* sim; uint8_t* sflg;  // [NP][D][S] theta-ordered, rows = image tracks
+  // Limb points by ARRIVAL SLOT, one contiguous record per source (a source's refinement is owned by one
+  // warp, refine_fused_body: its reads and writes are whole 16 D-byte columns):
+  cb200_d2* z;             // [S][NP][D] images of the limb point in arrival slot `slot`
+  uint32_t* fw;            // [S][NP]    3 flag bits per image: bit0 real image, bit1 det J > 0, bit2 det J == 0
+  double* theta;           // [S][NP]    limb angle by arrival slot
+  uint16_t* order;         // [S][NP]    arrival slot of the p-th point in theta order
+  // Theta-ordered image tracks, structure of arrays with the source index fastest (thread-per-source phases):
+  double* sre; double* sim; uint8_t* sflg;  // [NP][D][S], rows = image tracks
+  // One-pass uniform-disk path (sweep_body / open_body):
+  uint64_t* perm;          // [S][NP]    4 bits per track: which image of limb point p (theta order) the track took
+  double* sw_total;        // [S]        signed area of the closed tracks
+  uint32_t* sw_closed;     // [S]        mask of closed tracks
+  int32_t* open_list;      // [S]        sources (slots of this pass) whose open tracks still have to be stitched
+  int32_t* open_count;     //            their number
   cb200_d2* vz; double* vP; double* vQ; uint8_t* vcid; double* vth;   // vth: optional theta per vertex   // [VMAX][S] limb-darkening vertex lists
   int32_t* vcount;         // [S]
   int32_t* ncont;          // [S] number of contours emitted
@@ -85,8 +93,13 @@ __device__ __forceinline__ int64_t nsrc(const ExtCfg& c, const ExtBuf& b) {
 __device__ __forceinline__ int64_t src_index(const ExtBuf& b, int64_t s) {
   return b.list ? (int64_t)b.list[b.list_off + s] : s;
 }
-#define I2(p, s) ((int64_t)(p) * cfg.S + (s))
-#define I3(p, j, s) (((int64_t)(p) * cfg.D + (j)) * cfg.S + (s))
+#define IS(p, s) ((int64_t)(s) * cfg.NP + (p))                          // per-source records by slot / position
+#define IZ(slot, j, s) (((int64_t)(s) * cfg.NP + (slot)) * cfg.D + (j))
+#define IT(p, i, s) (((int64_t)(p) * cfg.D + (i)) * cfg.S + (s))        // tracks
+
+__device__ __forceinline__ uint32_t flag_bits(bool real_image, double detj) {
+  return (real_image ? 1u : 0u) | (detj > 0 ? 2u : 0u) | (detj == 0 ? 4u : 0u);
+}
 
 __device__ __forceinline__ cd source_centre(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s) {
   const cb200_d2 v = b.w[src_index(b, s)];
@@ -111,7 +124,7 @@ __device__ __forceinline__ void single_lens_images(cd w, cd (&z)[2]) {
 }
 
 // Solve the lens polynomial at w (warm start when `warm`: roots already in the shared planes) and
-// write the roots, real-image flags and parity signs to arrival slot `slot`.
+// write the images and their flag word to arrival slot `slot`.
 template <int NL, bool COMP, int NT>
 __device__ __forceinline__ void solve_and_store(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,
                                                 EASmem<NL * NL + 1, COMP, NT>& sm, int tid, bool active,
@@ -139,28 +152,31 @@ __device__ __forceinline__ void solve_and_store(const ExtCfg& cfg, const ExtBuf&
       ea_solve_thread<D, COMP, NT, CB200_EXT_STRAIGHT != 0>(p, sm, tid, bad, false, EA_INIT_REFERENCE, cfg.itmax);
   }
   if (!active) return;
+  cb200_d2* col = b.z + IZ(slot, 0, s);
+  uint32_t fw = 0;
 #pragma unroll
   for (int j = 0; j < D; ++j) {
     const cd z = mk(sm.zre[j][tid], sm.zim[j][tid]);
     bool real_image;
     double detj;
     image_eval<NL>(L, z, w, real_image, detj);
-    b.zre[I3(slot, j, s)] = z.re;
-    b.zim[I3(slot, j, s)] = z.im;
-    b.flg[I3(slot, j, s)] = (real_image ? 1 : 0) | (detj > 0 ? 2 : 0) | (detj == 0 ? 4 : 0);
+    col[j] = make_cb200_d2(z.re, z.im);
+    fw |= flag_bits(real_image, detj) << (3 * j);
   }
+  b.fw[IS(slot, s)] = fw;
 }
 
 __device__ __forceinline__ void store_single(const ExtCfg& cfg, const ExtBuf& b, cd w, int slot, int64_t s) {
   cd z[2];
   single_lens_images(w, z);
+  uint32_t fw = 0;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const double det = 1.0 - 1.0 / (norm2(z[j]) * norm2(z[j]));  // 1 - 1/|zbar^2|^2, point_source.py:1562
-    b.zre[I3(slot, j, s)] = z[j].re;
-    b.zim[I3(slot, j, s)] = z[j].im;
-    b.flg[I3(slot, j, s)] = 1 | (det > 0 ? 2 : 0) | (det == 0 ? 4 : 0);
+    b.z[IZ(slot, j, s)] = make_cb200_d2(z[j].re, z[j].im);
+    fw |= (1u | (det > 0 ? 2u : 0u) | (det == 0 ? 4u : 0u)) << (3 * j);
   }
+  b.fw[IS(slot, s)] = fw;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,10 +189,7 @@ __device__ void limb_walk_body(const ExtCfg& cfg, const ExtBuf& b, const LensCon
     const cd w = limb_point(w0, cfg.rho, th);
     // roots_compensated is not forwarded to the sequential walk (extended_source.py:104-106)
     solve_and_store<NL, false, NT>(cfg, b, L, sm, tid, active, w, k > 0, k, s);
-    if (active) {
-      b.theta[I2(k, s)] = th;
-      b.order[I2(k, s)] = (uint16_t)k;
-    }
+    if (active) b.theta[IS(k, s)] = th;
   }
 }
 
@@ -211,17 +224,21 @@ __device__ void limb_walk_group_body(const ExtCfg& cfg, const ExtBuf& b, const L
       ea_normalise<D>(p);
       ea_solve_group<D>(p, z, lane, valid, cfg.itmax);
     }
+    uint32_t mine = 0;
     if (valid) {
       bool real_image;
       double detj;
       image_eval<NL>(L, z, w, real_image, detj);
-      b.zre[I3(k, r, s)] = z.re;
-      b.zim[I3(k, r, s)] = z.im;
-      b.flg[I3(k, r, s)] = (real_image ? 1 : 0) | (detj > 0 ? 2 : 0) | (detj == 0 ? 4 : 0);
-      if (r == 0) {
-        b.theta[I2(k, s)] = th;
-        b.order[I2(k, s)] = (uint16_t)k;
-      }
+      b.z[IZ(k, r, s)] = make_cb200_d2(z.re, z.im);
+      mine = flag_bits(real_image, detj) << (3 * r);
+    }
+    // the group's flag word: every lane collects the D contributions of its group
+    uint32_t fw = 0;
+#pragma unroll
+    for (int q = 0; q < D; ++q) fw |= __shfl_sync(0xffffffffu, mine, (grp < G ? grp * D : 0) + q);
+    if (valid && r == 0) {
+      b.fw[IS(k, s)] = fw;
+      b.theta[IS(k, s)] = th;
     }
   }
 }
@@ -233,8 +250,7 @@ __device__ void limb_walk_single_body(const ExtCfg& cfg, const ExtBuf& b, const 
   for (int k = 0; k < cfg.N0; ++k) {
     const double th = theta_init(k, cfg.N0);
     store_single(cfg, b, limb_point(w0, cfg.rho, th), k, s);
-    b.theta[I2(k, s)] = th;
-    b.order[I2(k, s)] = (uint16_t)k;
+    b.theta[IS(k, s)] = th;
   }
 }
 
@@ -242,93 +258,61 @@ __device__ void limb_walk_single_body(const ExtCfg& cfg, const ExtBuf& b, const 
 // the tracks where at least one end is a real image (extended_source.py:118-125)
 template <int D>
 __device__ __forceinline__ double interval_width2(const ExtCfg& cfg, const ExtBuf& b, int sa, int sb, int64_t s) {
+  const cb200_d2* ca = b.z + IZ(sa, 0, s);
+  const cb200_d2* cb_ = b.z + IZ(sb, 0, s);
+  const uint32_t f = b.fw[IS(sa, s)] | b.fw[IS(sb, s)];
   double dmax = 0.0;
 #pragma unroll
   for (int j = 0; j < D; ++j) {
-    const double dx = b.zre[I3(sb, j, s)] - b.zre[I3(sa, j, s)], dy = b.zim[I3(sb, j, s)] - b.zim[I3(sa, j, s)];
-    const double d2 = ((b.flg[I3(sa, j, s)] | b.flg[I3(sb, j, s)]) & 1) ? dx * dx + dy * dy : 0.0;
+    const cb200_d2 za = ca[j], zb = cb_[j];
+    const double dx = zb.x - za.x, dy = zb.y - za.y;
+    const double d2 = ((f >> (3 * j)) & 1u) ? dx * dx + dy * dy : 0.0;
     dmax = fmax(dmax, d2);
   }
   return dmax;
 }
-template <int D>
-__device__ __forceinline__ void update_widths(const ExtCfg& cfg, const ExtBuf& b, int r, int slot, int64_t s) {
-  const int lf = b.left[I2(r, s)], rt = b.right[I2(r, s)];
-  b.dval[I2(lf, s)] = interval_width2<D>(cfg, b, lf, slot, s);
-  b.dval[I2(slot, s)] = interval_width2<D>(cfg, b, slot, rt, s);
-}
 
 // ---------------------------------------------------------------------------------------------
-// One refinement round, selection part: rank the intervals of the current theta order by the largest
-// image displacement across them (only tracks where at least one end is a real image), take the
-// nadd widest -- ties to the higher index, like argsort(...)[::-1] -- put a new point at each
-// midpoint and splice the new arrival slots into the order.
-template <int D>
-__device__ void refine_select_body(const ExtCfg& cfg, const ExtBuf& b, int round, int64_t s) {
-  if (s >= nsrc(cfg, b)) return;
-  const int cur = cfg.N0 + round * cfg.nadd, n = cfg.nadd;
+// Refinement (extended_source.py:109-133), NITER rounds: rank the intervals of the current theta order by
+// the largest image displacement across them, take the nadd widest -- ties to the higher index, like
+// argsort(...)[::-1] -- put a new limb point at each midpoint (warm-started from the interval's left end)
+// and splice the new arrival slots into the order.
+//
+// A source's refinement state is small: the order (2 NP bytes) and one width per interval (8 NP bytes,
+// `dval`, indexed by the slot that STARTS the interval; a new point changes exactly two of them).  One warp
+// owns G = 32 / nadd sources for all rounds and keeps that state in shared memory (refine_fused_body): the
+// selection never touches global memory, the solves read and write whole columns of the source's record,
+// and the ten rounds are a loop inside one kernel instead of twenty launches.
+#ifdef CB200_HOSTSIM
+constexpr int EXT_WARP = 1;      // the host logic tests run a "warp" of one lane
+#else
+constexpr int EXT_WARP = 32;
+#endif
+
+// One source's selection, serial (one lane).  order/dval/theta/left/right: this source's arrays.
+__device__ void refine_select_core(int cur, int n, uint16_t* order, const double* dval, double* theta,
+                                   uint16_t* left, uint16_t* right) {
   double val[NADD_MAX];
   int idx[NADD_MAX];
   int cnt = 0;
   val[0] = 0.0;
-  // Interval widths are kept per interval (dval, indexed by the slot that starts it): round 0 measures
-  // all of them, later rounds only read them -- a new point changes exactly two (refine_solve_body).
-  double pre[D], pim[D];
-  uint8_t pf[D];
-  int pslot = b.order[I2(0, s)];
-  if (round == 0) {
-#pragma unroll
-    for (int j = 0; j < D; ++j) { pre[j] = b.zre[I3(pslot, j, s)]; pim[j] = b.zim[I3(pslot, j, s)]; pf[j] = b.flg[I3(pslot, j, s)]; }
-  }
   // descending list; a later interval with an equal value ranks BEFORE earlier ones
-  auto consider = [&](double dmax, int i) {
+  for (int i = 0; i + 1 < cur; ++i) {
+    const double dmax = dval[order[i]];
     if (cnt < n || dmax >= val[cnt - 1]) {
       int pos = cnt < n ? cnt : n - 1;
       while (pos > 0 && val[pos - 1] <= dmax) { val[pos] = val[pos - 1]; idx[pos] = idx[pos - 1]; --pos; }
       val[pos] = dmax; idx[pos] = i;
       if (cnt < n) ++cnt;
     }
-  };
-  if (round == 0) {
-    for (int i = 0; i + 1 < cur; ++i) {
-      double dmax = 0.0;
-      const int slot = b.order[I2(i + 1, s)];
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        const double re = b.zre[I3(slot, j, s)], im = b.zim[I3(slot, j, s)];
-        const uint8_t f = b.flg[I3(slot, j, s)];
-        const double dx = re - pre[j], dy = im - pim[j];
-        const double d2 = ((f | pf[j]) & 1) ? dx * dx + dy * dy : 0.0;
-        dmax = fmax(dmax, d2);
-        pre[j] = re; pim[j] = im; pf[j] = f;
-      }
-      b.dval[I2(pslot, s)] = dmax;
-      pslot = slot;
-      consider(dmax, i);
-    }
-  } else {
-    // the two loads per interval (order -> width) are issued eight intervals at a time, so a small
-    // batch of sources is not serialised on global-memory latency
-    constexpr int BATCH = 8;
-    for (int i0 = 0; i0 + 1 < cur; i0 += BATCH) {
-      int sl[BATCH];
-      double dv[BATCH];
-#pragma unroll
-      for (int k = 0; k < BATCH; ++k) sl[k] = (i0 + k + 1 < cur) ? (int)b.order[I2(i0 + k, s)] : 0;
-#pragma unroll
-      for (int k = 0; k < BATCH; ++k) dv[k] = b.dval[I2(sl[k], s)];
-#pragma unroll
-      for (int k = 0; k < BATCH; ++k)
-        if (i0 + k + 1 < cur) consider(dv[k], i0 + k);
-    }
   }
   // new points: rank r -> arrival slot cur + r; theta at the interval midpoint, warm start from the left end
   for (int r = 0; r < n; ++r) {
     const int i = idx[r];
-    const int sl = b.order[I2(i, s)], sr = b.order[I2(i + 1, s)];
-    b.theta[I2(cur + r, s)] = 0.5 * (b.theta[I2(sl, s)] + b.theta[I2(sr, s)]);
-    b.left[I2(r, s)] = (uint16_t)sl;
-    b.right[I2(r, s)] = (uint16_t)sr;
+    const int sl = order[i], sr = order[i + 1];
+    theta[cur + r] = 0.5 * (theta[sl] + theta[sr]);
+    left[r] = (uint16_t)sl;
+    right[r] = (uint16_t)sr;
   }
   // splice: jnp.insert(x, idcs + 1, new) -- element for interval i lands right after position i.
   // Work from the back so nothing is overwritten before it is moved.  rk[] = ranks sorted by interval.
@@ -339,169 +323,96 @@ __device__ void refine_select_body(const ExtCfg& cfg, const ExtBuf& b, int round
     rk[pos] = r;   // descending by interval index
   }
   int shift = n, q = 0;   // q walks rk[] (largest interval first)
-  constexpr int SB = 8;
-  for (int p0 = cur - 1; p0 >= 0 && shift > 0; p0 -= SB) {
-    uint16_t ov[SB];
-#pragma unroll
-    for (int k = 0; k < SB; ++k) ov[k] = (p0 - k >= 0) ? b.order[I2(p0 - k, s)] : (uint16_t)0;   // loads first
-#pragma unroll
-    for (int k = 0; k < SB; ++k) {
-      const int pth = p0 - k;
-      if (pth < 0 || shift == 0) break;
-      // every selected interval i >= pth has its new element after position i >= pth
-      while (q < n && idx[rk[q]] >= pth) {
-        b.order[I2(idx[rk[q]] + shift, s)] = (uint16_t)(cur + rk[q]);
-        --shift; ++q;
-      }
-      if (shift == 0) break;
-      b.order[I2(pth + shift, s)] = ov[k];
+  for (int pth = cur - 1; pth >= 0 && shift > 0; --pth) {
+    // every selected interval i >= pth has its new element after position i >= pth
+    while (q < n && idx[rk[q]] >= pth) {
+      order[idx[rk[q]] + shift] = (uint16_t)(cur + rk[q]);
+      --shift; ++q;
     }
+    if (shift == 0) break;
+    order[pth + shift] = order[pth];
   }
 }
 
-// The same selection for SMALL batches, one WARP per source: the thread-per-source version above is a
-// chain of ~200 dependent global loads per round, which is latency-bound when there are only a few
-// hundred sources (a light curve's full-integration points).  Here the lanes share the intervals, the
-// top-n is n rounds of a warp arg-max with the same ordering (value descending, ties to the higher
-// interval index), and the splice is one parallel scatter.
-#ifdef CB200_HOSTSIM
-constexpr int SEL_LANES = 1;
-constexpr int SEL_PER_LANE = 4000;            // the host logic test runs the "warp" with one lane
-#else
-constexpr int SEL_LANES = 32;
-constexpr int SEL_PER_LANE = 4000 / 32 + 1;   // NP <= 4000
-#endif
-
-template <int D>
-__device__ void refine_select_warp_body(const ExtCfg& cfg, const ExtBuf& b, int round, int64_t s, int lane) {
-  const int cur = cfg.N0 + round * cfg.nadd, n = cfg.nadd;
-  const int nint = cur - 1;
-  // widths of this lane's intervals i = lane, lane + 32, ...
-  double myv[SEL_PER_LANE];
-  int cntl = 0;
-  for (int i = lane; i < nint; i += SEL_LANES, ++cntl) {
-    const int sa = b.order[I2(i, s)];
-    double d;
-    if (round == 0) {
-      d = interval_width2<D>(cfg, b, sa, b.order[I2(i + 1, s)], s);
-      b.dval[I2(sa, s)] = d;
-    } else {
-      d = b.dval[I2(sa, s)];
-    }
-    myv[cntl] = d;
-  }
-  // n rounds of arg-max over (value, interval index), lexicographic, descending
-  int sel[NADD_MAX];
-  for (int r = 0; r < n; ++r) {
-    double bv = -1.0; int bi = -1;
-    for (int k = 0, i = lane; k < cntl; ++k, i += SEL_LANES)
-      if (myv[k] > bv || (myv[k] == bv && i > bi)) { bv = myv[k]; bi = i; }
-#ifndef CB200_HOSTSIM
+// warm start of new point r of a round: the left neighbour's images plus the reference's jitters
+// (extended_source.py:83-85), into the lane's shared root planes
+template <int D, bool COMP, int NT>
+__device__ __forceinline__ void warm_start_from(const ExtCfg& cfg, const ExtBuf& b, EASmem<D, COMP, NT>& sm, int tid,
+                                                int lf, int r, int64_t s) {
+  const cb200_d2* col = b.z + IZ(lf, 0, s);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
-    }
-#endif
-    sel[r] = bi;
-    if (bi >= 0 && (bi % SEL_LANES) == lane) myv[bi / SEL_LANES] = -2.0;   // taken
-  }
-  // new points (rank r -> arrival slot cur + r): lanes share the ranks
-  for (int r = lane; r < n; r += SEL_LANES) {
-    const int i = sel[r];
-    const int sl = b.order[I2(i, s)], sr = b.order[I2(i + 1, s)];
-    b.theta[I2(cur + r, s)] = 0.5 * (b.theta[I2(sl, s)] + b.theta[I2(sr, s)]);
-    b.left[I2(r, s)] = (uint16_t)sl;
-    b.right[I2(r, s)] = (uint16_t)sr;
-  }
-  // splice: the element at position p moves to p + #(selected intervals < p); the new element of
-  // interval i lands at i + 1 + #(selected < i).  Read everything first, then scatter.
-  uint16_t mine[SEL_PER_LANE];
-  int np = 0;
-  for (int pth = lane; pth < cur; pth += SEL_LANES, ++np) mine[np] = b.order[I2(pth, s)];
-  __syncwarp();
-  np = 0;
-  for (int pth = lane; pth < cur; pth += SEL_LANES, ++np) {
-    int c = 0;
-    for (int r = 0; r < n; ++r) c += sel[r] < pth ? 1 : 0;
-    if (c) b.order[I2(pth + c, s)] = mine[np];
-  }
-  for (int r = lane; r < n; r += SEL_LANES) {
-    int c = 0;
-    for (int q = 0; q < n; ++q) c += sel[q] < sel[r] ? 1 : 0;
-    b.order[I2(sel[r] + 1 + c, s)] = (uint16_t)(cur + r);
-  }
-}
-
-template <int NL, bool COMP, int NT>
-__device__ void refine_solve_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int round, EASmem<NL * NL + 1, COMP, NT>& sm, int tid, int64_t g) {
-  constexpr int D = NL * NL + 1;
-  const int64_t ns = nsrc(cfg, b);
-  // consecutive threads = consecutive sources of the same new point (coalesced)
-  const int r = (int)(g / cfg.S);
-  const int64_t s = g - (int64_t)r * cfg.S;
-  const bool active = r < cfg.nadd && s < ns;
-  const int slot = cfg.N0 + round * cfg.nadd + r;
-  cd w = mk(0.3, 0.2);
-  if (active) {
-    const cd w0 = source_centre(cfg, b, L, s);
-    w = limb_point(w0, cfg.rho, b.theta[I2(slot, s)]);
-    const int lf = b.left[I2(r, s)];
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-      const double* jt = b.jit + 2 * (j * cfg.nadd + r);  // extended_source.py:83-85
-      sm.zre[j][tid] = b.zre[I3(lf, j, s)] + jt[0];
-      sm.zim[j][tid] = b.zim[I3(lf, j, s)] + jt[1];
-    }
-  }
-  solve_and_store<NL, COMP, NT>(cfg, b, L, sm, tid, active, w, true, slot, s);
-  if (active) update_widths<D>(cfg, b, r, slot, s);
-}
-
-// Small batches, lane-per-root (see limb_walk_group_body): a warp solves G = 32 / D new limb points,
-// lane g*D + j follows image track j of new point g from its left neighbour's root (plain mode).
-#ifndef CB200_HOSTSIM
-template <int NL>
-__device__ void refine_solve_group_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int round, int tid, int64_t warp_id) {
-  constexpr int D = NL * NL + 1, G = 32 / D;
-  const int lane = tid & 31, grp = lane / D, j = lane - grp * D;
-  const int64_t g = warp_id * G + grp;            // (new point, source) pair, sources fastest
-  const int r = (int)(g / cfg.S);
-  const int64_t s = g - (int64_t)r * cfg.S;
-  const bool valid = grp < G && r < cfg.nadd && s < nsrc(cfg, b);
-  const int slot = cfg.N0 + round * cfg.nadd + r;
-  cd w = mk(0.3, 0.2), z = mk(0.05 + 0.1 * lane, 0.07 * lane);
-  if (valid) {
-    w = limb_point(source_centre(cfg, b, L, s), cfg.rho, b.theta[I2(slot, s)]);
-    const int lf = b.left[I2(r, s)];
+  for (int j = 0; j < D; ++j) {
     const double* jt = b.jit + 2 * (j * cfg.nadd + r);
-    z = mk(b.zre[I3(lf, j, s)] + jt[0], b.zim[I3(lf, j, s)] + jt[1]);
+    const cb200_d2 v = col[j];
+    sm.zre[j][tid] = v.x + jt[0];
+    sm.zim[j][tid] = v.y + jt[1];
   }
-  cd p[D + 1];
-  lens_poly<NL>(L, w, p);
-  ea_normalise<D>(p);
-  ea_solve_group<D>(p, z, lane, valid, cfg.itmax);
-  if (valid) {
-    bool real_image;
-    double detj;
-    image_eval<NL>(L, z, w, real_image, detj);
-    b.zre[I3(slot, j, s)] = z.re;
-    b.zim[I3(slot, j, s)] = z.im;
-    b.flg[I3(slot, j, s)] = (real_image ? 1 : 0) | (detj > 0 ? 2 : 0) | (detj == 0 ? 4 : 0);
+}
+
+// The fused refinement of the sources of one warp.  Shared memory per warp (carved by the kernel):
+//   s_order[G][NP] uint16, s_dval[G][NP] double, s_lr[G][2][NADD_MAX] uint16, and the solver planes.
+// Lane g * LPS + q works for source g of the warp (LPS = min(nadd, warp) lanes per source); new point r of a
+// round is solved by lane q = r mod LPS.
+template <int NL, bool COMP>
+__device__ void refine_fused_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,
+                                  EASmem<(NL == 1 ? 2 : NL * NL + 1), COMP, EXT_WARP>& sm, uint16_t* s_order,
+                                  double* s_dval, uint16_t* s_lr, int lane, int64_t warp_id) {
+  constexpr int D = NL == 1 ? 2 : NL * NL + 1;
+  const int NP = cfg.NP, n = cfg.nadd;
+  const int LPS = n < EXT_WARP ? n : EXT_WARP, G = EXT_WARP / LPS;
+  const int64_t ns = nsrc(cfg, b);
+  const int64_t s_first = warp_id * G;
+  if (s_first >= ns) return;   // warp-uniform
+  // ---- prologue: identity order, widths of the N0 - 1 initial intervals (lanes share the intervals)
+  for (int g = 0; g < G; ++g) {
+    const int64_t s = s_first + g;
+    if (s >= ns) break;
+    for (int i = lane; i < NP; i += EXT_WARP) {
+      s_order[g * NP + i] = (uint16_t)i;
+      s_dval[g * NP + i] = i + 1 < cfg.N0 ? interval_width2<D>(cfg, b, i, i + 1, s) : 0.0;
+    }
   }
   __syncwarp();
-  if (valid && j == 0) update_widths<D>(cfg, b, r, slot, s);
-}
-#endif
-
-__device__ void refine_solve_single_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int round, int64_t g) {
-  const int r = (int)(g / cfg.S);
-  const int64_t s = g - (int64_t)r * cfg.S;
-  if (r >= cfg.nadd || s >= nsrc(cfg, b)) return;
-  const int slot = cfg.N0 + round * cfg.nadd + r;
-  store_single(cfg, b, limb_point(source_centre(cfg, b, L, s), cfg.rho, b.theta[I2(slot, s)]), slot, s);
-  update_widths<2>(cfg, b, r, slot, s);
+  const int g = lane / LPS, q = lane - g * LPS;
+  const int64_t s = s_first + g;
+  const bool valid = g < G && s < ns;
+  uint16_t* ord = s_order + (valid ? g : 0) * NP;
+  double* dv = s_dval + (valid ? g : 0) * NP;
+  uint16_t* lft = s_lr + (valid ? g : 0) * 2 * NADD_MAX;
+  uint16_t* rgt = lft + NADD_MAX;
+  const cd w0 = valid ? source_centre(cfg, b, L, s) : mk(0.3, 0.2);
+  for (int round = 0; round < NITER; ++round) {
+    const int cur = cfg.N0 + round * n;
+    if (valid && q == 0) refine_select_core(cur, n, ord, dv, b.theta + IS(0, s), lft, rgt);
+    __syncwarp();
+    for (int r0 = 0; r0 < n; r0 += LPS) {   // one pass unless nadd > warp size
+      const int r = r0 + q;
+      const bool active = valid && r < n;
+      const int slot = cur + (active ? r : 0);
+      const int lf = active ? lft[r] : 0, rt = active ? rgt[r] : 0;
+      if constexpr (NL == 1) {
+        if (active) store_single(cfg, b, limb_point(w0, cfg.rho, b.theta[IS(slot, s)]), slot, s);
+      } else {
+        cd w = mk(0.3, 0.2);
+        if (active) {
+          w = limb_point(w0, cfg.rho, b.theta[IS(slot, s)]);
+          warm_start_from<D, COMP, EXT_WARP>(cfg, b, sm, lane, lf, r, s);
+        }
+        solve_and_store<NL, COMP, EXT_WARP>(cfg, b, L, sm, lane, active, w, true, slot, s);
+      }
+      if (active) {
+        dv[lf] = interval_width2<D>(cfg, b, lf, slot, s);
+        dv[slot] = interval_width2<D>(cfg, b, slot, rt, s);
+      }
+    }
+    __syncwarp();
+  }
+  // ---- epilogue: the final theta order goes to the source's record
+  for (int gg = 0; gg < G; ++gg) {
+    const int64_t sg = s_first + gg;
+    if (sg >= ns) break;
+    for (int i = lane; i < NP; i += EXT_WARP) b.order[IS(i, sg)] = s_order[gg * NP + i];
+  }
 }
 
 // The (deg, nadd) jitter table is the same for every source and every round: one tiny launch fills it
@@ -520,28 +431,32 @@ __device__ __noinline__ double duplicate_jitter_cold(int j, int p, int deg, int 
 // ---------------------------------------------------------------------------------------------
 // theta order + duplicate guard + greedy nearest-neighbour track matching (utils.py:15-40): for each
 // track i in order, the nearest not-yet-taken root of the next limb point (ties: lowest index).
+// TrackWalk visits the limb points of one source in theta order; step(p) hands out limb point p's images
+// in TRACK order together with the permutation (4 bits per track: which image of the column it took).
 template <int D>
-__device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
-  if (s >= nsrc(cfg, b)) return;
-  double cre[D], cim[D];   // carry: previous column in track order
-  // the raw column of the NEXT limb point is fetched while the current one is matched
-  double nzr[D], nzi[D];
-  uint8_t nf[D];
-  {
-    const int slot0 = b.order[I2(0, s)];
+struct TrackWalk {
+  const ExtCfg& cfg; const ExtBuf& b; const int64_t s;
+  double cre[D], cim[D];                  // previous column in track order
+  double nzr[D], nzi[D]; uint32_t nfw;    // raw column of the NEXT limb point, fetched while the current one is matched
+  int nslot, slot;
+  __device__ __forceinline__ void fetch(int p) {
+    nslot = b.order[IS(p, s)];
+    const cb200_d2* col = b.z + IZ(nslot, 0, s);
+    nfw = b.fw[IS(nslot, s)];
 #pragma unroll
-    for (int j = 0; j < D; ++j) { nzr[j] = b.zre[I3(slot0, j, s)]; nzi[j] = b.zim[I3(slot0, j, s)]; nf[j] = b.flg[I3(slot0, j, s)]; }
+    for (int j = 0; j < D; ++j) { const cb200_d2 v = col[j]; nzr[j] = v.x; nzi[j] = v.y; }
   }
-  for (int p = 0; p < cfg.NP; ++p) {
+  __device__ __forceinline__ TrackWalk(const ExtCfg& c, const ExtBuf& bb, int64_t ss) : cfg(c), b(bb), s(ss) { fetch(0); }
+  // WRITE_BACK: a duplicate's offset is also stored into the source's record, so that later random access
+  // through the permutation (Tracks, perm mode) sees the value the matching saw
+  template <bool WRITE_BACK>
+  __device__ __forceinline__ uint64_t step(int p, double (&vr)[D], double (&vi)[D], uint8_t (&vf)[D]) {
     double zr[D], zi[D];
-    uint8_t f[D];
+    const uint32_t fw = nfw;
+    slot = nslot;
 #pragma unroll
-    for (int j = 0; j < D; ++j) { zr[j] = nzr[j]; zi[j] = nzi[j]; f[j] = nf[j]; }
-    if (p + 1 < cfg.NP) {
-      const int slotn = b.order[I2(p + 1, s)];
-#pragma unroll
-      for (int j = 0; j < D; ++j) { nzr[j] = b.zre[I3(slotn, j, s)]; nzi[j] = b.zim[I3(slotn, j, s)]; nf[j] = b.flg[I3(slotn, j, s)]; }
-    }
+    for (int j = 0; j < D; ++j) { zr[j] = nzr[j]; zi[j] = nzi[j]; }
+    if (p + 1 < cfg.NP) fetch(p + 1);
     // exact duplicates (inside the column, or an unchanged warm start) get a tiny real offset
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -551,10 +466,13 @@ __device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
         if (k < j && zr[k] == zr[j] && zi[k] == zi[j]) dup = true;
         if (p > 0 && cre[k] == zr[j] && cim[k] == zi[j]) dup = true;
       }
-      if (dup) zr[j] += duplicate_jitter_cold(j, p, D, cfg.NP);   // extended_source.py:144-148
+      if (dup) {
+        zr[j] += duplicate_jitter_cold(j, p, D, cfg.NP);   // extended_source.py:144-148
+        if (WRITE_BACK) b.z[IZ(slot, j, s)].x = zr[j];
+      }
     }
     unsigned used = 0;
-    double nre[D], nim[D];
+    uint64_t perm = 0;
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       int best = i;
@@ -573,16 +491,100 @@ __device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
         }
       }
       used |= 1u << best;
-      double vr = 0, vi = 0; uint8_t vf = 0;
+      perm |= (uint64_t)best << (4 * i);
+      double r = 0, m = 0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) if (k == best) { vr = zr[k]; vi = zi[k]; vf = f[k]; }
-      nre[i] = vr; nim[i] = vi;
-      b.sre[I3(p, i, s)] = vr;
-      b.sim[I3(p, i, s)] = vi;
-      b.sflg[I3(p, i, s)] = vf;
+      for (int k = 0; k < D; ++k) if (k == best) { r = zr[k]; m = zi[k]; }
+      vr[i] = r; vi[i] = m;
+      vf[i] = (uint8_t)((fw >> (3 * best)) & 7u);
     }
+    return perm;
+  }
+  __device__ __forceinline__ void advance(const double (&vr)[D], const double (&vi)[D]) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) { cre[i] = nre[i]; cim[i] = nim[i]; }
+    for (int i = 0; i < D; ++i) { cre[i] = vr[i]; cim[i] = vi[i]; }
+  }
+};
+
+// the theta-ordered tracks as arrays (consumed by contours_body; limb-darkened, tangent and export calls)
+template <int D>
+__device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
+  if (s >= nsrc(cfg, b)) return;
+  TrackWalk<D> W(cfg, b, s);
+  for (int p = 0; p < cfg.NP; ++p) {
+    double vr[D], vi[D];
+    uint8_t vf[D];
+    W.template step<false>(p, vr, vi, vf);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      b.sre[IT(p, i, s)] = vr[i];
+      b.sim[IT(p, i, s)] = vi[i];
+      b.sflg[IT(p, i, s)] = vf[i];
+    }
+    W.advance(vr, vi);
+  }
+}
+
+// Uniform disk, large batches: ONE pass over the source's record does the track matching AND integrates
+// every closed track while its vertices go by (the trapezoid sum of integrate.py:23-27 only ever needs
+// the previous vertex, which is the matching's carry).  Nothing but the 8-byte permutation per limb point
+// is written.  A source whose limb crosses a caustic -- some track holds real images but is not closed --
+// is appended to `open_list`; open_body splits, stitches and integrates its open tracks by random access
+// through the permutation and adds them to the closed-track sum saved here.  Sums are formed in the order
+// contours_body forms them (per track in theta order, closed tracks in track order, then the stitched
+// contours), so the two paths agree bit for bit.
+template <int D>
+__device__ void sweep_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
+  if (s >= nsrc(cfg, b)) return;
+  constexpr unsigned FULL = (1u << D) - 1u;
+  const int NP = cfg.NP;
+  TrackWalk<D> W(cfg, b, s);
+  double fre[D], fim[D], sum[D];
+  unsigned all_real = FULL, any_real = 0, f0 = 0;
+  uint64_t* perm = b.perm + IS(0, s);
+  {
+    double vr[D], vi[D];
+    uint8_t vf[D];
+    perm[0] = W.template step<true>(0, vr, vi, vf);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      fre[i] = vr[i]; fim[i] = vi[i]; sum[i] = 0.0;
+      f0 |= (unsigned)vf[i] << (3 * i);
+      if (vf[i] & 1) any_real |= 1u << i; else all_real &= ~(1u << i);
+    }
+    W.advance(vr, vi);
+  }
+  for (int p = 1; p < NP; ++p) {
+    double vr[D], vi[D];
+    uint8_t vf[D];
+    perm[p] = W.template step<true>(p, vr, vi, vf);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      sum[i] += 0.5 * (W.cre[i] * vi[i] - vr[i] * W.cim[i]);
+      if (vf[i] & 1) any_real |= 1u << i; else all_real &= ~(1u << i);
+    }
+    W.advance(vr, vi);
+  }
+  unsigned closed = 0;
+  double total = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const double dx = fre[i] - W.cre[i], dy = fim[i] - W.cim[i];
+    const bool cl = cfg.nl == 1 || (((all_real >> i) & 1u) && dx * dx + dy * dy < 1e-10);
+    if (cl) {
+      closed |= 1u << i;
+      const unsigned f = (f0 >> (3 * i)) & 7u;
+      const double par = (f & 4) ? 0.0 : ((f & 2) ? 1.0 : -1.0);
+      const double S = sum[i] + 0.5 * (W.cre[i] * fim[i] - fre[i] * W.cim[i]);
+      total += par * S;
+    }
+  }
+  if (any_real & ~closed) {
+    b.sw_total[s] = total;
+    b.sw_closed[s] = closed;
+    b.open_list[cb200_atomic_inc(b.open_count)] = (int32_t)s;
+  } else {
+    b.mag[src_index(b, s)] = fabs(total) * (1.0 / (3.14159265358979323846 * cfg.rho * cfg.rho));
   }
 }
 
@@ -597,17 +599,23 @@ struct TrackStage { const double* re; const double* im; const uint8_t* f; const 
 
 struct Tracks {
   const ExtCfg& cfg; const ExtBuf& b; int64_t s; const TrackStage* st;
+  const uint64_t* perm;    // non-null: no track arrays, read the source's record through order and permutation
   __device__ __forceinline__ cd pt(int track, int p) const {
     if (st) return mk(st->re[p * cfg.D + track], st->im[p * cfg.D + track]);
+    if (perm) {
+      const cb200_d2 v = b.z[IZ(b.order[IS(p, s)], (int)((perm[p] >> (4 * track)) & 15u), s)];
+      return mk(v.x, v.y);
+    }
     return mk(b.sre[(((int64_t)p * cfg.D + track) * cfg.S + s)], b.sim[(((int64_t)p * cfg.D + track) * cfg.S + s)]);
   }
   __device__ __forceinline__ double th(int p) const {
     if (!b.vth && !b.grad) return 0.0;
     if (st) return st->th[p];
-    return b.theta[(int64_t)b.order[(int64_t)p * cfg.S + s] * cfg.S + s];
+    return b.theta[(int64_t)s * cfg.NP + b.order[(int64_t)s * cfg.NP + p]];
   }
   __device__ __forceinline__ uint8_t fl(int track, int p) const {
     if (st) return st->f[p * cfg.D + track];
+    if (perm) return (uint8_t)((b.fw[IS(b.order[IS(p, s)], s)] >> (3 * (int)((perm[p] >> (4 * track)) & 15u))) & 7u);
     return b.sflg[(((int64_t)p * cfg.D + track) * cfg.S + s)];
   }
 };
@@ -788,9 +796,11 @@ struct LdEmit {
   }
 };
 
+// `resume`: the closed tracks were integrated by sweep_body (their mask and sum are in sw_closed / sw_total);
+// only the open tracks are left, read through the permutation.
 template <int D, bool GRAD = false>
 __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s,
-                              const TrackStage* stage = nullptr) {
+                              const TrackStage* stage = nullptr, bool resume = false) {
   if (s >= nsrc(cfg, b)) return;
   constexpr int NLG = D == 2 ? 1 : (D == 5 ? 2 : 3);
   GreenTangent<NLG> GT(L, cfg.rho);
@@ -799,7 +809,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
 #pragma unroll
     for (int k = 0; k < NGRAD; ++k) dtot[k] = 0.0;
   }
-  const Tracks T{cfg, b, s, stage};
+  const Tracks T{cfg, b, s, stage, resume ? b.perm + IS(0, s) : nullptr};
   const int NP = cfg.NP;
   const double norm = 1.0 / (3.14159265358979323846 * cfg.rho * cfg.rho);
   const int64_t out_idx = src_index(b, s);
@@ -810,7 +820,8 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
 
   // closed tracks: every image real and the track returns to its start (extended_source.py:290)
   unsigned closed = 0;
-  for (int i = 0; i < D; ++i) {
+  if (resume) { closed = b.sw_closed[s]; total = b.sw_total[s]; }
+  for (int i = 0; i < D && !resume; ++i) {
     bool all_real = true;
 #pragma unroll 8
     for (int p = 0; p < NP; ++p) all_real = all_real && (T.fl(i, p) & 1);

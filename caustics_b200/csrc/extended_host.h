@@ -50,7 +50,7 @@ inline int fill_gl_tables(int n1, int n2, double* tab) {
 }
 
 struct Layout {
-  size_t theta, zre, zim, flg, order, left, right, dval, sre, sim, sflg, vz, vP, vQ, vcid, vcount, ncont, cz0, cpar, cstart, gl, jit, list, count, total;
+  size_t theta, z, fw, order, sre, sim, sflg, perm, sw_total, sw_closed, open_list, open_count, vz, vP, vQ, vcid, vcount, ncont, cz0, cpar, cstart, gl, jit, list, count, total;
 };
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -62,9 +62,17 @@ inline Layout make_layout(const ExtCfg& c, int64_t npoints = -1) {
   const size_t NL = npoints > (int64_t)S ? (size_t)npoints : S;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
   l.theta = take(NP * S * 8);
-  l.zre = take(NP * D * S * 8); l.zim = take(NP * D * S * 8); l.flg = take(NP * D * S);
-  l.order = take(NP * S * 2); l.left = take((size_t)NADD_MAX * S * 2); l.right = take((size_t)NADD_MAX * S * 2); l.dval = take(NP * S * 8);
-  l.sre = take(NP * D * S * 8); l.sim = take(NP * D * S * 8); l.sflg = take(NP * D * S);
+  l.z = take(NP * D * S * 16); l.fw = take(NP * S * 4);
+  l.order = take(NP * S * 2);
+  // the theta-ordered track arrays are needed by limb-darkened, tangent and export calls only; the plain
+  // uniform-disk call integrates in one pass (sweep_body) and keeps 8 bytes per limb point instead
+  if (c.ld || c.tracks) {
+    l.sre = take(NP * D * S * 8); l.sim = take(NP * D * S * 8); l.sflg = take(NP * D * S);
+    l.perm = l.sw_total = l.sw_closed = l.open_list = l.open_count = 0;
+  } else {
+    l.sre = l.sim = l.sflg = 0;
+    l.perm = take(NP * S * 8); l.sw_total = take(S * 8); l.sw_closed = take(S * 4); l.open_list = take(S * 4); l.open_count = take(256);
+  }
   if (c.ld) {
     l.vz = take((size_t)c.VMAX * S * 16); l.vP = take((size_t)c.VMAX * S * 8); l.vQ = take((size_t)c.VMAX * S * 8);
     l.vcid = take((size_t)c.VMAX * S); l.vcount = take(S * 4); l.ncont = take(S * 4);
@@ -87,7 +95,7 @@ inline int make_cfg(int64_t S, double rho, int nlenses, int npts_limb, int limb_
   c.NP = c.N0 + NITER * c.nadd;
   if (c.N0 < 4 || c.nadd < 1 || c.nadd > NADD_MAX || c.NP > 4000) return CAUSTICS_ERR_BAD_ARG;
   c.rho = rho; c.itmax = itmax; c.comp = compensated ? 1 : 0;
-  c.ld = limb_darkening ? 1 : 0; c.u1 = u1;
+  c.ld = (limb_darkening & 3) ? 1 : 0; c.u1 = u1;
   c.ld_adapt = (limb_darkening & 2) ? 1 : 0;
   c.n1 = npts_ld / 2; c.n2 = npts_ld - c.n1;
   if (c.ld && (c.n1 < 1 || npts_ld > 2048)) return CAUSTICS_ERR_BAD_ARG;
@@ -102,9 +110,14 @@ inline ExtBuf bind(const ExtCfg& c, const Layout& l, void* ws) {
   char* base = (char*)ws;
   ExtBuf b; memset(&b, 0, sizeof(b));
   b.theta = (double*)(base + l.theta);
-  b.zre = (double*)(base + l.zre); b.zim = (double*)(base + l.zim); b.flg = (uint8_t*)(base + l.flg);
-  b.order = (uint16_t*)(base + l.order); b.left = (uint16_t*)(base + l.left); b.right = (uint16_t*)(base + l.right); b.dval = (double*)(base + l.dval);
-  b.sre = (double*)(base + l.sre); b.sim = (double*)(base + l.sim); b.sflg = (uint8_t*)(base + l.sflg);
+  b.z = (cb200_d2*)(base + l.z); b.fw = (uint32_t*)(base + l.fw);
+  b.order = (uint16_t*)(base + l.order);
+  if (c.ld || c.tracks) {
+    b.sre = (double*)(base + l.sre); b.sim = (double*)(base + l.sim); b.sflg = (uint8_t*)(base + l.sflg);
+  } else {
+    b.perm = (uint64_t*)(base + l.perm); b.sw_total = (double*)(base + l.sw_total); b.sw_closed = (uint32_t*)(base + l.sw_closed);
+    b.open_list = (int32_t*)(base + l.open_list); b.open_count = (int32_t*)(base + l.open_count);
+  }
   if (c.ld) {
     b.vz = (cb200_d2*)(base + l.vz); b.vP = (double*)(base + l.vP); b.vQ = (double*)(base + l.vQ);
     b.vcid = (uint8_t*)(base + l.vcid); b.vcount = (int32_t*)(base + l.vcount); b.ncont = (int32_t*)(base + l.ncont);

@@ -36,8 +36,11 @@ def _to_device(w):
     return flat, lambda m: m.cpu().numpy().reshape(shape)
 
 
-def _chunk_len(L, n, nlenses, npts_limb, ld, npts_ld, budget=None):
-    ld = int(bool(ld))
+_WS_MAG_ONLY = 4   # CAUSTICS_WS_MAG_ONLY: a uniform-disk workspace for magnifications alone (no track arrays)
+
+
+def _chunk_len(L, n, nlenses, npts_limb, ld, npts_ld, budget=None, mag_only=False):
+    ld = int(bool(ld)) or (_WS_MAG_ONLY if mag_only else 0)
     per1 = L.caustics_ext_workspace_bytes(1, nlenses, npts_limb, ld, npts_ld)
     if per1 == 0:
         raise ValueError("unsupported extended-source configuration "
@@ -76,7 +79,7 @@ def _run(w, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax, r
                                            cnt.data_ptr(), n, rho, lens, float(q), cfg[4], comp, st))
             nfull = int(cnt.item())
             if nfull:
-                chunk = _chunk_len(L, nfull, nlenses, npts_limb, limb_darkening, npts_ld, _MAX_GATED_WS_BYTES)
+                chunk = _chunk_len(L, nfull, nlenses, npts_limb, limb_darkening, npts_ld, _MAX_GATED_WS_BYTES, mag_only=True)
                 nbytes = L.caustics_mag_workspace_bytes(nfull, chunk, nlenses, cfg[0], ld, cfg[3])
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
                 _lib.check(L.caustics_mag_extended_source_list(flat.data_ptr(), mag.data_ptr(), lst.data_ptr(),
@@ -85,14 +88,14 @@ def _run(w, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax, r
         elif gate:
             # one stream-ordered call (CUDA-graph capturable; triple lens: every point is integrated):
             # the survivor count stays on the device, the workspace holds `chunk` sources at a time
-            chunk = _chunk_len(L, n, nlenses, npts_limb, limb_darkening, npts_ld)
+            chunk = _chunk_len(L, n, nlenses, npts_limb, limb_darkening, npts_ld, mag_only=True)
             nbytes = L.caustics_mag_workspace_bytes(n, chunk, nlenses, cfg[0], ld, cfg[3])
             ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
             _lib.check(L.caustics_mag(flat.data_ptr(), mag.data_ptr(), test.data_ptr(), n, rho, lens, float(q),
                                       *cfg, ws.data_ptr(), nbytes, st))
         else:
-            chunk = _chunk_len(L, n, nlenses, npts_limb, limb_darkening, npts_ld)
-            nbytes = L.caustics_ext_workspace_bytes(chunk, nlenses, cfg[0], ld, cfg[3])
+            chunk = _chunk_len(L, n, nlenses, npts_limb, limb_darkening, npts_ld, mag_only=True)
+            nbytes = L.caustics_ext_workspace_bytes(chunk, nlenses, cfg[0], ld or _WS_MAG_ONLY, cfg[3])
             ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
             for off in range(0, n, chunk):
                 m = min(chunk, n - off)

@@ -214,6 +214,10 @@ int caustics_mag_point_source_grid_host(double x0, double y0, double dx, double 
  * keeps its nodes).  Opt-in: it moves results by up to 7e-5, so the default stays the
  * reference's rule. */
 #define CAUSTICS_LD_ADAPTIVE 2
+/* caustics_ext_workspace_bytes only, OR-ed into limb_darkening = 0: the workspace will serve
+ * caustics_mag_extended_source alone (not the tangent / contour-export entry points, which keep the image
+ * tracks as arrays): about half the bytes per source. */
+#define CAUSTICS_WS_MAG_ONLY 4
 size_t caustics_ext_workspace_bytes(int64_t n, int nlenses, int npts_limb, int limb_darkening, int npts_ld);
 /* workspace of a GATED call (caustics_mag, caustics_mag_extended_source_list) over n points that
  * integrates at most max_full sources at a time: per-source arrays for max_full sources + the compact

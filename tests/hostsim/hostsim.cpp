@@ -141,16 +141,23 @@ static void ext_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, int64_
   for (int64_t s = 0; s < ns; ++s) {
     if (NL == 1) limb_walk_single_body(cfg, b, L, s); else limb_walk_body<NLS, 1>(cfg, b, L, sm0, 0, s);
   }
-  for (int r = 0; r < NITER; ++r) {
+  {
+    // the fused refinement with a one-lane "warp": one source per warp, the new points of a round in turn
+    std::vector<uint16_t> ord(cfg.NP), lr(2 * NADD_MAX);
+    std::vector<double> dv(cfg.NP);
+    static EASmem<D, false, 1> rf0;
+    static EASmem<D, true, 1> rf1;
     for (int64_t s = 0; s < ns; ++s) {
-      if (s & 1) refine_select_warp_body<D>(cfg, b, r, s, 0);   // odd sources: the small-batch variant (same result)
-      else refine_select_body<D>(cfg, b, r, s);
+      if (cfg.comp && NL != 1) refine_fused_body<NL, true>(cfg, b, L, rf1, ord.data(), dv.data(), lr.data(), 0, s);
+      else refine_fused_body<NL, false>(cfg, b, L, rf0, ord.data(), dv.data(), lr.data(), 0, s);
     }
-    for (int64_t g = 0; g < (int64_t)cfg.nadd * cfg.S; ++g) {
-      if (NL == 1) refine_solve_single_body(cfg, b, L, r, g);
-      else if (cfg.comp) refine_solve_body<NLS, true, 1>(cfg, b, L, r, sm1, 0, g);
-      else refine_solve_body<NLS, false, 1>(cfg, b, L, r, sm0, 0, g);
-    }
+  }
+  if (!cfg.ld && !cfg.tracks) {
+    // plain uniform disk: one pass, then the listed caustic-crossing sources
+    *b.open_count = 0;
+    for (int64_t s = 0; s < ns; ++s) sweep_body<D>(cfg, b, s);
+    for (int32_t g = 0; g < *b.open_count; ++g) contours_body<D, false>(cfg, b, L, b.open_list[g], nullptr, true);
+    return;
   }
   for (int64_t s = 0; s < ns; ++s) tracks_body<D>(cfg, b, s);
   for (int64_t s = 0; s < ns; ++s) {
@@ -166,6 +173,9 @@ static void ext_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, int64_
 // optional: where the next hostsim_mag_extended call writes d mag / d(a, e1, e2, Re r3, Im r3, Re w, Im w, rho), (8, n)
 static double* g_hostsim_grad = nullptr;
 extern "C" void hostsim_set_grad(double* out) { g_hostsim_grad = out; }
+// 1: uniform-disk calls also take the track-array path (tracks_body + contours_body) instead of sweep_body / open pass
+static int g_hostsim_force_tracks = 0;
+extern "C" void hostsim_force_tracks(int on) { g_hostsim_force_tracks = on; }
 
 extern "C" int hostsim_mag_extended(const double* w, double* mag, uint8_t* test_out, int64_t n, double rho, int nlenses,
                                     const double* eps, const double* r, const double* H, const double* G, double x_cm,
@@ -174,6 +184,7 @@ extern "C" int hostsim_mag_extended(const double* w, double* mag, uint8_t* test_
   ExtCfg cfg;
   int rc = make_cfg(n, rho, nlenses, npts_limb, ld, u1, npts_ld, itmax, comp, &cfg);
   if (rc) return rc;
+  cfg.tracks = (tracks_out || g_hostsim_grad || g_hostsim_force_tracks) ? 1 : 0;
   Layout lay = make_layout(cfg);
   std::vector<char> ws(lay.total + 256, 0);
   LensConst L;

@@ -117,7 +117,7 @@ def test_round2_entry_points_without_compute(built_lib):
     small = L.caustics_mag_workspace_bytes(1_000_000, 60_000, 2, 200, 1, 100)
     one = L.caustics_mag_workspace_bytes(1_000_000, 1, 2, 200, 1, 100)
     assert one < small < full and small < 4 << 30 and one >= 4_000_000
-    assert L.caustics_mag_workspace_bytes(1000, 5000, 2, 200, 0, 100) == L.caustics_ext_workspace_bytes(1000, 2, 200, 0, 100)
+    assert L.caustics_mag_workspace_bytes(1000, 5000, 2, 200, 0, 100) == L.caustics_ext_workspace_bytes(1000, 2, 200, 4, 100)   # 4 = CAUSTICS_WS_MAG_ONLY
     assert L.caustics_mag_workspace_bytes(1000, 10, 7, 200, 0, 100) == 0          # bad nlenses
     # peer buffers
     p = ctypes.c_void_p()

@@ -210,7 +210,13 @@ def test_fused_tangent_kernel_vs_python_rule(cb):
         kern = run(lambda w, rho, t: es._mag_uniform_kernel_grad(w, rho, nl, 200, 2500, False, t))
         spec = run(lambda w, rho, t: es._mag_from_contours(es._get_contours(w, rho, nl, 200, 2500, False, t),
                                                            w.reshape(-1), rho, nl, t))
-        assert torch.allclose(kern[0], spec[0], rtol=1e-10, atol=0)       # (another summation order)
+        # the specification re-polishes every vertex by one Newton step (z0 - J^-1 F(z0)): F(z0) is the solver's
+        # residual, not 0, and near a caustic J^-1 is large, so the two magnifications differ at the level of the
+        # roots' own accuracy -- the forward value of the tangent kernel IS the plain kernel's, asserted below
+        dev = ((kern[0] - spec[0]).abs() / spec[0].abs()).max().item()
+        assert dev < 1e-8, (nl, dev)
+        plain = es._run(torch.from_numpy(w_np).cuda(), 1e-2, nl, 200, False, 0.0, 100, 2500, False, False, 0.0, hp)
+        assert torch.allclose(kern[0], plain.reshape(-1), rtol=1e-13, atol=0), nl
         assert torch.allclose(kern[1], spec[1], rtol=1e-8, atol=1e-9 * spec[1].abs().max().item())
         assert abs(kern[2].item() - spec[2].item()) <= 1e-8 * abs(spec[2].item())
         for k in hp:

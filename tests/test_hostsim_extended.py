@@ -302,3 +302,19 @@ def test_adaptive_limb_darkening_quadrature(hs, g):
         ada = hs_ext(hs, w, rho, nl, hp, ld=3, u1=u1)
         assert np.abs(ada / ref - 1).max() < 1e-4 and not np.array_equal(ada, ref)
     assert np.abs(hs_ext(hs, g["b_w_0.01"][:16], 1e-2, 2, HP2, ld=1, u1=0.7) / g["b_ld_0.01"] - 1).max() < 1e-9
+
+
+def test_one_pass_path_equals_track_array_path(hs, g):
+    """The plain uniform-disk call integrates closed tracks while it matches them (sweep_body) and stitches the
+    open ones through the permutation (contours_body, resume); limb-darkened / tangent / export calls
+    materialise the track arrays (tracks_body + contours_body).  Same sums in the same order: bit-identical."""
+    hs.hostsim_force_tracks.argtypes = [ctypes.c_int]
+    for nl, hp, w in ((2, HP2, g["b_w_0.01"][:24]), (3, HP3, g["t_w_0.01"][:10]), (1, {}, g["s_w_0.1"] + 1e-9)):
+        rho = 0.1 if nl == 1 else 1e-2
+        one = hs_ext(hs, w, rho, nl, hp)
+        hs.hostsim_force_tracks(1)
+        try:
+            two = hs_ext(hs, w, rho, nl, hp)
+        finally:
+            hs.hostsim_force_tracks(0)
+        assert np.array_equal(one, two), nl
