@@ -36,21 +36,29 @@ using namespace cb200;
 namespace {
 
 constexpr int NT = 128;
-// Phase-variant mask: 1 warp-per-source selection, 2 stitching on a shared-memory copy of the tracks,
-// 4 warp-per-source limb-darkened sum, 8 lane-per-root limb walk, 16 lane-per-root refinement solves.
-// The batch-size rules below were measured on one B200 (npts_limb = 200): warp-per-source selection wins
-// up to ~32 Ki sources, staged stitching and the lane-per-root walk up to ~16 Ki (binary) / ~8 Ki (triple),
-// the lane-per-root refinement up to ~2048 / ~128.
+// resident CTAs per SM the register allocation aims at (measured, profiles/r02_ext_variants.txt): the
+// one-pass track kernel is fastest with all 255 registers (2 CTAs), the refinement with 168 (6 CTAs of 2 warps;
+// 128 registers and 7-8 CTAs: 8.97 / 9.15 ms against 8.75 on C4)
+#ifndef SW_MINB
+#define SW_MINB 2
+#endif
+#ifndef RF_MINB
+#define RF_MINB 6
+#endif
+// Phase-variant mask (caustics_set_tuning("ext_variants", mask) overrides the rules; tests, experiments):
+//    2  stitching on a shared-memory copy of the tracks, one warp per source (track-array path)
+//    4  warp-per-source limb-darkened sum
+//    8  lane-per-root limb walk (k_limb_walk_group)
+//   32  thread-per-source open-track pass instead of the staged one
+// (1 and 16 belonged to earlier pipelines -- a selection kernel per round; a thread-per-source kernel that
+// walked AND refined, measured at 16.5-18 ms against 5.6 + 8.8 ms for k_limb_walk + k_refine_fused -- ignored.)
 // `n` is the number of sources that are integrated (a gated call passes its estimate).
-// caustics_set_tuning("ext_variants", mask) overrides the rules (tests, experiments).
 inline int small_mask(int64_t n, int nlenses) {
   const int k = tuning_get(TUNE_EXT_VARIANTS);
-  if (k >= 0) return k & 31;
-  // measured on one B200 at npts_limb = 200 (profiles/r02_variant_sweep.jsonl, batches of 3 000 ... 100 000)
+  if (k >= 0) return k & 63;
+  // measured on one B200 at npts_limb = 200 (batches of 3 000 ... 100 000)
   int m = 0;
-  if (n <= 32768) m |= 1;
   if (n <= (nlenses == 2 ? 16384 : 8192)) m |= 6 | 8;
-  if (n <= (nlenses == 2 ? 2048 : 128)) m |= 16;
   return m;
 }
 
@@ -79,7 +87,7 @@ inline size_t refine_warp_bytes(const ExtCfg& c, size_t solver_planes) {
   return (n + 15) & ~(size_t)15;
 }
 template <int NL, bool COMP>
-__global__ void __launch_bounds__(RF_WPC * 32) k_refine_fused(ExtCfg cfg, ExtBuf b, LensConst L, int warp_bytes) {
+__global__ void __launch_bounds__(RF_WPC * 32, RF_MINB) k_refine_fused(ExtCfg cfg, ExtBuf b, LensConst L, int warp_bytes) {
   extern __shared__ __align__(16) unsigned char rf_smem[];
   typedef EASmem<(NL == 1 ? 2 : NL * NL + 1), COMP, 32> Planes;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(NT) k_tracks(ExtCfg cfg, ExtBuf b) {
   tracks_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
 template <int D>
-__global__ void __launch_bounds__(NT) k_sweep(ExtCfg cfg, ExtBuf b) {
+__global__ void __launch_bounds__(NT, SW_MINB) k_sweep(ExtCfg cfg, ExtBuf b) {
   sweep_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
 // the sources sweep_body listed: open tracks -> segments -> stitched contours, added to the closed-track sum
@@ -119,6 +127,50 @@ __global__ void __launch_bounds__(NT) k_open(ExtCfg cfg, ExtBuf b, LensConst L) 
   const int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
   if (g >= *b.open_count) return;
   contours_body<D, false>(cfg, b, L, b.open_list[g], nullptr, true);
+}
+// The same with one warp per listed source, persistent over the list: the lanes gather the source's tracks
+// (through order and permutation; a lane takes a limb point and issues its D image loads together) into
+// shared memory, lane i splits track i into segments, lane 0 stitches and integrates on the copy.  The
+// listed sources are few (the limb crosses a caustic) and their processing is a chain of dependent reads:
+// from shared memory, and spread over every SM instead of count / 128 CTAs.
+inline size_t open_stage_bytes(int NP, int D) {
+  return (size_t)NP * D * 17 + (size_t)(D * MAXPARTS + MAXSEG) * sizeof(Seg) + 64 + 64;
+}
+template <int D>
+__global__ void __launch_bounds__(32) k_open_staged(ExtCfg cfg, ExtBuf b, LensConst L) {
+  extern __shared__ __align__(16) double stage_mem[];
+  const int lane = threadIdx.x, n = cfg.NP * D;
+  double* re = stage_mem;
+  double* im = re + n;
+  Seg* tp = (Seg*)(im + n);
+  Seg* parts = tp + D * MAXPARTS;
+  int* tn = (int*)(parts + MAXSEG);
+  uint8_t* f = (uint8_t*)(tn + 16);
+  const int count = *b.open_count;
+  for (int g = blockIdx.x; g < count; g += gridDim.x) {
+    const int64_t s = b.open_list[g];
+    const uint64_t* perm = b.perm + s * cfg.NP;
+    for (int pth = lane; pth < cfg.NP; pth += 32) {
+      const int slot = b.order[s * cfg.NP + pth];
+      const uint64_t pm = perm[pth];
+      const uint32_t fw = b.fw[s * cfg.NP + slot];
+      const double2* col = b.z + (s * cfg.NP + slot) * D;
+      double2 v[D];
+#pragma unroll
+      for (int t = 0; t < D; ++t) v[t] = col[(int)((pm >> (4 * t)) & 15u)];
+#pragma unroll
+      for (int t = 0; t < D; ++t) {
+        re[pth * D + t] = v[t].x; im[pth * D + t] = v[t].y;
+        f[pth * D + t] = (uint8_t)((fw >> (3 * (int)((pm >> (4 * t)) & 15u))) & 7u);
+      }
+    }
+    __syncwarp();
+    const TrackStage st{re, im, f, nullptr};
+    const Tracks T{cfg, b, s, &st, nullptr};
+    const int np = build_parts_warp<D>(cfg, T, b.sw_closed[s], tp, tn, parts, lane);
+    if (lane == 0) contours_body<D, false>(cfg, b, L, s, &st, true, parts, np);
+    __syncwarp();
+  }
 }
 template <int D, bool GRAD>
 __global__ void __launch_bounds__(NT) k_contours(ExtCfg cfg, ExtBuf b, LensConst L) {
@@ -236,7 +288,15 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
     cudaError_t e = cudaMemsetAsync(b.open_count, 0, 4, st);
     if (e != cudaSuccess) return cuda_rc(e);
     k_sweep<D><<<gs, NT, 0, st>>>(cfg, b);
-    k_open<D><<<gs, NT, 0, st>>>(cfg, b, L);
+    const size_t open_bytes = open_stage_bytes(cfg.NP, D);
+    if (open_bytes <= 200 * 1024 && !(cfg.small & 32)) {
+      if (open_bytes > 48 * 1024) cudaFuncSetAttribute(k_open_staged<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)open_bytes);
+      const int64_t per_sm = (int64_t)(220 * 1024 / (open_bytes + 1024));
+      const int64_t slots = 148 * (per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm));
+      k_open_staged<D><<<(unsigned)(cfg.S < slots ? cfg.S : slots), 32, open_bytes, st>>>(cfg, b, L);
+    } else {
+      k_open<D><<<gs, NT, 0, st>>>(cfg, b, L);
+    }
     return cuda_rc(cudaGetLastError());
   }
   k_tracks<D><<<gs, NT, 0, st>>>(cfg, b);

@@ -126,35 +126,39 @@ __device__ __forceinline__ void single_lens_images(cd w, cd (&z)[2]) {
 // Solve the lens polynomial at w (warm start when `warm`: roots already in the shared planes) and
 // write the images and their flag word to arrival slot `slot`.
 template <int NL, bool COMP, int NT>
-__device__ __forceinline__ void solve_and_store(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,
+__device__ __forceinline__ uint32_t solve_and_store(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,
                                                 EASmem<NL * NL + 1, COMP, NT>& sm, int tid, bool active,
                                                 cd w, bool warm, int slot, int64_t s) {
   constexpr int D = NL * NL + 1;
   cd p[D + 1];
   lens_poly<NL>(L, w, p);
   ea_normalise<D>(p);
-  ea_solve_thread<D, COMP, NT, CB200_EXT_STRAIGHT != 0>(p, sm, tid, active, warm, EA_INIT_REFERENCE, cfg.itmax);
-  if (warm) {
-    // Coinciding warm-start values make an Aberth term 0 * inf = NaN, and a NaN root passes the stopping
-    // test (|h| > eps b is false): the image would silently vanish.  Redo such a solve from the default
-    // initial estimates, as the point-source walks do (ps_walk.cuh).  Warp-uniform branch.
+  // Coinciding warm-start values make an Aberth term 0 * inf = NaN, and a NaN root passes the stopping
+  // test (|h| > eps b is false): the image would silently vanish.  Such a solve is redone from the default
+  // initial estimates, as the point-source walks do (ps_walk.cuh).  One copy of the solver in the code (the
+  // kernels that walk a limb are bound by instruction fetch, not by arithmetic): the redo is a second trip
+  // through the same loop, taken on a warp vote.
+  bool todo = active;
+#pragma unroll 1
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ea_solve_thread<D, COMP, NT, CB200_EXT_STRAIGHT != 0>(p, sm, tid, todo, warm && attempt == 0, EA_INIT_REFERENCE, cfg.itmax);
+    if (!warm || attempt == 1) break;
     double chk = 0.0;
     if (active) {
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < D; ++j) chk += fabs(sm.zre[j][tid]) + fabs(sm.zim[j][tid]);
     }
-    const bool bad = active && !(chk < 1e300);
+    todo = active && !(chk < 1e300);
 #ifndef CB200_HOSTSIM
-    if (__any_sync(0xffffffffu, bad))
+    if (!__any_sync(0xffffffffu, todo)) break;
 #else
-    if (bad)
+    if (!todo) break;
 #endif
-      ea_solve_thread<D, COMP, NT, CB200_EXT_STRAIGHT != 0>(p, sm, tid, bad, false, EA_INIT_REFERENCE, cfg.itmax);
   }
-  if (!active) return;
+  if (!active) return 0u;
   cb200_d2* col = b.z + IZ(slot, 0, s);
   uint32_t fw = 0;
-#pragma unroll
+#pragma unroll 2
   for (int j = 0; j < D; ++j) {
     const cd z = mk(sm.zre[j][tid], sm.zim[j][tid]);
     bool real_image;
@@ -164,6 +168,7 @@ __device__ __forceinline__ void solve_and_store(const ExtCfg& cfg, const ExtBuf&
     fw |= flag_bits(real_image, detj) << (3 * j);
   }
   b.fw[IS(slot, s)] = fw;
+  return fw;
 }
 
 __device__ __forceinline__ void store_single(const ExtCfg& cfg, const ExtBuf& b, cd w, int slot, int64_t s) {
@@ -272,66 +277,147 @@ __device__ __forceinline__ double interval_width2(const ExtCfg& cfg, const ExtBu
   return dmax;
 }
 
+// the same for the limb point just solved (images in the lane's shared root planes, flag word fw) against the
+// stored limb points in slots sa and sb: both widths in one pass, the 2 D image loads issued together
+template <int D, bool COMP, int NT>
+__device__ __forceinline__ void interval_widths2_planes(const ExtCfg& cfg, const ExtBuf& b, const EASmem<D, COMP, NT>& sm,
+                                                        int tid, uint32_t fw, int sa, int sb, int64_t s, double& wa, double& wb) {
+  const cb200_d2* ca = b.z + IZ(sa, 0, s);
+  const cb200_d2* cb_ = b.z + IZ(sb, 0, s);
+  const uint32_t fa = fw | b.fw[IS(sa, s)], fb = fw | b.fw[IS(sb, s)];
+  double ma = 0.0, mb = 0.0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const cb200_d2 za = ca[j], zb = cb_[j];
+    const double x = sm.zre[j][tid], y = sm.zim[j][tid];
+    const double ax = x - za.x, ay = y - za.y, bx = zb.x - x, by = zb.y - y;
+    ma = fmax(ma, ((fa >> (3 * j)) & 1u) ? ax * ax + ay * ay : 0.0);
+    mb = fmax(mb, ((fb >> (3 * j)) & 1u) ? bx * bx + by * by : 0.0);
+  }
+  wa = ma; wb = mb;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Refinement (extended_source.py:109-133), NITER rounds: rank the intervals of the current theta order by
 // the largest image displacement across them, take the nadd widest -- ties to the higher index, like
 // argsort(...)[::-1] -- put a new limb point at each midpoint (warm-started from the interval's left end)
-// and splice the new arrival slots into the order.
+// and insert the new arrival slots into the theta order.
 //
-// A source's refinement state is small: the order (2 NP bytes) and one width per interval (8 NP bytes,
-// `dval`, indexed by the slot that STARTS the interval; a new point changes exactly two of them).  One warp
-// owns G = 32 / nadd sources for all rounds and keeps that state in shared memory (refine_fused_body): the
-// selection never touches global memory, the solves read and write whole columns of the source's record,
-// and the ten rounds are a loop inside one kernel instead of twenty launches.
+// A source's refinement state is small: the theta order (2 NP bytes of links) and one width per interval
+// (8 NP bytes, `dval`, indexed by the slot that STARTS the interval; a new point changes exactly two of them).
+// One warp owns G = 32 / nadd sources for all rounds and keeps that state in shared memory
+// (refine_fused_body): the selection never touches global memory, the solves read and write whole columns of
+// the source's record, and the ten rounds are a loop inside one kernel instead of twenty launches.
 #ifdef CB200_HOSTSIM
 constexpr int EXT_WARP = 1;      // the host logic tests run a "warp" of one lane
 #else
 constexpr int EXT_WARP = 32;
 #endif
 
-// One source's selection, serial (one lane).  order/dval/theta/left/right: this source's arrays.
-__device__ void refine_select_core(int cur, int n, uint16_t* order, const double* dval, double* theta,
-                                   uint16_t* left, uint16_t* right) {
-  double val[NADD_MAX];
-  int idx[NADD_MAX];
-  int cnt = 0;
-  val[0] = 0.0;
-  // descending list; a later interval with an equal value ranks BEFORE earlier ones
-  for (int i = 0; i + 1 < cur; ++i) {
-    const double dmax = dval[order[i]];
-    if (cnt < n || dmax >= val[cnt - 1]) {
-      int pos = cnt < n ? cnt : n - 1;
-      while (pos > 0 && val[pos - 1] <= dmax) { val[pos] = val[pos - 1]; idx[pos] = idx[pos - 1]; --pos; }
-      val[pos] = dmax; idx[pos] = i;
-      if (cnt < n) ++cnt;
+#ifdef CB200_HOSTSIM
+__device__ __forceinline__ unsigned cb200_warp_max(unsigned v) { return v; }
+#else
+__device__ __forceinline__ unsigned cb200_warp_max(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+#endif
+
+// Selection.  The state is indexed by ARRIVAL SLOT and is independent of the theta order: dval[slot] is the
+// squared width of the interval that starts at `slot`, next[slot] the slot that follows it in theta order (a
+// singly linked list; the last point, slot N0 - 1 at theta = pi - 1e-8, starts no interval).  The reference
+// ranks the intervals by width with argsort(...)[::-1], i.e. descending, equal widths by DESCENDING position
+// -- and position order is theta order -- so the scan runs over the slots as they lie in memory and breaks
+// ties by theta.  A new point is linked in between its interval's ends: no splice, nothing is shifted.
+//
+// All lanes of a warp select for ONE source.  Each lane holds its share of the widths (slots lane, lane + 32,
+// ...) in registers for the round; pass r = every lane's best, a warp arg-max, and the winner drops the entry it contributed.  Widths are
+// non-negative doubles, whose order is the order of their bit patterns: the arg-max is two 32-bit
+// redux.sync (high words, then low words among the lanes that tie on the high word) and a ballot.  Equal
+// widths (rare) are ranked by theta.  Beyond 32 * SEL_REG limb points: n passes over shared memory, a butterfly
+// arg-max per pass (this is also what a one-lane host "warp" runs).
+constexpr int SEL_REG = 8;         // widths per lane held in registers: cur <= 32 * SEL_REG, else the generic passes
+__device__ __forceinline__ void refine_select_warp(int cur, int n, int N0, uint16_t* next, const double* dval, double* theta,
+                                                   uint16_t* left, uint16_t* right, int lane) {
+  if (cur <= EXT_WARP * SEL_REG) {
+    double dv[SEL_REG];
+#pragma unroll
+    for (int k = 0; k < SEL_REG; ++k) {
+      const int i = lane + k * EXT_WARP;
+      dv[k] = (i < cur && i != N0 - 1) ? dval[i] : -1.0;
+    }
+    for (int r = 0; r < n; ++r) {
+      double bd = dv[0];
+      int bk = 0;
+#pragma unroll
+      for (int k = 1; k < SEL_REG; ++k) {
+        bool better = dv[k] > bd;
+        if (dv[k] == bd && bd >= 0.0) better = theta[lane + k * EXT_WARP] > theta[lane + bk * EXT_WARP];
+        if (better) { bd = dv[k]; bk = k; }
+      }
+      const int mine = lane + bk * EXT_WARP;
+      // bit patterns of widths >= 0 order like the widths; 0 = "no entry left"
+      const unsigned hi = bd >= 0.0 ? (unsigned)__double2hiint(bd) + 1u : 0u;
+      const unsigned mh = cb200_warp_max(hi);
+      const unsigned lo = hi == mh ? (unsigned)__double2loint(bd) : 0u;
+      const unsigned ml = cb200_warp_max(lo);
+      bool win = hi == mh && lo == ml;
+      unsigned winners = __ballot_sync(0xffffffffu, win);
+      if (winners & (winners - 1u)) {          // several lanes hold this width: the one latest in theta
+        double th = win ? theta[mine] : -1e300;
+        double mth = th;
+#pragma unroll
+        for (int off = EXT_WARP / 2; off > 0; off >>= 1) mth = fmax(mth, __shfl_xor_sync(0xffffffffu, mth, off));
+        win = win && th == mth;
+        winners = __ballot_sync(0xffffffffu, win);
+      }
+      const int wl = __ffs(winners) - 1;
+      const int pick = __shfl_sync(0xffffffffu, mine, wl);
+      if (lane == 0) left[r] = (uint16_t)pick;
+      if (lane == wl) {
+#pragma unroll
+        for (int k = 0; k < SEL_REG; ++k) if (k == bk) dv[k] = -1.0;
+      }
+    }
+  } else {
+    double pd = 1e300;
+    int pi = -1;                       // the previous pass's pick (width, slot)
+    for (int r = 0; r < n; ++r) {
+      double bd = -1.0;
+      int bi = 0;
+      for (int i = lane; i < cur; i += EXT_WARP) {
+        const double d = dval[i];
+        bool take = d < pd && d > bd && i != N0 - 1;
+        if (((d == pd && i != pi) || d == bd) && i != N0 - 1) {
+          const double th = theta[i];
+          take = (d < pd || (d == pd && th < theta[pi])) && (d > bd || (d == bd && th > theta[bi]));
+        }
+        if (take) { bd = d; bi = i; }
+      }
+#pragma unroll
+      for (int off = EXT_WARP / 2; off > 0; off >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        // lanes without a candidate hold -1; equal widths (rare) by theta, so that both partners keep the same one
+        if (od > bd || (od == bd && od >= 0.0 && oi != bi && theta[oi] > theta[bi])) { bd = od; bi = oi; }
+      }
+      if (lane == 0) left[r] = (uint16_t)bi;
+      pd = bd; pi = bi;
     }
   }
+  __syncwarp();
   // new points: rank r -> arrival slot cur + r; theta at the interval midpoint, warm start from the left end
-  for (int r = 0; r < n; ++r) {
-    const int i = idx[r];
-    const int sl = order[i], sr = order[i + 1];
+  // (the selected intervals are distinct, so the lanes link their points in independently)
+  for (int r = lane; r < n; r += EXT_WARP) {
+    const int sl = left[r], sr = next[sl];
     theta[cur + r] = 0.5 * (theta[sl] + theta[sr]);
-    left[r] = (uint16_t)sl;
     right[r] = (uint16_t)sr;
+    next[cur + r] = (uint16_t)sr;
+    next[sl] = (uint16_t)(cur + r);
   }
-  // splice: jnp.insert(x, idcs + 1, new) -- element for interval i lands right after position i.
-  // Work from the back so nothing is overwritten before it is moved.  rk[] = ranks sorted by interval.
-  int rk[NADD_MAX];
-  for (int r = 0; r < n; ++r) {
-    int pos = r;
-    while (pos > 0 && idx[rk[pos - 1]] < idx[r]) { rk[pos] = rk[pos - 1]; --pos; }
-    rk[pos] = r;   // descending by interval index
-  }
-  int shift = n, q = 0;   // q walks rk[] (largest interval first)
-  for (int pth = cur - 1; pth >= 0 && shift > 0; --pth) {
-    // every selected interval i >= pth has its new element after position i >= pth
-    while (q < n && idx[rk[q]] >= pth) {
-      order[idx[rk[q]] + shift] = (uint16_t)(cur + rk[q]);
-      --shift; ++q;
-    }
-    if (shift == 0) break;
-    order[pth + shift] = order[pth];
-  }
+  __syncwarp();
+}
+// the theta order as an array (arrival slot of the p-th point), from the linked list
+__device__ __forceinline__ void order_from_links(int NP, const uint16_t* next, uint16_t* order) {
+  int slot = 0;   // theta = -pi is the first limb point of the walk
+  for (int p = 0; p < NP; ++p) { order[p] = (uint16_t)slot; slot = next[slot]; }
 }
 
 // warm start of new point r of a round: the left neighbour's images plus the reference's jitters
@@ -350,7 +436,8 @@ __device__ __forceinline__ void warm_start_from(const ExtCfg& cfg, const ExtBuf&
 }
 
 // The fused refinement of the sources of one warp.  Shared memory per warp (carved by the kernel):
-//   s_order[G][NP] uint16, s_dval[G][NP] double, s_lr[G][2][NADD_MAX] uint16, and the solver planes.
+//   s_order[G][NP] uint16 (the theta-order links, see refine_select_warp), s_dval[G][NP] double,
+//   s_lr[G][2][NADD_MAX] uint16, and the solver planes.
 // Lane g * LPS + q works for source g of the warp (LPS = min(nadd, warp) lanes per source); new point r of a
 // round is solved by lane q = r mod LPS.
 template <int NL, bool COMP>
@@ -368,7 +455,7 @@ __device__ void refine_fused_body(const ExtCfg& cfg, const ExtBuf& b, const Lens
     const int64_t s = s_first + g;
     if (s >= ns) break;
     for (int i = lane; i < NP; i += EXT_WARP) {
-      s_order[g * NP + i] = (uint16_t)i;
+      s_order[g * NP + i] = (uint16_t)(i + 1 < cfg.N0 ? i + 1 : 0);
       s_dval[g * NP + i] = i + 1 < cfg.N0 ? interval_width2<D>(cfg, b, i, i + 1, s) : 0.0;
     }
   }
@@ -383,8 +470,11 @@ __device__ void refine_fused_body(const ExtCfg& cfg, const ExtBuf& b, const Lens
   const cd w0 = valid ? source_centre(cfg, b, L, s) : mk(0.3, 0.2);
   for (int round = 0; round < NITER; ++round) {
     const int cur = cfg.N0 + round * n;
-    if (valid && q == 0) refine_select_core(cur, n, ord, dv, b.theta + IS(0, s), lft, rgt);
-    __syncwarp();
+    for (int gg = 0; gg < G; ++gg) {          // the warp's sources in turn, all lanes on each selection
+      if (s_first + gg >= ns) break;
+      refine_select_warp(cur, n, cfg.N0, s_order + gg * NP, s_dval + gg * NP, b.theta + IS(0, s_first + gg),
+                         s_lr + gg * 2 * NADD_MAX, s_lr + gg * 2 * NADD_MAX + NADD_MAX, lane);
+    }
     for (int r0 = 0; r0 < n; r0 += LPS) {   // one pass unless nadd > warp size
       const int r = r0 + q;
       const bool active = valid && r < n;
@@ -398,9 +488,10 @@ __device__ void refine_fused_body(const ExtCfg& cfg, const ExtBuf& b, const Lens
           w = limb_point(w0, cfg.rho, b.theta[IS(slot, s)]);
           warm_start_from<D, COMP, EXT_WARP>(cfg, b, sm, lane, lf, r, s);
         }
-        solve_and_store<NL, COMP, EXT_WARP>(cfg, b, L, sm, lane, active, w, true, slot, s);
+        const uint32_t fw = solve_and_store<NL, COMP, EXT_WARP>(cfg, b, L, sm, lane, active, w, true, slot, s);
+        if (active) interval_widths2_planes<D, COMP, EXT_WARP>(cfg, b, sm, lane, fw, lf, rt, s, dv[lf], dv[slot]);
       }
-      if (active) {
+      if (NL == 1 && active) {
         dv[lf] = interval_width2<D>(cfg, b, lf, slot, s);
         dv[slot] = interval_width2<D>(cfg, b, slot, rt, s);
       }
@@ -408,11 +499,7 @@ __device__ void refine_fused_body(const ExtCfg& cfg, const ExtBuf& b, const Lens
     __syncwarp();
   }
   // ---- epilogue: the final theta order goes to the source's record
-  for (int gg = 0; gg < G; ++gg) {
-    const int64_t sg = s_first + gg;
-    if (sg >= ns) break;
-    for (int i = lane; i < NP; i += EXT_WARP) b.order[IS(i, sg)] = s_order[gg * NP + i];
-  }
+  if (valid && q == 0) order_from_links(NP, ord, b.order + IS(0, s));
 }
 
 // The (deg, nadd) jitter table is the same for every source and every round: one tiny launch fills it
@@ -539,7 +626,7 @@ __device__ void sweep_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
   constexpr unsigned FULL = (1u << D) - 1u;
   const int NP = cfg.NP;
   TrackWalk<D> W(cfg, b, s);
-  double fre[D], fim[D], sum[D];
+  double sum[D];
   unsigned all_real = FULL, any_real = 0, f0 = 0;
   uint64_t* perm = b.perm + IS(0, s);
   {
@@ -548,7 +635,7 @@ __device__ void sweep_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
     perm[0] = W.template step<true>(0, vr, vi, vf);
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      fre[i] = vr[i]; fim[i] = vi[i]; sum[i] = 0.0;
+      sum[i] = 0.0;
       f0 |= (unsigned)vf[i] << (3 * i);
       if (vf[i] & 1) any_real |= 1u << i; else all_real &= ~(1u << i);
     }
@@ -567,15 +654,19 @@ __device__ void sweep_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
   }
   unsigned closed = 0;
   double total = 0.0;
+  // the first limb point again (track i = image i of that column; a duplicate's offset was written back)
+  const cb200_d2* col0 = b.z + IZ(b.order[IS(0, s)], 0, s);
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    const double dx = fre[i] - W.cre[i], dy = fim[i] - W.cim[i];
+    const cb200_d2 first = col0[i];
+    const double fre_i = first.x, fim_i = first.y;
+    const double dx = fre_i - W.cre[i], dy = fim_i - W.cim[i];
     const bool cl = cfg.nl == 1 || (((all_real >> i) & 1u) && dx * dx + dy * dy < 1e-10);
     if (cl) {
       closed |= 1u << i;
       const unsigned f = (f0 >> (3 * i)) & 7u;
       const double par = (f & 4) ? 0.0 : ((f & 2) ? 1.0 : -1.0);
-      const double S = sum[i] + 0.5 * (W.cre[i] * fim[i] - fre[i] * W.cim[i]);
+      const double S = sum[i] + 0.5 * (W.cre[i] * fim_i - fre_i * W.cim[i]);
       total += par * S;
     }
   }
@@ -796,11 +887,105 @@ struct LdEmit {
   }
 };
 
+// Split the open tracks of one source into segments: runs of real images of one parity without jumps > 0.1
+// (extended_source.py:156-250).  track_parts scans ONE track and returns its (start, end) pairs in
+// increasing order (the first MAXPARTS starts and ends are kept, :202-203); part_segment turns a pair into
+// a segment, or returns false for the reference's "empty" marker and for runs of fewer than two points (:232).
+__device__ int track_parts(const ExtCfg& cfg, const Tracks& T, int i, int16_t* lo, int16_t* hi) {
+  const int NP = cfg.NP;
+  int np_ = 0, nend = 0;
+  bool prev_real = false; double prev_par = 0.0; cd prev_z = mk(0, 0);
+#pragma unroll 4
+  for (int p = 0; p <= NP; ++p) {
+    bool real = false; double par = 0.0; cd z = mk(0, 0);
+    {
+      // unconditional loads (clamped index) so that unrolled iterations overlap their latency
+      const int pc = p < NP ? p : NP - 1;
+      const uint8_t f = T.fl(i, pc);
+      const cd zz = T.pt(i, pc);
+      real = (p < NP) && (f & 1);
+      if (real) { par = (f & 4) ? 0.0 : ((f & 2) ? 1.0 : -1.0); z = zz; }
+    }
+    bool start = false, end = false;
+    if (p == 0) start = real;
+    else if (p == NP) end = prev_real;
+    else {
+      const double dm = (real ? 1.0 : 0.0) - (prev_real ? 1.0 : 0.0);
+      const bool change = norm2(z - prev_z) > 0.01 || par != prev_par || dm != 0.0;
+      start = change && dm >= 0.0;
+      end = change && dm <= 0.0;
+    }
+    if (end && nend < MAXPARTS) hi[nend++] = (int16_t)p;
+    if (start && np_ < MAXPARTS) lo[np_++] = (int16_t)p;
+    prev_real = real; prev_par = par; prev_z = z;
+  }
+  return np_ < nend ? np_ : nend;   // k-th start pairs with k-th end
+}
+__device__ bool part_segment(const Tracks& T, int i, int lo, int hi, Seg& g) {
+  if (hi - lo < 2 || (lo == 0 && hi == 0)) return false;
+  g.track = (int16_t)i; g.lo = (int16_t)lo; g.hi = (int16_t)hi;
+  const uint8_t f = T.fl(i, lo);
+  g.par = (f & 4) ? 0 : ((f & 2) ? 1 : -1);
+  double len = 0.0; cd q0 = T.pt(i, lo);
+  for (int p = lo + 1; p < hi; ++p) { const cd q1 = T.pt(i, p); len += sqrt(norm2(q1 - q0)); q0 = q1; }
+  g.len = len;
+  return true;
+}
+// The reference keeps, of all parts in (track, start) order REVERSED, the first 3(nl^2+1) that have at least
+// two points: walk the tracks backwards and each track's parts backwards.  Returns the number of segments
+// written to parts[MAXSEG].
+template <int D>
+__device__ int build_parts_serial(const ExtCfg& cfg, const Tracks& T, unsigned closed, Seg* parts) {
+  int nparts_total = 0;
+  const int nseg_max = 3 * (cfg.nl * cfg.nl + 1);
+  for (int i = D - 1; i >= 0 && nparts_total < nseg_max; --i) {
+    if ((closed >> i) & 1u) continue;
+    int16_t lo[MAXPARTS], hi[MAXPARTS];
+    const int npair = track_parts(cfg, T, i, lo, hi);
+    for (int k = npair - 1; k >= 0 && nparts_total < nseg_max; --k) {
+      Seg g;
+      if (part_segment(T, i, lo[k], hi[k], g)) parts[nparts_total++] = g;
+    }
+  }
+  return nparts_total;
+}
+// One warp per source, the tracks staged in shared memory: lane i splits track i (the scans are independent),
+// lane 0 then collects the segments in the reference's order.  tp: [D][MAXPARTS] segments, tn: [D] their counts
+// (valid[k] in Seg::track < 0 marks a dropped pair).
+template <int D>
+__device__ int build_parts_warp(const ExtCfg& cfg, const Tracks& T, unsigned closed, Seg* tp, int* tn, Seg* parts, int lane) {
+  if (lane < D) {
+    int npair = 0;
+    if (!((closed >> lane) & 1u)) {
+      int16_t lo[MAXPARTS], hi[MAXPARTS];
+      npair = track_parts(cfg, T, lane, lo, hi);
+      for (int k = 0; k < npair; ++k) {
+        Seg g;
+        if (!part_segment(T, lane, lo[k], hi[k], g)) g.track = -1;
+        tp[lane * MAXPARTS + k] = g;
+      }
+    }
+    tn[lane] = npair;
+  }
+#ifndef CB200_HOSTSIM
+  __syncwarp();
+#endif
+  int nparts_total = 0;
+  if (lane == 0) {
+    const int nseg_max = 3 * (cfg.nl * cfg.nl + 1);
+    for (int i = D - 1; i >= 0 && nparts_total < nseg_max; --i)
+      for (int k = tn[i] - 1; k >= 0 && nparts_total < nseg_max; --k)
+        if (tp[i * MAXPARTS + k].track >= 0) parts[nparts_total++] = tp[i * MAXPARTS + k];
+  }
+  return nparts_total;
+}
+
 // `resume`: the closed tracks were integrated by sweep_body (their mask and sum are in sw_closed / sw_total);
 // only the open tracks are left, read through the permutation.
 template <int D, bool GRAD = false>
 __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s,
-                              const TrackStage* stage = nullptr, bool resume = false) {
+                              const TrackStage* stage = nullptr, bool resume = false,
+                              const Seg* pre_parts = nullptr, int pre_nparts = 0) {
   if (s >= nsrc(cfg, b)) return;
   constexpr int NLG = D == 2 ? 1 : (D == 5 ? 2 : 3);
   GreenTangent<NLG> GT(L, cfg.rho);
@@ -850,53 +1035,13 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
 
   if (closed != (1u << D) - 1u) {
     // ---- split the open tracks into runs of real images of one parity without jumps > 0.1
-    Seg parts[MAXSEG];
-    int nparts_total = 0;
-    // The reference keeps, of all parts in (track, start) order REVERSED, the first 3(nl^2+1) that
-    // have at least two points; walk the tracks backwards and each track's parts backwards.
     const int nseg_max = 3 * (cfg.nl * cfg.nl + 1);
-    for (int i = D - 1; i >= 0 && nparts_total < nseg_max; --i) {
-      if ((closed >> i) & 1u) continue;
-      int16_t lo[MAXPARTS], hi[MAXPARTS];
-      int np_ = 0, nend = 0;
-      // boundaries in increasing order; the first MAXPARTS starts and ends are kept (:202-203)
-      bool prev_real = false; double prev_par = 0.0; cd prev_z = mk(0, 0);
-#pragma unroll 4
-      for (int p = 0; p <= NP; ++p) {
-        bool real = false; double par = 0.0; cd z = mk(0, 0);
-        {
-          // unconditional loads (clamped index) so that unrolled iterations overlap their latency
-          const int pc = p < NP ? p : NP - 1;
-          const uint8_t f = T.fl(i, pc);
-          const cd zz = T.pt(i, pc);
-          real = (p < NP) && (f & 1);
-          if (real) { par = (f & 4) ? 0.0 : ((f & 2) ? 1.0 : -1.0); z = zz; }
-        }
-        bool start = false, end = false;
-        if (p == 0) start = real;
-        else if (p == NP) end = prev_real;
-        else {
-          const double dm = (real ? 1.0 : 0.0) - (prev_real ? 1.0 : 0.0);
-          const bool change = norm2(z - prev_z) > 0.01 || par != prev_par || dm != 0.0;
-          start = change && dm >= 0.0;
-          end = change && dm <= 0.0;
-        }
-        if (end && nend < MAXPARTS) hi[nend++] = (int16_t)p;
-        if (start && np_ < MAXPARTS) lo[np_++] = (int16_t)p;
-        prev_real = real; prev_par = par; prev_z = z;
-      }
-      const int npair = np_ < nend ? np_ : nend;   // k-th start pairs with k-th end
-      for (int k = npair - 1; k >= 0 && nparts_total < nseg_max; --k) {
-        // a pair (0, 0) is the reference's "empty" marker; fewer than two points are dropped (:232)
-        if (hi[k] - lo[k] < 2 || (lo[k] == 0 && hi[k] == 0)) continue;
-        Seg g; g.track = (int16_t)i; g.lo = lo[k]; g.hi = hi[k];
-        const uint8_t f = T.fl(i, lo[k]);
-        g.par = (f & 4) ? 0 : ((f & 2) ? 1 : -1);
-        double len = 0.0; cd q0 = T.pt(i, lo[k]);
-        for (int p = lo[k] + 1; p < hi[k]; ++p) { const cd q1 = T.pt(i, p); len += sqrt(norm2(q1 - q0)); q0 = q1; }
-        g.len = len;
-        parts[nparts_total++] = g;
-      }
+    Seg parts_local[MAXSEG];
+    const Seg* parts = pre_parts;
+    int nparts_total = pre_nparts;
+    if (!pre_parts) {
+      nparts_total = build_parts_serial<D>(cfg, T, closed, parts_local);
+      parts = parts_local;
     }
     // ---- stitch (extended_source.py:495-667): three rounds; the active chain starts from the
     // shortest remaining segment and grows by the closest admissible connection

@@ -13,6 +13,8 @@ cap() {  # cap <name> <function base name> <target> [skip]
       -o gpurun_out/prof_${TAG}_$1 -f python scripts/profile_targets.py $3 > gpurun_out/ncu_${TAG}_$1.log 2>&1
   ncu -i gpurun_out/prof_${TAG}_$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_$1.csv 2>/dev/null
   ncu -i gpurun_out/prof_${TAG}_$1.ncu-rep --page details --csv > gpurun_out/${TAG}_ncu_$1_details.csv 2>/dev/null
+  # gpurun_out/ travels back only below 64 MiB: keep the CSV pages, drop the 25 MB report (KEEP_REP=1 keeps it)
+  [ -n "$KEEP_REP" ] || rm -f gpurun_out/prof_${TAG}_$1.ncu-rep
 }
 for w in $WHAT; do
   case $w in

@@ -41,7 +41,7 @@ def main():
         else:
             p, x_cm = cb.lens_params(2, s=0.9, q=0.2)
             lens = cb.point_source._c_lens(2, x_cm, **p)
-        for n in (100_000, 50_000, 25_000, 12_500, 6_250, 3_000):
+        for n in [int(x) for x in os.environ.get("SIZES", "100000,50000,25000,12500,6250,3000").split(",")]:
             w = torch.from_numpy(np.linspace(-2, 2, 100_000)[:n] * 1.0 + 0.1j).cuda()
             w = torch.from_numpy(np.linspace(-2, 2, n) + 0.1j).cuda()
             mag = torch.empty(n, dtype=torch.float64, device="cuda")

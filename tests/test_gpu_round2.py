@@ -197,7 +197,14 @@ def test_fused_tangent_kernel_vs_python_rule(cb):
     cases = [(2, dict(s=0.9, q=0.2), g["b_w_0.01"][:24]),
              (3, dict(s=0.9, q=0.2, q3=0.1, r3=0.8, psi=1.0), g["t_w_0.01"][:12]),
              (1, {}, np.array([0.003 + 0.001j, 0.02 - 0.01j, 0.5 + 0.2j]))]
+    # The two tangents are the same formula evaluated at vertices that differ by the solver's residual (the
+    # specification re-polishes each vertex); near a fold dz/dt grows like 1 / det J, so the agreement is the
+    # roots' accuracy times that factor.  With compensated roots (1e-16) the two agree to 1e-7 for every lens;
+    # with plain roots the triple lens -- whose plain-mode roots are only ~1e-9 accurate (DESIGN section 2,
+    # conditioning) -- agrees to 4e-5 at one fold-crossing source and 2e-8 elsewhere (scripts/tangent_probe.py).
+    GRAD_TOL = {(1, False): 1e-8, (2, False): 1e-8, (3, False): 2e-4, (1, True): 1e-7, (2, True): 1e-7, (3, True): 1e-7}
     for nl, hp, w_np in cases:
+      for comp in (False, True):
         def run(fn):
             w = torch.from_numpy(w_np).cuda().requires_grad_(True)
             rho = torch.tensor(1e-2, dtype=torch.float64, device="cuda", requires_grad=True)
@@ -207,20 +214,24 @@ def test_fused_tangent_kernel_vs_python_rule(cb):
             (m * wt).sum().backward()
             return m.detach(), w.grad, rho.grad, {k: v.grad for k, v in t.items()}
 
-        kern = run(lambda w, rho, t: es._mag_uniform_kernel_grad(w, rho, nl, 200, 2500, False, t))
-        spec = run(lambda w, rho, t: es._mag_from_contours(es._get_contours(w, rho, nl, 200, 2500, False, t),
+        kern = run(lambda w, rho, t: es._mag_uniform_kernel_grad(w, rho, nl, 200, 2500, comp, t))
+        spec = run(lambda w, rho, t: es._mag_from_contours(es._get_contours(w, rho, nl, 200, 2500, comp, t),
                                                            w.reshape(-1), rho, nl, t))
         # the specification re-polishes every vertex by one Newton step (z0 - J^-1 F(z0)): F(z0) is the solver's
         # residual, not 0, and near a caustic J^-1 is large, so the two magnifications differ at the level of the
         # roots' own accuracy -- the forward value of the tangent kernel IS the plain kernel's, asserted below
         dev = ((kern[0] - spec[0]).abs() / spec[0].abs()).max().item()
-        assert dev < 1e-8, (nl, dev)
-        plain = es._run(torch.from_numpy(w_np).cuda(), 1e-2, nl, 200, False, 0.0, 100, 2500, False, False, 0.0, hp)
-        assert torch.allclose(kern[0], plain.reshape(-1), rtol=1e-13, atol=0), nl
-        assert torch.allclose(kern[1], spec[1], rtol=1e-8, atol=1e-9 * spec[1].abs().max().item())
-        assert abs(kern[2].item() - spec[2].item()) <= 1e-8 * abs(spec[2].item())
+        assert dev < 1e-8, (nl, comp, dev)
+        plain = es._run(torch.from_numpy(w_np).cuda(), 1e-2, nl, 200, False, 0.0, 100, 2500, comp, False, 0.0, hp)
+        assert torch.allclose(kern[0], plain.reshape(-1), rtol=1e-13, atol=0), (nl, comp)
+        tol = GRAD_TOL[(nl, comp)]
+        gdev = ((kern[1] - spec[1]).abs() / (spec[1].abs() + 1e-9 * spec[1].abs().max())).max().item()
+        assert gdev < tol, (nl, comp, "d/dw", gdev)
+        rdev = abs(kern[2].item() - spec[2].item()) / abs(spec[2].item())
+        assert rdev < tol, (nl, comp, "d/drho", rdev)
         for k in hp:
-            assert abs(kern[3][k].item() - spec[3][k].item()) <= 1e-8 * max(abs(spec[3][k].item()), 1e-3), (nl, k)
+            pdev = abs(kern[3][k].item() - spec[3][k].item()) / max(abs(spec[3][k].item()), 1e-3)
+            assert pdev < tol, (nl, comp, k, pdev)
     # the public entry takes the kernel path and chunked calls agree with one call
     w = torch.from_numpy(g["b_w_0.01"][:24]).cuda().requires_grad_(True)
     m = cb.mag_extended_source(w, 1e-2, nlenses=2, npts_limb=200, s=0.9, q=0.2)

@@ -318,3 +318,11 @@ def test_one_pass_path_equals_track_array_path(hs, g):
         finally:
             hs.hostsim_force_tracks(0)
         assert np.array_equal(one, two), nl
+
+
+@pytest.mark.parametrize("npts", [150, 400])
+def test_other_limb_sampling(hs, g, npts):
+    """other limb samplings: 150 gives an odd N0 and nadd = 7, 400 twenty new points per refinement round"""
+    w = g["b_w_0.01"][:8]
+    want = np.array([extended.mag_extended_source(x, 1e-2, 2, npts, **HP2) for x in w])
+    assert np.allclose(hs_ext(hs, w, 1e-2, 2, HP2, npts=npts), want, rtol=1e-8)
