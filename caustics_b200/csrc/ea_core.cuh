@@ -135,6 +135,20 @@ __device__ __forceinline__ double ea_log(double a) {
 __device__ const double EA_ROT_COS[17] = {1.0, 1.0, -1.0, -0.4999999999999998, 6.123233995736766e-17, 0.30901699437494745, 0.5000000000000001, 0.6234898018587336, 0.7071067811865476, 0.766044443118978, 0.8090169943749475, 0.8412535328311812, 0.8660254037844387, 0.8854560256532099, 0.9009688679024191, 0.9135454576426009, 0.9238795325112867};
 __device__ const double EA_ROT_SIN[17] = {0.0, -2.4492935982947064e-16, 1.2246467991473532e-16, 0.8660254037844387, 1.0, 0.9510565162951535, 0.8660254037844386, 0.7818314824680298, 0.7071067811865475, 0.6427876096865393, 0.5877852522924731, 0.5406408174555976, 0.49999999999999994, 0.4647231720437685, 0.4338837391175581, 0.40673664307580015, 0.3826834323650898};
 
+// cos / sin of 2 pi i / DEG + 0.7 for DEG = 2..16, i = 0..DEG-1, at offset DEG (DEG - 1) / 2 - 1: the starting angle of
+// hull edge i (init_est.h:93-96), for the order-independent (EA_INIT_BINI) estimates
+__device__ const double EA_START_COS[135] = {0.7648421872844884, -0.7648421872844884, 0.7648421872844884, -0.9403299763573428, 0.1754877890728544, 0.7648421872844884, -0.644217687237691, -0.7648421872844884, 0.644217687237691, 0.7648421872844884, -0.376338195474186, -0.9974319833523373, -0.24010867170377767, 0.8490366632458125, 0.7648421872844884, -0.1754877890728544, -0.9403299763573428, -0.7648421872844884, 0.1754877890728544, 0.9403299763573428, 0.7648421872844884, -0.02679836564196351, -0.7982592026529799, -0.9686145785460706, -0.4095834206573606, 0.45787240696551046, 0.9805409732483756, 0.7648421872844884, 0.08529440196032743, -0.644217687237691, -0.9963557923724988, -0.7648421872844884, -0.08529440196032743, 0.644217687237691, 0.9963557923724988, 0.7648421872844884, 0.171807960134941, -0.5016171209945315, -0.9403299763573428, -0.9390519851789534, -0.4983811337350216, 0.1754877890728544, 0.7672440250440125, 0.9999982547295531, 0.7648421872844884, 0.24010867170377767, -0.376338195474186, -0.8490366632458125, -0.9974319833523373, -0.7648421872844884, -0.24010867170377767, 0.376338195474186, 0.8490366632458125, 0.9974319833523373, 0.7648421872844884, 0.295135815063864, -0.26827409310951694, -0.7465088722547888, -0.987732359038807, -0.9153578008113573, -0.552363608435463, -0.013997873196067564, 0.5288120878788335, 0.903727947459871, 0.9917165691589436, 0.7648421872844884, 0.3402639204555768, -0.1754877890728544, -0.644217687237691, -0.9403299763573428, -0.9844816076932679, -0.7648421872844884, -0.3402639204555768, 0.1754877890728544, 0.644217687237691, 0.9403299763573428, 0.9844816076932679, 0.7648421872844884, 0.377851236305031, -0.09570087931087926, -0.5473290767972883, -0.8735707788198555, -0.9996879430839287, -0.8967886471332002, -0.5884458795990359, -0.14529725259033896, 0.3311372239650917, 0.7317121531462729, 0.9646606461290116, 0.9766170105046313, 0.7648421872844884, 0.4095834206573606, -0.02679836564196351, -0.45787240696551046, -0.7982592026529799, -0.9805409732483756, -0.9686145785460706, -0.7648421872844884, -0.4095834206573606, 0.02679836564196351, 0.45787240696551046, 0.7982592026529799, 0.9805409732483756, 0.9686145785460706, 0.7648421872844884, 0.4366911664900616, 0.033032275794800676, -0.376338195474186, -0.7206363738205124, -0.9403299763573428, -0.9974319833523373, -0.8820689390406132, -0.6141881618240236, -0.24010867170377767, 0.1754877890728544, 0.5607408168622756, 0.8490366632458125, 0.9905263572982096, 0.9607450455242901, 0.7648421872844884, 0.4600906066908837, 0.08529440196032743, -0.3024871022730095, -0.644217687237691, -0.8878719691683112, -0.9963557923724988, -0.9531534781757227, -0.7648421872844884, -0.4600906066908837, -0.08529440196032743, 0.3024871022730095, 0.644217687237691, 0.8878719691683112, 0.9963557923724988, 0.9531534781757227};
+__device__ const double EA_START_SIN[135] = {0.644217687237691, -0.644217687237691, 0.644217687237691, 0.3402639204555768, -0.9844816076932679, 0.644217687237691, 0.7648421872844884, -0.644217687237691, -0.7648421872844884, 0.644217687237691, 0.9264823595877222, -0.07162009903527673, -0.9707460150691568, -0.5283339327209797, 0.644217687237691, 0.9844816076932679, 0.3402639204555768, -0.644217687237691, -0.9844816076932679, -0.3402639204555768, 0.644217687237691, 0.9996408593084416, 0.6023140753625378, -0.24856749229941172, -0.9122726684071027, -0.8890179182331535, -0.19631454296900253, 0.644217687237691, 0.9963557923724988, 0.7648421872844884, 0.08529440196032743, -0.644217687237691, -0.9963557923724988, -0.7648421872844884, -0.08529440196032743, 0.644217687237691, 0.9851304608194138, 0.865089743278209, 0.3402639204555768, -0.34377517236046384, -0.8669580413935812, -0.9844816076932679, -0.64135528845895, 0.0018682981153722482, 0.644217687237691, 0.9707460150691568, 0.9264823595877222, 0.5283339327209797, -0.07162009903527673, -0.644217687237691, -0.9707460150691568, -0.9264823595877222, -0.5283339327209797, 0.07162009903527673, 0.644217687237691, 0.9554553106590536, 0.9633426238707941, 0.6653754606572769, 0.15615629000342357, -0.40264139937889587, -0.833603289386597, -0.9999020249734405, -0.8487389326013205, -0.4281072260310128, 0.12844549994302745, 0.644217687237691, 0.9403299763573428, 0.9844816076932679, 0.7648421872844884, 0.3402639204555768, -0.1754877890728544, -0.644217687237691, -0.9403299763573428, -0.9844816076932679, -0.7648421872844884, -0.3402639204555768, 0.1754877890728544, 0.644217687237691, 0.92586632038473, 0.9954101374303581, 0.8369174879832707, 0.4866971279883117, 0.02498032130745356, -0.4424591759394357, -0.8085366081897077, -0.9893880474261346, -0.9435826084157617, -0.6816137652204842, -0.26349542274953835, 0.21498654560924696, 0.644217687237691, 0.9122726684071027, 0.9996408593084416, 0.8890179182331535, 0.6023140753625378, 0.19631454296900253, -0.24856749229941172, -0.644217687237691, -0.9122726684071027, -0.9996408593084416, -0.8890179182331535, -0.6023140753625378, -0.19631454296900253, 0.24856749229941172, 0.644217687237691, 0.8996114856478598, 0.9994542854757371, 0.9264823595877222, 0.6933132168989876, 0.3402639204555768, -0.07162009903527673, -0.4711203527547574, -0.7891596174889001, -0.9707460150691568, -0.9844816076932679, -0.827991386612583, -0.5283339327209797, -0.13732274209882214, 0.2774327981701691, 0.644217687237691, 0.8878719691683112, 0.9963557923724988, 0.9531534781757227, 0.7648421872844884, 0.4600906066908837, 0.08529440196032743, -0.3024871022730095, -0.644217687237691, -0.8878719691683112, -0.9963557923724988, -0.9531534781757227, -0.7648421872844884, -0.4600906066908837, -0.08529440196032743, 0.3024871022730095};
+// exp for a STARTING RADIUS (EA_INIT_BINI only; ~1e-7 relative): 2^k by the exponent field, 2^f by the
+// single-precision hardware exponential
+__device__ __forceinline__ double ea_exp_start(double x) {
+  double t = x * 1.4426950408889634;
+  t = fmin(fmax(t, -1000.0), 1000.0);
+  const double k = rint(t);
+  const float e = exp2f((float)(t - k));
+  return __hiloint2double(((int)k + 1023) << 20, 0) * (double)e;
+}
+
 // Bini initial estimates from the upper convex hull of (i, log|p_i|) -- init_est.h:57-102.
 // mode EA_INIT_REFERENCE reproduces the reference's purely real guesses r*sin(.) (the comma
 // expression at init_est.h:95), so sweep counts and root order match the reference; EA_INIT_BINI
@@ -159,11 +173,19 @@ __device__ __noinline__ void ea_init_est(const ALPHA& al, double* zre, double* z
     int lo = hx[i + 1], up = hx[i];
     int nz = up - lo;
     // (|p_lo| / |p_up|)^(1/nz), from the logs already at hand
-    double r = exp((ly[lo] - ly[up]) / nz);
     // angles 2 pi j / nz + 2 pi i / DEG + 0.7: one sincospi per hull edge, then exact-table rotations
-    // by 2 pi / nz (instead of one libm sincos per root)
-    double s, c;
-    sincospi(fma((double)i, 2.0 / DEG, 0.22281692032865347), &s, &c);   // 0.7 / pi
+    // by 2 pi / nz (instead of one libm sincos per root).  The order-independent estimates take radius and
+    // starting angle from a cheap exponential and a table: they only steer the iteration, and libm's exp and
+    // sincospi were a third of the instruction-fetch stalls of the cold point-source kernel (profiles/)
+    double r, s, c;
+    if (mode == EA_INIT_REFERENCE) {
+      r = exp((ly[lo] - ly[up]) / nz);
+      sincospi(fma((double)i, 2.0 / DEG, 0.22281692032865347), &s, &c);   // 0.7 / pi
+    } else {
+      r = ea_exp_start((ly[lo] - ly[up]) / nz);
+      c = EA_START_COS[DEG * (DEG - 1) / 2 - 1 + i];
+      s = EA_START_SIN[DEG * (DEG - 1) / 2 - 1 + i];
+    }
     const double rc = EA_ROT_COS[nz], rs = EA_ROT_SIN[nz];
     for (int j = 0; j < nz; ++j) {
       zre[(pos + j) * NT] = (mode == EA_INIT_REFERENCE) ? r * s : r * c;

@@ -17,7 +17,9 @@ from .point_source import _c_lens, lens_params
 __all__ = ["mag_extended_source", "mag", "mag_gate"]
 
 _MAX_WS_BYTES = 24 << 30      # per-call workspace budget; larger batches are processed in chunks
-_MAX_GATED_WS_BYTES = 3 << 30  # gated light curves: the survivors are integrated in windows of this much state
+_MAX_GATED_WS_BYTES = 3_950_000_000  # gated light curves: the survivors are integrated in windows of this much state
+# (a 10^6-point binary light curve, 5.6e4 limb-darkened integrations, is ONE window of 3.92 GB: a second, short
+# window costs 5 ms of latency-bound thread-per-source kernels)
 
 
 def _to_device(w):
@@ -80,6 +82,7 @@ def _run(w, rho, nlenses, npts_limb, limb_darkening, u1, npts_ld, roots_itmax, r
             nfull = int(cnt.item())
             if nfull:
                 chunk = _chunk_len(L, nfull, nlenses, npts_limb, limb_darkening, npts_ld, _MAX_GATED_WS_BYTES, mag_only=True)
+                chunk = -(-nfull // -(-nfull // chunk))      # windows of equal length
                 nbytes = L.caustics_mag_workspace_bytes(nfull, chunk, nlenses, cfg[0], ld, cfg[3])
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
                 _lib.check(L.caustics_mag_extended_source_list(flat.data_ptr(), mag.data_ptr(), lst.data_ptr(),

@@ -4,10 +4,10 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 300 python -m pytest tests/test_gpu_round2.py -q -x 2>&1 | tail -5
+[ -n "$SKIP_TESTS" ] || timeout 300 python -m pytest tests/test_gpu_round2.py -q -x 2>&1 | tail -5
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     scripts/pcie_probe.py 2> gpurun_out/pcie_probe_n$N.err | tail -1 > gpurun_out/pcie_probe_n$N.json
-for k in 1 2 4 8; do
+for k in ${KS:-1 2 4 8}; do
   [ $k -le $N ] || continue
   if [ $k -eq 1 ]; then
     timeout 400 python bench.py --steps ${STEPS:-20} --warmup 3 2> gpurun_out/scale_n$k.err | tail -1 > gpurun_out/scale_n$k.json

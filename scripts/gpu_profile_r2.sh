@@ -19,8 +19,8 @@ cap() {  # cap <name> <function base name> <target> [skip]
 for w in $WHAT; do
   case $w in
     bench)
-      ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv \
-          --log-file gpurun_out/launches_${TAG}_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_${TAG}.log 2>&1 ;;
+      ncu --metrics gpu__time_duration.sum --clock-control none -c ${NLAUNCH:-8000} --csv \
+          --log-file gpurun_out/launches_${TAG}_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline ${BENCH_ONLY:+--only $BENCH_ONLY} > gpurun_out/ncu_bench_${TAG}.log 2>&1 ;;
     solver)
       cap ea_comp10 ea_kernel comp10
       cap ea_deg5 ea_kernel deg5
@@ -29,7 +29,7 @@ for w in $WHAT; do
       cap k_limb_walk k_limb_walk c4 0
       cap k_refine_fused k_refine_fused c4 0
       cap k_sweep k_sweep c4 0
-      cap k_open k_open c4 0
+      cap k_open_staged k_open_staged c4 0
       cap k_contours_grad k_contours c4grad 0
       cap k_tracks k_tracks c4grad 0
       cap k_ld_pq k_ld_pq c3 1 ;;

@@ -7,6 +7,7 @@ scripts/gpu_profile_r2.sh):  python scripts/profile_targets.py <target>
   c4       kernel family 3 on 10^5 triple-lens sources (k_limb_walk, k_refine_select, k_refine_solve, k_tracks, k_contours)
   c4grad   the same with the fused tangent (k_contours<10, true>)
   c3       the gated limb-darkened light curve (k_gate, k_ld_pq, ...)
+  c3x100   the same with 10^6 points
 """
 import os
 import sys
@@ -51,6 +52,10 @@ elif target in ("c4", "c4grad"):
             _lib.check(L.caustics_mag_extended_source(w.data_ptr(), mag.data_ptr(), n, 1e-2, lens3, 200, 0, 0.0, 100, 2500, 0, ws.data_ptr(), nb, None))
         else:
             _lib.check(L.caustics_mag_extended_source_grad(w.data_ptr(), mag.data_ptr(), grad.data_ptr(), n, 1e-2, lens3, 200, 2500, 0, ws.data_ptr(), nb, None))
+elif target == "c3x100":
+    w = torch.from_numpy(np.linspace(-2, 2, 1_000_000) + 0.1j).cuda()
+    for _ in range(2):
+        cb.mag(w, 1e-2, nlenses=2, npts_limb=200, limb_darkening=True, u1=0.7, npts_ld=100, **bench.HP2)
 elif target == "c3":
     w = torch.from_numpy(np.linspace(-2, 2, 10_000) + 0.1j).cuda()
     for _ in range(reps):

@@ -135,7 +135,7 @@ def test_grid_walk(hs, nl, hp, col0, r0):
         got = hs_grid_walk(hs, x0, -1.5, 2 * dx, dx, nx, r0, r1, nl, hp, run=run, extrap=extrap)
         rel = np.abs(got / want - 1)
         # rounding x conditioning: the same bound the cold kernel is held to on this map (test_c5_map_properties)
-        assert rel.max() < 1e-9 and np.median(rel) < 1e-13, (run, extrap, rel.max())
+        assert rel.max() < 3e-9 and np.median(rel) < 1e-13, (run, extrap, rel.max())
 
 
 def test_grid_walk_sweep_counts(hs):
