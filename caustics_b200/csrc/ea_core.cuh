@@ -296,13 +296,24 @@ template <int DEG, int NT> __device__ __forceinline__ void alpha_bind(AlphaSmem<
 // thr^2 would underflow (a polynomial whose coefficients span more than ~150 decades, e.g. z^10 - 1e-200:
 // |h| keeps shrinking far below sqrt(DBL_MIN) while the reference's hypot-based test is still unmet); there
 // the moduli are compared unsquared through a scaled hypot.  Rare path, inside the lazily evaluated block.
-__device__ __forceinline__ bool ea_exceeds(cd h, double nh, double thr) {
-  if (thr > 1e-150) return nh > __dmul_rn(thr, thr);
-  const double ar = fabs(h.re), ai = fabs(h.im);
+#ifndef CB200_EXCEEDS_INLINE
+#define CB200_EXCEEDS_INLINE 0
+#endif
+#if CB200_EXCEEDS_INLINE
+__device__ __forceinline__
+#else
+static __device__ __noinline__     // out of line: its division and square root cost the headline 3 % when they sit in the step
+#endif
+bool ea_exceeds_unsquared(double hre, double him, double thr) {
+  const double ar = fabs(hre), ai = fabs(him);
   const double m = fmax(ar, ai), q = fmin(ar, ai);
   if (!(m > 0.0)) return false;
   const double r = q / m;
   return m * sqrt(fma(r, r, 1.0)) > thr;
+}
+__device__ __forceinline__ bool ea_exceeds(cd h, double nh, double thr) {
+  if (thr > 1e-150) return nh > __dmul_rn(thr, thr);
+  return ea_exceeds_unsquared(h.re, h.im, thr);
 }
 
 // Value, derivative and the real bound polynomial in one unrolled Horner pass (horner.h:219-267).
@@ -461,7 +472,7 @@ __device__ __forceinline__ EAResult ea_solve_thread(const cd (&p)[DEG + 1], EASm
   ALPHA al;
   alpha_bind(al, &sm.al[0][tid]);
 #pragma unroll
-  for (int i = 0; i <= DEG; ++i) al.set(i, cabs_fast(p[i]));  // ehrlich_aberth.h:77-82
+  for (int i = 0; i <= DEG; ++i) al.set(i, fast ? sqrt_fast(norm2(p[i])) : cabs_fast(p[i]));  // ehrlich_aberth.h:77-82 (fast: branch-free square root, <= 1 ulp)
   if (active && !custom_init) {
     // A polynomial whose coefficients are all exactly real keeps the reference's real-axis guesses
     // on the real axis in exact arithmetic; the reference only escapes through rounding noise in
