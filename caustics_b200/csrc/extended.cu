@@ -37,21 +37,17 @@ namespace {
 
 constexpr int NT = 128;
 // resident CTAs per SM the register allocation aims at (measured, profiles/r02_ext_variants.txt): the
-// one-pass track kernel is fastest with all 255 registers (2 CTAs), the refinement with 168 (6 CTAs of 2 warps;
-// 128 registers and 7-8 CTAs: 8.97 / 9.15 ms against 8.75 on C4)
+// one-pass track kernel is fastest with all 255 registers (2 CTAs); the triple-lens refinement solves with 128
+// (4 CTAs: 17.0 ms against 17.4 on C4)
 #ifndef SW_MINB
 #define SW_MINB 2
-#endif
-#ifndef RF_MINB
-#define RF_MINB 6
 #endif
 // Phase-variant mask (caustics_set_tuning("ext_variants", mask) overrides the rules; tests, experiments):
 //    2  stitching on a shared-memory copy of the tracks, one warp per source (track-array path)
 //    4  warp-per-source limb-darkened sum
 //    8  lane-per-root limb walk (k_limb_walk_group)
 //   32  thread-per-source open-track pass instead of the staged one
-// (1 and 16 belonged to earlier pipelines -- a selection kernel per round; a thread-per-source kernel that
-// walked AND refined, measured at 16.5-18 ms against 5.6 + 8.8 ms for k_limb_walk + k_refine_fused -- ignored.)
+// (1, 16 belonged to earlier pipelines and are ignored.)
 // `n` is the number of sources that are integrated (a gated call passes its estimate).
 inline int small_mask(int64_t n, int nlenses) {
   const int k = tuning_get(TUNE_EXT_VARIANTS);
@@ -78,40 +74,15 @@ __global__ void __launch_bounds__(NT) k_limb_walk_group(ExtCfg cfg, ExtBuf b, Le
 __global__ void __launch_bounds__(NT) k_limb_walk_single(ExtCfg cfg, ExtBuf b, LensConst L) {
   limb_walk_single_body(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
-// All NITER refinement rounds of G = 32 / nadd sources per warp; the warps of a CTA are independent
-// (no CTA barrier), a CTA is just RF_WPC private slices of dynamic shared memory.
-constexpr int RF_WPC = 2;
-inline size_t refine_warp_bytes(const ExtCfg& c, size_t solver_planes) {
-  const int lps = c.nadd < 32 ? c.nadd : 32, G = 32 / lps;
-  const size_t n = (size_t)G * c.NP * 8 + solver_planes + (size_t)G * c.NP * 2 + (size_t)G * 2 * NADD_MAX * 2;
-  return (n + 15) & ~(size_t)15;
+// the refinement: a selection kernel + a solve kernel per round
+template <int D>
+__global__ void __launch_bounds__(NT) k_round_select(ExtCfg cfg, ExtBuf b, int round) {
+  round_select_body<D>(cfg, b, round, threadIdx.x & 31, (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5));
 }
 template <int NL, bool COMP>
-__global__ void __launch_bounds__(RF_WPC * 32, RF_MINB) k_refine_fused(ExtCfg cfg, ExtBuf b, LensConst L, int warp_bytes) {
-  extern __shared__ __align__(16) unsigned char rf_smem[];
-  typedef EASmem<(NL == 1 ? 2 : NL * NL + 1), COMP, 32> Planes;
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int lps = cfg.nadd < 32 ? cfg.nadd : 32, G = 32 / lps;
-  unsigned char* base = rf_smem + (size_t)wid * warp_bytes;
-  double* s_dval = (double*)base;
-  Planes* sm = (Planes*)(base + (size_t)G * cfg.NP * 8);
-  uint16_t* s_order = (uint16_t*)(base + (size_t)G * cfg.NP * 8 + sizeof(Planes));
-  uint16_t* s_lr = s_order + (size_t)G * cfg.NP;
-  refine_fused_body<NL, COMP>(cfg, b, L, *sm, s_order, s_dval, s_lr, lane, (int64_t)blockIdx.x * RF_WPC + wid);
-}
-template <int NL, bool COMP>
-int launch_refine(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, cudaStream_t st) {
-  typedef EASmem<(NL == 1 ? 2 : NL * NL + 1), COMP, 32> Planes;
-  const size_t wb = refine_warp_bytes(cfg, sizeof(Planes)), bytes = wb * RF_WPC;
-  if (bytes > 200 * 1024) return CAUSTICS_ERR_BAD_ARG;
-  if (bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_refine_fused<NL, COMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return cuda_rc(e);
-  }
-  const int lps = cfg.nadd < 32 ? cfg.nadd : 32, G = 32 / lps;
-  const int64_t warps = (cfg.S + G - 1) / G;
-  k_refine_fused<NL, COMP><<<(unsigned)((warps + RF_WPC - 1) / RF_WPC), RF_WPC * 32, bytes, st>>>(cfg, b, L, (int)wb);
-  return CAUSTICS_OK;
+__global__ void __launch_bounds__(NT, (NL == 3 && !COMP) ? 4 : 1) k_round_solve(ExtCfg cfg, ExtBuf b, LensConst L, int round) {
+  __shared__ EASmem<(NL == 1 ? 2 : NL * NL + 1), COMP, NT> sm;
+  round_solve_body<NL, COMP, NT>(cfg, b, L, sm, threadIdx.x, (int64_t)blockIdx.x * NT + threadIdx.x, round);
 }
 template <int D>
 __global__ void __launch_bounds__(NT) k_tracks(ExtCfg cfg, ExtBuf b) {
@@ -280,8 +251,13 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
     k_limb_walk_group<(NL == 1 ? 2 : NL)><<<(unsigned)((warps + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(cfg, b, L);
   } else k_limb_walk<(NL == 1 ? 2 : NL)><<<gs, NT, 0, st>>>(cfg, b, L);
   {
-    const int rc = cfg.comp && NL != 1 ? launch_refine<NL, true>(cfg, b, L, st) : launch_refine<NL, false>(cfg, b, L, st);
-    if (rc) return rc;
+    const unsigned gsel = (unsigned)((cfg.S + NT / 32 - 1) / (NT / 32));
+    const unsigned gsol = (unsigned)((cfg.S * cfg.nadd + NT - 1) / NT);
+    for (int round = 0; round < NITER; ++round) {
+      k_round_select<D><<<gsel, NT, 0, st>>>(cfg, b, round);
+      if (cfg.comp && NL != 1) k_round_solve<NL, true><<<gsol, NT, 0, st>>>(cfg, b, L, round);
+      else k_round_solve<NL, false><<<gsol, NT, 0, st>>>(cfg, b, L, round);
+    }
   }
   if (!cfg.ld && !cfg.tracks) {
     // plain uniform-disk magnification: one pass (matching + closed tracks), then the caustic-crossing sources

@@ -61,12 +61,16 @@ struct ExtBuf {
   const int32_t* list;     // optional: indices into w of the sources to integrate (else identity)
   const int32_t* count;    // optional: device-side number of listed sources (else S)
   int64_t list_off;        // this pass integrates list[list_off .. list_off + S) (gated calls with a small workspace)
-  // Limb points by ARRIVAL SLOT, one contiguous record per source (a source's refinement is owned by one
-  // warp, refine_fused_body: its reads and writes are whole 16 D-byte columns):
+  // Limb points by ARRIVAL SLOT, one contiguous record per source (a refinement solve reads and writes whole
+  // 16 D-byte columns of it):
   cb200_d2* z;             // [S][NP][D] images of the limb point in arrival slot `slot`
   uint32_t* fw;            // [S][NP]    3 flag bits per image: bit0 real image, bit1 det J > 0, bit2 det J == 0
   double* theta;           // [S][NP]    limb angle by arrival slot
   uint16_t* order;         // [S][NP]    arrival slot of the p-th point in theta order
+  // Refinement state (round_select_body / round_solve_body):
+  double* rdval;           // [S][NP]    squared width of the interval that starts at this slot (aliases perm / sre)
+  uint16_t* rnext;         // [S][NP]    theta-order links
+  uint16_t* rlr;           // [S][2][NADD_MAX]  left / right slots of the round's new points
   // Theta-ordered image tracks, structure of arrays with the source index fastest (thread-per-source phases):
   double* sre; double* sim; uint8_t* sflg;  // [NP][D][S], rows = image tracks
   // One-pass uniform-disk path (sweep_body / open_body):
@@ -305,9 +309,6 @@ __device__ __forceinline__ void interval_widths2_planes(const ExtCfg& cfg, const
 //
 // A source's refinement state is small: the theta order (2 NP bytes of links) and one width per interval
 // (8 NP bytes, `dval`, indexed by the slot that STARTS the interval; a new point changes exactly two of them).
-// One warp owns G = 32 / nadd sources for all rounds and keeps that state in shared memory
-// (refine_fused_body): the selection never touches global memory, the solves read and write whole columns of
-// the source's record, and the ten rounds are a loop inside one kernel instead of twenty launches.
 #ifdef CB200_HOSTSIM
 constexpr int EXT_WARP = 1;      // the host logic tests run a "warp" of one lane
 #else
@@ -327,7 +328,7 @@ __device__ __forceinline__ unsigned cb200_warp_max(unsigned v) { return __reduce
 // -- and position order is theta order -- so the scan runs over the slots as they lie in memory and breaks
 // ties by theta.  A new point is linked in between its interval's ends: no splice, nothing is shifted.
 //
-// All lanes of a warp select for ONE source.  Each lane holds its share of the widths (slots lane, lane + 32,
+// All lanes of a warp select for ONE source (round_select_body).  Each lane holds its share of the widths (slots lane, lane + 32,
 // ...) in registers for the round; pass r = every lane's best, a warp arg-max, and the winner drops the entry it contributed.  Widths are
 // non-negative doubles, whose order is the order of their bit patterns: the arg-max is two 32-bit
 // redux.sync (high words, then low words among the lanes that tie on the high word) and a ballot.  Equal
@@ -435,71 +436,62 @@ __device__ __forceinline__ void warm_start_from(const ExtCfg& cfg, const ExtBuf&
   }
 }
 
-// The fused refinement of the sources of one warp.  Shared memory per warp (carved by the kernel):
-//   s_order[G][NP] uint16 (the theta-order links, see refine_select_warp), s_dval[G][NP] double,
-//   s_lr[G][2][NADD_MAX] uint16, and the solver planes.
-// Lane g * LPS + q works for source g of the warp (LPS = min(nadd, warp) lanes per source); new point r of a
-// round is solved by lane q = r mod LPS.
-template <int NL, bool COMP>
-__device__ void refine_fused_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,
-                                  EASmem<(NL == 1 ? 2 : NL * NL + 1), COMP, EXT_WARP>& sm, uint16_t* s_order,
-                                  double* s_dval, uint16_t* s_lr, int lane, int64_t warp_id) {
-  constexpr int D = NL == 1 ? 2 : NL * NL + 1;
+// One selection kernel and one solve kernel PER ROUND, state in global memory: a warp per source selects
+// (coalesced lane-strided reads of the source's widths and links), then a THREAD per (source, new point) solves --
+// consecutive threads are one source's nadd points, so a warp's accesses stay inside three or four records.
+// (Round 2 also built the rounds as a loop inside one kernel, a warp owning 32 / nadd sources with widths and
+// links in shared memory: 8.7 ms for the C4 batch against 7.0 ms for these twenty launches, and slower or equal
+// at every batch size down to 1000 sources -- the selection is a latency-bound phase of ten dependent passes that a
+// warp-owned kernel cannot hide behind its own solves; profiles/r02_ext_variants.txt.)
+template <int D>
+__device__ void round_select_body(const ExtCfg& cfg, const ExtBuf& b, int round, int lane, int64_t s) {
+  if (s >= nsrc(cfg, b)) return;   // warp-uniform
   const int NP = cfg.NP, n = cfg.nadd;
-  const int LPS = n < EXT_WARP ? n : EXT_WARP, G = EXT_WARP / LPS;
-  const int64_t ns = nsrc(cfg, b);
-  const int64_t s_first = warp_id * G;
-  if (s_first >= ns) return;   // warp-uniform
-  // ---- prologue: identity order, widths of the N0 - 1 initial intervals (lanes share the intervals)
-  for (int g = 0; g < G; ++g) {
-    const int64_t s = s_first + g;
-    if (s >= ns) break;
+  double* dv = b.rdval + IS(0, s);
+  uint16_t* nxt = b.rnext + IS(0, s);
+  uint16_t* lft = b.rlr + s * 2 * NADD_MAX;
+  if (round == 0) {
     for (int i = lane; i < NP; i += EXT_WARP) {
-      s_order[g * NP + i] = (uint16_t)(i + 1 < cfg.N0 ? i + 1 : 0);
-      s_dval[g * NP + i] = i + 1 < cfg.N0 ? interval_width2<D>(cfg, b, i, i + 1, s) : 0.0;
-    }
-  }
-  __syncwarp();
-  const int g = lane / LPS, q = lane - g * LPS;
-  const int64_t s = s_first + g;
-  const bool valid = g < G && s < ns;
-  uint16_t* ord = s_order + (valid ? g : 0) * NP;
-  double* dv = s_dval + (valid ? g : 0) * NP;
-  uint16_t* lft = s_lr + (valid ? g : 0) * 2 * NADD_MAX;
-  uint16_t* rgt = lft + NADD_MAX;
-  const cd w0 = valid ? source_centre(cfg, b, L, s) : mk(0.3, 0.2);
-  for (int round = 0; round < NITER; ++round) {
-    const int cur = cfg.N0 + round * n;
-    for (int gg = 0; gg < G; ++gg) {          // the warp's sources in turn, all lanes on each selection
-      if (s_first + gg >= ns) break;
-      refine_select_warp(cur, n, cfg.N0, s_order + gg * NP, s_dval + gg * NP, b.theta + IS(0, s_first + gg),
-                         s_lr + gg * 2 * NADD_MAX, s_lr + gg * 2 * NADD_MAX + NADD_MAX, lane);
-    }
-    for (int r0 = 0; r0 < n; r0 += LPS) {   // one pass unless nadd > warp size
-      const int r = r0 + q;
-      const bool active = valid && r < n;
-      const int slot = cur + (active ? r : 0);
-      const int lf = active ? lft[r] : 0, rt = active ? rgt[r] : 0;
-      if constexpr (NL == 1) {
-        if (active) store_single(cfg, b, limb_point(w0, cfg.rho, b.theta[IS(slot, s)]), slot, s);
-      } else {
-        cd w = mk(0.3, 0.2);
-        if (active) {
-          w = limb_point(w0, cfg.rho, b.theta[IS(slot, s)]);
-          warm_start_from<D, COMP, EXT_WARP>(cfg, b, sm, lane, lf, r, s);
-        }
-        const uint32_t fw = solve_and_store<NL, COMP, EXT_WARP>(cfg, b, L, sm, lane, active, w, true, slot, s);
-        if (active) interval_widths2_planes<D, COMP, EXT_WARP>(cfg, b, sm, lane, fw, lf, rt, s, dv[lf], dv[slot]);
-      }
-      if (NL == 1 && active) {
-        dv[lf] = interval_width2<D>(cfg, b, lf, slot, s);
-        dv[slot] = interval_width2<D>(cfg, b, slot, rt, s);
-      }
+      nxt[i] = (uint16_t)(i + 1 < cfg.N0 ? i + 1 : 0);
+      dv[i] = i + 1 < cfg.N0 ? interval_width2<D>(cfg, b, i, i + 1, s) : 0.0;
     }
     __syncwarp();
   }
-  // ---- epilogue: the final theta order goes to the source's record
-  if (valid && q == 0) order_from_links(NP, ord, b.order + IS(0, s));
+  refine_select_warp(cfg.N0 + round * n, n, cfg.N0, nxt, dv, b.theta + IS(0, s), lft, lft + NADD_MAX, lane);
+  // the links are final after the last selection (solves add no points): the theta order as an array
+  if (round == NITER - 1 && lane == 0) order_from_links(NP, nxt, b.order + IS(0, s));
+}
+template <int NL, bool COMP, int NT>
+__device__ void round_solve_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L,
+                                 EASmem<(NL == 1 ? 2 : NL * NL + 1), COMP, NT>& sm, int tid, int64_t g, int round) {
+  constexpr int D = NL == 1 ? 2 : NL * NL + 1;
+  const int n = cfg.nadd;
+  const int64_t s = g / n;
+  const int r = (int)(g - s * n), slot = cfg.N0 + round * n + r;
+  const bool active = s < nsrc(cfg, b);
+  int lf = 0, rt = 0;
+  cd w = mk(0.3, 0.2);
+  if (active) {
+    const uint16_t* lft = b.rlr + s * 2 * NADD_MAX;
+    lf = lft[r]; rt = lft[NADD_MAX + r];
+    w = limb_point(source_centre(cfg, b, L, s), cfg.rho, b.theta[IS(slot, s)]);
+  }
+  double wl = 0.0, wr = 0.0;
+  if constexpr (NL == 1) {
+    if (active) {
+      store_single(cfg, b, w, slot, s);
+      wl = interval_width2<D>(cfg, b, lf, slot, s);
+      wr = interval_width2<D>(cfg, b, slot, rt, s);
+    }
+  } else {
+    if (active) warm_start_from<D, COMP, NT>(cfg, b, sm, tid, lf, r, s);
+    const uint32_t fw = solve_and_store<NL, COMP, NT>(cfg, b, L, sm, tid, active, w, true, slot, s);
+    if (active) interval_widths2_planes<D, COMP, NT>(cfg, b, sm, tid, fw, lf, rt, s, wl, wr);
+  }
+  if (active) {
+    b.rdval[IS(lf, s)] = wl;
+    b.rdval[IS(slot, s)] = wr;
+  }
 }
 
 // The (deg, nadd) jitter table is the same for every source and every round: one tiny launch fills it

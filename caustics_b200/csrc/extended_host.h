@@ -50,7 +50,7 @@ inline int fill_gl_tables(int n1, int n2, double* tab) {
 }
 
 struct Layout {
-  size_t theta, z, fw, order, sre, sim, sflg, perm, sw_total, sw_closed, open_list, open_count, vz, vP, vQ, vcid, vcount, ncont, cz0, cpar, cstart, gl, jit, list, count, total;
+  size_t theta, z, fw, order, rnext, rlr, sre, sim, sflg, perm, sw_total, sw_closed, open_list, open_count, vz, vP, vQ, vcid, vcount, ncont, cz0, cpar, cstart, gl, jit, list, count, total;
 };
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -64,6 +64,7 @@ inline Layout make_layout(const ExtCfg& c, int64_t npoints = -1) {
   l.theta = take(NP * S * 8);
   l.z = take(NP * D * S * 16); l.fw = take(NP * S * 4);
   l.order = take(NP * S * 2);
+  l.rnext = take(NP * S * 2); l.rlr = take((size_t)2 * NADD_MAX * S * 2);
   // the theta-ordered track arrays are needed by limb-darkened, tangent and export calls only; the plain
   // uniform-disk call integrates in one pass (sweep_body) and keeps 8 bytes per limb point instead
   if (c.ld || c.tracks) {
@@ -112,10 +113,13 @@ inline ExtBuf bind(const ExtCfg& c, const Layout& l, void* ws) {
   b.theta = (double*)(base + l.theta);
   b.z = (cb200_d2*)(base + l.z); b.fw = (uint32_t*)(base + l.fw);
   b.order = (uint16_t*)(base + l.order);
+  b.rnext = (uint16_t*)(base + l.rnext); b.rlr = (uint16_t*)(base + l.rlr);
   if (c.ld || c.tracks) {
     b.sre = (double*)(base + l.sre); b.sim = (double*)(base + l.sim); b.sflg = (uint8_t*)(base + l.sflg);
+    b.rdval = b.sre;          // the widths are dead before k_tracks writes the tracks
   } else {
-    b.perm = (uint64_t*)(base + l.perm); b.sw_total = (double*)(base + l.sw_total); b.sw_closed = (uint32_t*)(base + l.sw_closed);
+    b.perm = (uint64_t*)(base + l.perm); b.rdval = (double*)(base + l.perm);   // dead before k_sweep writes perm
+    b.sw_total = (double*)(base + l.sw_total); b.sw_closed = (uint32_t*)(base + l.sw_closed);
     b.open_list = (int32_t*)(base + l.open_list); b.open_count = (int32_t*)(base + l.open_count);
   }
   if (c.ld) {

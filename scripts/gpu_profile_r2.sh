@@ -27,7 +27,8 @@ for w in $WHAT; do
       cap ps_map ps_kernel map ;;
     ext)
       cap k_limb_walk k_limb_walk c4 0
-      cap k_refine_fused k_refine_fused c4 0
+      cap k_round_select k_round_select c4 1
+      cap k_round_solve k_round_solve c4 1
       cap k_sweep k_sweep c4 0
       cap k_open_staged k_open_staged c4 0
       cap k_contours_grad k_contours c4grad 0

@@ -142,14 +142,15 @@ static void ext_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, int64_
     if (NL == 1) limb_walk_single_body(cfg, b, L, s); else limb_walk_body<NLS, 1>(cfg, b, L, sm0, 0, s);
   }
   {
-    // the fused refinement with a one-lane "warp": one source per warp, the new points of a round in turn
-    std::vector<uint16_t> ord(cfg.NP), lr(2 * NADD_MAX);
-    std::vector<double> dv(cfg.NP);
+    // the refinement: selection for every source, then every (source, new point), round by round
     static EASmem<D, false, 1> rf0;
     static EASmem<D, true, 1> rf1;
-    for (int64_t s = 0; s < ns; ++s) {
-      if (cfg.comp && NL != 1) refine_fused_body<NL, true>(cfg, b, L, rf1, ord.data(), dv.data(), lr.data(), 0, s);
-      else refine_fused_body<NL, false>(cfg, b, L, rf0, ord.data(), dv.data(), lr.data(), 0, s);
+    for (int round = 0; round < NITER; ++round) {
+      for (int64_t s = 0; s < ns; ++s) round_select_body<D>(cfg, b, round, 0, s);
+      for (int64_t g = 0; g < ns * cfg.nadd; ++g) {
+        if (cfg.comp && NL != 1) round_solve_body<NL, true, 1>(cfg, b, L, rf1, 0, g, round);
+        else round_solve_body<NL, false, 1>(cfg, b, L, rf0, 0, g, round);
+      }
     }
   }
   if (!cfg.ld && !cfg.tracks) {
