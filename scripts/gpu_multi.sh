@@ -5,7 +5,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 [ -n "$SKIP_TESTS" ] || timeout 300 python -m pytest tests/test_gpu_round2.py -q -x 2>&1 | tail -5
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+[ -n "$SKIP_PROBE" ] || timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     scripts/pcie_probe.py 2> gpurun_out/pcie_probe_n$N.err | tail -1 > gpurun_out/pcie_probe_n$N.json
 for k in ${KS:-1 2 4 8}; do
   [ $k -le $N ] || continue
@@ -28,7 +28,7 @@ except Exception as e:
     print("N=$k: no line", e)
 PY
 done
-python -c "
+[ -n "$SKIP_PROBE" ] || python -c "
 import json; d=json.load(open('gpurun_out/pcie_probe_n$N.json'))
 for k,v in d['results'].items(): print(k, '%.1f GB/s per rank, %.1f aggregate' % (v['per_rank_gbs'], v['aggregate_gbs']))
 print('\n'.join(d['topo']))
