@@ -536,7 +536,21 @@ struct TrackWalk {
 #pragma unroll
     for (int j = 0; j < D; ++j) { zr[j] = nzr[j]; zi[j] = nzi[j]; }
     if (p + 1 < cfg.NP) fetch(p + 1);
-    // exact duplicates (inside the column, or an unchanged warm start) get a tiny real offset
+    // exact duplicates (inside the column, or an unchanged warm start) get a tiny real offset.  They are rare:
+    // the full test (2 D^2 compares of both parts) runs only when some REAL parts coincide, on a warp vote
+    bool maybe = false;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        if (k < j) maybe = maybe || zr[k] == zr[j];
+        if (p > 0) maybe = maybe || cre[k] == zr[j];
+      }
+    }
+#ifndef CB200_HOSTSIM
+    maybe = __any_sync(__activemask(), maybe);
+#endif
+    if (maybe) {
 #pragma unroll
     for (int j = 0; j < D; ++j) {
       bool dup = false;
@@ -549,6 +563,7 @@ struct TrackWalk {
         zr[j] += duplicate_jitter_cold(j, p, D, cfg.NP);   // extended_source.py:144-148
         if (WRITE_BACK) b.z[IZ(slot, j, s)].x = zr[j];
       }
+    }
     }
     unsigned used = 0;
     uint64_t perm = 0;

@@ -56,6 +56,8 @@ def main():
                 rec[f"mask{m}"] = round(timeit(fn), 3)
                 if ref is None:
                     ref = mag.clone()
+                    if os.environ.get("DUMP"):  # bitwise comparisons between library builds
+                        np.save(os.path.join(ROOT, "gpurun_out", f"{os.environ['DUMP']}_{nl}_{n}.npy"), ref.cpu().numpy())
                 else:
                     rec[f"dev{m}"] = float(((mag - ref).abs() / ref).max().item())
             L.caustics_set_tuning(b"ext_variants", -1)
