@@ -47,11 +47,12 @@ constexpr int NT = 128;
 //    4  warp-per-source limb-darkened sum
 //    8  lane-per-root limb walk (k_limb_walk_group)
 //   32  thread-per-source open-track pass instead of the staged one
+//   64  the whole-record staged open pass (k_open_staged) instead of the compact one (k_open_compact)
 // (1, 16 belonged to earlier pipelines and are ignored.)
 // `n` is the number of sources that are integrated (a gated call passes its estimate).
 inline int small_mask(int64_t n, int nlenses) {
   const int k = tuning_get(TUNE_EXT_VARIANTS);
-  if (k >= 0) return k & 63;
+  if (k >= 0) return k & 127;
   // measured on one B200 at npts_limb = 200 (batches of 3 000 ... 100 000)
   int m = 0;
   if (n <= (nlenses == 2 ? 16384 : 8192)) m |= 6 | 8;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(NT) k_open(ExtCfg cfg, ExtBuf b, LensConst L) 
 // listed sources are few (the limb crosses a caustic) and their processing is a chain of dependent reads:
 // from shared memory, and spread over every SM instead of count / 128 CTAs.
 inline size_t open_stage_bytes(int NP, int D) {
-  return (size_t)NP * D * 17 + (size_t)(D * MAXPARTS + MAXSEG) * sizeof(Seg) + 64 + 64;
+  return (size_t)NP * D * 17 + (size_t)(D * MAXPARTS + MAXSEG) * sizeof(Seg) + 64 + 128 + 64;
 }
 template <int D>
 __global__ void __launch_bounds__(32) k_open_staged(ExtCfg cfg, ExtBuf b, LensConst L) {
@@ -116,7 +117,8 @@ __global__ void __launch_bounds__(32) k_open_staged(ExtCfg cfg, ExtBuf b, LensCo
   Seg* tp = (Seg*)(im + n);
   Seg* parts = tp + D * MAXPARTS;
   int* tn = (int*)(parts + MAXSEG);
-  uint8_t* f = (uint8_t*)(tn + 16);
+  int8_t* chain_mem = (int8_t*)(tn + 16);
+  uint8_t* f = (uint8_t*)(chain_mem + 128);
   const int count = *b.open_count;
   for (int g = blockIdx.x; g < count; g += gridDim.x) {
     const int64_t s = b.open_list[g];
@@ -136,10 +138,122 @@ __global__ void __launch_bounds__(32) k_open_staged(ExtCfg cfg, ExtBuf b, LensCo
       }
     }
     __syncwarp();
-    const TrackStage st{re, im, f, nullptr};
+    const TrackStage st{re, im, f, nullptr, D, 1};
     const Tracks T{cfg, b, s, &st, nullptr};
-    const int np = build_parts_warp<D>(cfg, T, b.sw_closed[s], tp, tn, parts, lane);
-    if (lane == 0) contours_body<D, false>(cfg, b, L, s, &st, true, parts, np);
+    const int np = build_parts_warp<D>(cfg, T, b.sw_closed[s] & ((1u << D) - 1u), tp, tn, parts, lane);
+    if (lane == 0) contours_body<D, false>(cfg, b, L, s, &st, true, parts, np, chain_mem);
+    __syncwarp();
+  }
+}
+// The open pass as built at the end of round 2: one warp per listed source, persistent, staging ONLY the tracks that
+// hold real images and are not closed (typically 2-4 of a triple lens's 10: the pair born at a fold and whatever the
+// matching tangled with it), track-major and renumbered 0..W-1 in track order -- the reference's segment order only
+// ever compares track indices, so the renumbering is invisible.  The two scans of a track are spread over the lanes:
+// a lane takes a limb point, decides start / end of a run from the point and its predecessor exactly as
+// track_parts does (ballots give the run boundaries in increasing order) and stores the chord length to the
+// predecessor; a lane per run then adds its run's chord lengths in limb order (the same additions as part_segment's
+// serial loop: same bits).  Lane 0 stitches and integrates on the copy.  Sources with wlo < W <= whi are taken by
+// this launch (the staging buffer holds whi tracks); a second launch takes the rest.
+inline size_t open_compact_bytes(int NP, int whi) {
+  return (size_t)NP * whi * 25 + (size_t)(whi * MAXPARTS + MAXSEG) * sizeof(Seg) + (size_t)whi * MAXPARTS * 4 + 128 + 128 + 64;
+}
+template <int D>
+__global__ void __launch_bounds__(32) k_open_compact(ExtCfg cfg, ExtBuf b, LensConst L, int wlo, int whi) {
+  extern __shared__ __align__(16) double stage_mem[];
+  const int lane = threadIdx.x, NP = cfg.NP, n = NP * whi;
+  double* re = stage_mem;
+  double* im = re + n;
+  double* dl = im + n;                              // dl[t * NP + p] = |pt(t, p) - pt(t, p - 1)|
+  Seg* tp = (Seg*)(dl + n);
+  Seg* parts = tp + whi * MAXPARTS;
+  int16_t* lo = (int16_t*)(parts + MAXSEG);         // [whi][MAXPARTS]
+  int16_t* hi = lo + whi * MAXPARTS;
+  int* tn = (int*)(hi + whi * MAXPARTS);            // [whi] (<= 16 tracks)
+  int8_t* chain_mem = (int8_t*)(tn + 16);           // 128 bytes: the active chain's pieces
+  uint8_t* f = (uint8_t*)(chain_mem + 128);
+  const int count = *b.open_count;
+  for (int g = blockIdx.x; g < count; g += gridDim.x) {
+    const int64_t s = b.open_list[g];
+    const unsigned work = b.sw_closed[s] >> 16;
+    const int W = __popc(work);
+    if (W <= wlo || W > whi) continue;              // warp-uniform
+    // ---- gather the W tracks through order and permutation
+    const uint64_t* perm = b.perm + s * NP;
+    for (int pth = lane; pth < NP; pth += 32) {
+      const int slot = b.order[s * NP + pth];
+      const uint64_t pm = perm[pth];
+      const uint32_t fw = b.fw[s * NP + slot];
+      const double2* col = b.z + (s * NP + slot) * D;
+      unsigned wk = work;
+      for (int t = 0; t < W; ++t) {
+        const int tr = __ffs(wk) - 1; wk &= wk - 1;
+        const int j = (int)((pm >> (4 * tr)) & 15u);
+        const double2 v = col[j];
+        re[t * NP + pth] = v.x; im[t * NP + pth] = v.y;
+        f[t * NP + pth] = (uint8_t)((fw >> (3 * j)) & 7u);
+      }
+    }
+    __syncwarp();
+    // ---- runs of real images of one parity without jumps (track_parts, lane per limb point)
+    for (int t = 0; t < W; ++t) {
+      int np_ = 0, nend = 0;
+      for (int base = 0; base <= NP; base += 32) {
+        const int p = base + lane;
+        bool start = false, end = false;
+        if (p <= NP) {
+          const int pc = p < NP ? p : NP - 1, pq = p > 0 ? p - 1 : 0;
+          const uint8_t fc = f[t * NP + pc], fq = f[t * NP + pq];
+          const cd zc = mk(re[t * NP + pc], im[t * NP + pc]), zq = mk(re[t * NP + pq], im[t * NP + pq]);
+          const bool real = p < NP && (fc & 1), prev_real = p > 0 && (fq & 1);
+          const double par = real ? ((fc & 4) ? 0.0 : ((fc & 2) ? 1.0 : -1.0)) : 0.0;
+          const double prev_par = prev_real ? ((fq & 4) ? 0.0 : ((fq & 2) ? 1.0 : -1.0)) : 0.0;
+          const cd z = real ? zc : mk(0, 0), prev_z = prev_real ? zq : mk(0, 0);
+          if (p == 0) start = real;
+          else if (p == NP) end = prev_real;
+          else {
+            const double dm = (real ? 1.0 : 0.0) - (prev_real ? 1.0 : 0.0);
+            const bool change = norm2(z - prev_z) > 0.01 || par != prev_par || dm != 0.0;
+            start = change && dm >= 0.0;
+            end = change && dm <= 0.0;
+            dl[t * NP + p] = sqrt(norm2(zc - zq));
+          }
+        }
+        unsigned sm = __ballot_sync(0xffffffffu, start), em = __ballot_sync(0xffffffffu, end);
+        if (lane == 0) {
+          while (em && nend < MAXPARTS) { hi[t * MAXPARTS + nend++] = (int16_t)(base + __ffs(em) - 1); em &= em - 1; }
+          while (sm && np_ < MAXPARTS) { lo[t * MAXPARTS + np_++] = (int16_t)(base + __ffs(sm) - 1); sm &= sm - 1; }
+        }
+      }
+      if (lane == 0) tn[t] = np_ < nend ? np_ : nend;
+    }
+    __syncwarp();
+    // ---- a lane per run: the segment record (part_segment)
+    for (int item = lane; item < W * MAXPARTS; item += 32) {
+      const int t = item / MAXPARTS, k = item - t * MAXPARTS;
+      if (k >= tn[t]) continue;
+      const int a = lo[item], e = hi[item];
+      Seg gsg;
+      gsg.track = -1; gsg.lo = (int16_t)a; gsg.hi = (int16_t)e; gsg.par = 0; gsg.len = 0.0;
+      if (!(e - a < 2 || (a == 0 && e == 0))) {
+        gsg.track = (int16_t)t;
+        const uint8_t fa = f[t * NP + a];
+        gsg.par = (fa & 4) ? 0 : ((fa & 2) ? 1 : -1);
+        double len = 0.0;
+        for (int p = a + 1; p < e; ++p) len += dl[t * NP + p];
+        gsg.len = len;
+      }
+      tp[item] = gsg;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      int np = 0;
+      const int nseg_max = 3 * (cfg.nl * cfg.nl + 1);
+      for (int i = W - 1; i >= 0 && np < nseg_max; --i)
+        for (int k = tn[i] - 1; k >= 0 && np < nseg_max; --k)
+          if (tp[i * MAXPARTS + k].track >= 0) parts[np++] = tp[i * MAXPARTS + k];
+      const TrackStage st{re, im, f, nullptr, 1, NP};
+      contours_body<D, false>(cfg, b, L, s, &st, true, parts, np, chain_mem);
+    }
     __syncwarp();
   }
 }
@@ -158,7 +272,8 @@ __global__ void __launch_bounds__(32) k_contours_staged(ExtCfg cfg, ExtBuf b, Le
   double* re = stage_mem;
   double* im = re + n;
   double* th = im + n;
-  uint8_t* f = (uint8_t*)(th + cfg.NP);
+  int8_t* chain_mem = (int8_t*)(th + cfg.NP);
+  uint8_t* f = (uint8_t*)(chain_mem + 128);
   for (int k = threadIdx.x; k < n; k += 32) {
     const int64_t g = (int64_t)k * cfg.S + s;    // k = p * D + track, same order as the global planes
     re[k] = b.sre[g]; im[k] = b.sim[g]; f[k] = b.sflg[g];
@@ -168,8 +283,8 @@ __global__ void __launch_bounds__(32) k_contours_staged(ExtCfg cfg, ExtBuf b, Le
       th[pth] = b.theta[s * cfg.NP + b.order[s * cfg.NP + pth]];
   __syncwarp();
   if (threadIdx.x == 0) {
-    const TrackStage st{re, im, f, th};
-    contours_body<D, GRAD>(cfg, b, L, s, &st);
+    const TrackStage st{re, im, f, th, D, 1};
+    contours_body<D, GRAD>(cfg, b, L, s, &st, false, nullptr, 0, chain_mem);
   }
 }
 template <int NL>
@@ -265,7 +380,19 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
     if (e != cudaSuccess) return cuda_rc(e);
     k_sweep<D><<<gs, NT, 0, st>>>(cfg, b);
     const size_t open_bytes = open_stage_bytes(cfg.NP, D);
-    if (open_bytes <= 200 * 1024 && !(cfg.small & 32)) {
+    const int tw = tuning_get(TUNE_OPEN_WSMALL);
+    const int wsmall = tw > 0 ? (tw < D ? tw : D) : 2;
+    if (!(cfg.small & 64) && open_compact_bytes(cfg.NP, D) <= 200 * 1024) {
+      // sources with at most wsmall tracks to look at first (small staging buffer, many warps per SM), then the rest
+      for (int pass = 0; pass < (wsmall < D ? 2 : 1); ++pass) {
+        const int wlo = pass == 0 ? 0 : wsmall, whi = (pass == 0 && wsmall < D) ? wsmall : D;
+        const size_t nb = open_compact_bytes(cfg.NP, whi);
+        if (nb > 48 * 1024) cudaFuncSetAttribute(k_open_compact<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)open_compact_bytes(cfg.NP, D));
+        const int64_t per_sm = (int64_t)(220 * 1024 / (nb + 1024));
+        const int64_t slots = 148 * (per_sm < 1 ? 1 : (per_sm > 24 ? 24 : per_sm));
+        k_open_compact<D><<<(unsigned)(cfg.S < slots ? cfg.S : slots), 32, nb, st>>>(cfg, b, L, wlo, whi);
+      }
+    } else if (open_bytes <= 200 * 1024 && !(cfg.small & 32)) {
       if (open_bytes > 48 * 1024) cudaFuncSetAttribute(k_open_staged<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)open_bytes);
       const int64_t per_sm = (int64_t)(220 * 1024 / (open_bytes + 1024));
       const int64_t slots = 148 * (per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm));
@@ -276,7 +403,7 @@ int run_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, cudaStream_t s
     return cuda_rc(cudaGetLastError());
   }
   k_tracks<D><<<gs, NT, 0, st>>>(cfg, b);
-  const size_t stage_bytes = (size_t)cfg.NP * D * 17 + (size_t)cfg.NP * 8 + 64;
+  const size_t stage_bytes = (size_t)cfg.NP * D * 17 + (size_t)cfg.NP * 8 + 128 + 64;
   if ((cfg.small & 2) && stage_bytes <= 200 * 1024) {
     if (stage_bytes > 48 * 1024) {
       cudaFuncSetAttribute(k_contours_staged<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);

@@ -76,7 +76,7 @@ struct ExtBuf {
   // One-pass uniform-disk path (sweep_body / open_body):
   uint64_t* perm;          // [S][NP]    4 bits per track: which image of limb point p (theta order) the track took
   double* sw_total;        // [S]        signed area of the closed tracks
-  uint32_t* sw_closed;     // [S]        mask of closed tracks
+  uint32_t* sw_closed;     // [S]        mask of closed tracks | mask of tracks with real images that are not closed << 16
   int32_t* open_list;      // [S]        sources (slots of this pass) whose open tracks still have to be stitched
   int32_t* open_count;     //            their number
   cb200_d2* vz; double* vP; double* vQ; uint8_t* vcid; double* vth;   // vth: optional theta per vertex   // [VMAX][S] limb-darkening vertex lists
@@ -679,7 +679,7 @@ __device__ void sweep_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
   }
   if (any_real & ~closed) {
     b.sw_total[s] = total;
-    b.sw_closed[s] = closed;
+    b.sw_closed[s] = closed | ((any_real & ~closed) << 16);   // high half: the tracks the open pass has to look at
     b.open_list[cb200_atomic_inc(b.open_count)] = (int32_t)s;
   } else {
     b.mag[src_index(b, s)] = fabs(total) * (1.0 / (3.14159265358979323846 * cfg.rho * cfg.rho));
@@ -693,13 +693,15 @@ struct Seg { int16_t track, lo, hi; int8_t par; double len; };
 
 // Optional shared-memory copy of one source's tracks ([p][track] planes), used for small batches:
 // the stitching logic is a chain of dependent reads, ~20x faster from shared memory than from L2.
-struct TrackStage { const double* re; const double* im; const uint8_t* f; const double* th; };
+// Element (track, p) lives at [p * sp + track * st]: sp = D, st = 1 for the [p][track] planes; the compact open pass
+// stages only the tracks it needs, track-major (sp = 1, st = NP), and numbers them 0..W-1.
+struct TrackStage { const double* re; const double* im; const uint8_t* f; const double* th; int sp, st; };
 
 struct Tracks {
   const ExtCfg& cfg; const ExtBuf& b; int64_t s; const TrackStage* st;
   const uint64_t* perm;    // non-null: no track arrays, read the source's record through order and permutation
   __device__ __forceinline__ cd pt(int track, int p) const {
-    if (st) return mk(st->re[p * cfg.D + track], st->im[p * cfg.D + track]);
+    if (st) return mk(st->re[p * st->sp + track * st->st], st->im[p * st->sp + track * st->st]);
     if (perm) {
       const cb200_d2 v = b.z[IZ(b.order[IS(p, s)], (int)((perm[p] >> (4 * track)) & 15u), s)];
       return mk(v.x, v.y);
@@ -712,18 +714,22 @@ struct Tracks {
     return b.theta[(int64_t)s * cfg.NP + b.order[(int64_t)s * cfg.NP + p]];
   }
   __device__ __forceinline__ uint8_t fl(int track, int p) const {
-    if (st) return st->f[p * cfg.D + track];
+    if (st) return st->f[p * st->sp + track * st->st];
     if (perm) return (uint8_t)((b.fw[IS(b.order[IS(p, s)], s)] >> (3 * (int)((perm[p] >> (4 * track)) & 15u))) & 7u);
     return b.sflg[(((int64_t)p * cfg.D + track) * cfg.S + s)];
   }
 };
 
 struct Chain {
-  // pieces live in a deque so that H-T / H-H connections can prepend (extended_source.py:445-492)
-  int8_t seg[64]; int8_t rev[64]; int head, tail;   // pieces [head, tail)
+  // pieces live in a deque so that H-T / H-H connections can prepend (extended_source.py:445-492).  The storage
+  // (2 x 64 bytes) is the caller's: a local array for the thread-per-source kernels, shared memory where one lane of a
+  // warp stitches (a lane's local array is spread over 128-byte lines it alone uses, which thrash L1)
+  int8_t* seg; int8_t* rev; int head, tail;   // pieces [head, tail)
   int npts;
-  __device__ void init(int sg, int n) { head = 32; tail = 33; seg[32] = (int8_t)sg; rev[32] = 0; npts = n; }
+  __device__ void init(int8_t* mem, int sg, int n) { seg = mem; rev = mem + 64; head = 32; tail = 33; seg[32] = (int8_t)sg; rev[32] = 0; npts = n; }
 };
+// a candidate segment seen as a chain of one piece (never materialised)
+struct OneSeg { int sg; int npts; };
 
 __device__ __forceinline__ int seg_n(const Seg& g) { return g.hi - g.lo; }
 __device__ __forceinline__ cd seg_pt(const Tracks& T, const Seg& g, int k, bool reversed) {
@@ -750,19 +756,25 @@ __device__ cd chain_pt(const Tracks& T, const Seg* segs, const Chain& c, int k, 
   }
   return mk(0, 0);
 }
+__device__ __forceinline__ cd chain_pt(const Tracks& T, const Seg* segs, const OneSeg& c, int k, bool from_tail) {
+  if (k < 0 || k >= c.npts) return mk(0, 0);
+  return seg_pt(T, segs[c.sg], from_tail ? c.npts - 1 - k : k, false);
+}
 __device__ __forceinline__ double chain_parity(const Seg* segs, const Chain& c) {
   const double p = segs[c.seg[c.head]].par;
   return c.rev[c.head] ? -p : p;
 }
+__device__ __forceinline__ double chain_parity(const Seg* segs, const OneSeg& c) { return segs[c.sg].par; }
 // the two points that define the direction at an end, connection point last; a near-duplicate end
 // vertex (< 1e-5) is skipped (extended_source.py:368-390)
-__device__ void end_line(const Tracks& T, const Seg* segs, const Chain& c, bool tail, cd& a, cd& bb) {
+template <class C>
+__device__ void end_line(const Tracks& T, const Seg* segs, const C& c, bool tail, cd& a, cd& bb) {
   const int t = c.npts - 1;
   const cd p0 = chain_pt(T, segs, c, 0, tail), p1 = chain_pt(T, segs, c, 1, tail);
   if (norm2(p1 - p0) > 1e-10 || t <= 1) { a = p1; bb = p0; }
   else { a = chain_pt(T, segs, c, 2, tail); bb = p1; }
 }
-__device__ bool connect_ok(const Tracks& T, const Seg* segs, const Chain& c1, const Chain& c2, int ctype) {
+__device__ bool connect_ok(const Tracks& T, const Seg* segs, const Chain& c1, const OneSeg& c2, int ctype) {
   const bool same = chain_parity(segs, c1) * chain_parity(segs, c2) > 0.0;
   if ((ctype < 2) != same) return false;
   cd a1, b1, a2, b2;
@@ -992,7 +1004,7 @@ __device__ int build_parts_warp(const ExtCfg& cfg, const Tracks& T, unsigned clo
 template <int D, bool GRAD = false>
 __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensConst& L, int64_t s,
                               const TrackStage* stage = nullptr, bool resume = false,
-                              const Seg* pre_parts = nullptr, int pre_nparts = 0) {
+                              const Seg* pre_parts = nullptr, int pre_nparts = 0, int8_t* chain_mem = nullptr) {
   if (s >= nsrc(cfg, b)) return;
   constexpr int NLG = D == 2 ? 1 : (D == 5 ? 2 : 3);
   GreenTangent<NLG> GT(L, cfg.rho);
@@ -1012,7 +1024,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
 
   // closed tracks: every image real and the track returns to its start (extended_source.py:290)
   unsigned closed = 0;
-  if (resume) { closed = b.sw_closed[s]; total = b.sw_total[s]; }
+  if (resume) { closed = b.sw_closed[s] & ((1u << D) - 1u); total = b.sw_total[s]; }
   for (int i = 0; i < D && !resume; ++i) {
     bool all_real = true;
 #pragma unroll 8
@@ -1052,21 +1064,22 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
     }
     // ---- stitch (extended_source.py:495-667): three rounds; the active chain starts from the
     // shortest remaining segment and grows by the closest admissible connection
-    bool alive[MAXSEG];
-    for (int k = 0; k < nparts_total; ++k) alive[k] = true;
+    static_assert(MAXSEG <= 32, "the live-segment set is one 32-bit mask");
+    unsigned alive = nparts_total >= 32 ? 0xffffffffu : (1u << nparts_total) - 1u;
+    int8_t chain_local[128];
+    int8_t* const cmem = chain_mem ? chain_mem : chain_local;
     int pool_size = nseg_max;                 // fixed-shape pool incl. empty slots, shrinks by one per round
     int max_in = 20;
     for (int round = 0; round < 3; ++round, max_in -= 2) {
       int a = -1;
       for (int k = 0; k < nparts_total; ++k)
-        if (alive[k] && parts[k].len != 0.0 && (a < 0 || parts[k].len < parts[a].len)) a = k;
+        if (((alive >> k) & 1u) && parts[k].len != 0.0 && (a < 0 || parts[k].len < parts[a].len)) a = k;
       --pool_size;
       if (a < 0) break;                       // only empty segments left: the remaining contours are empty
-      alive[a] = false;
-      Chain act; act.init(a, seg_n(parts[a]));
+      alive &= ~(1u << a);
+      Chain act; act.init(cmem, a, seg_n(parts[a]));
       for (int step = 0; step < max_in; ++step) {
-        int nreal = 0;
-        for (int k = 0; k < nparts_total; ++k) nreal += alive[k] ? 1 : 0;
+        const int nreal = __popc(alive);
         if (nreal == 0) break;
         const int nempty = pool_size - nreal;
         const cd ah = chain_pt(T, parts, act, 0, false), at = chain_pt(T, parts, act, 0, true);
@@ -1079,7 +1092,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
           double bd = 1e300; int bc = -1, bk = -1;
           for (int c = 0; c < 4; ++c)
             for (int k = 0; k < nparts_total; ++k) {
-              if (!alive[k]) continue;
+              if (!((alive >> k) & 1u)) continue;
               const cd mine = (c == 0 || c == 3) ? at : ah;
               const Seg& g = parts[k];
               const cd theirs = (c == 0 || c == 2) ? T.pt(g.track, g.lo) : T.pt(g.track, g.hi - 1);
@@ -1093,7 +1106,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
           if (nempty > 0) ahead = (dt0 < bd ? 2 * nempty : 0) + (dh0 < bd ? 2 * nempty : 0);
           // (rank counts real candidates already examined)
           if (rank + ahead >= 4) { exhausted = true; break; }
-          Chain other; other.init(bk, seg_n(parts[bk]));
+          const OneSeg other{bk, seg_n(parts[bk])};
           if (connect_ok(T, parts, act, other, bc)) {
             const int n2 = seg_n(parts[bk]);
             if (bc == 0) { act.seg[act.tail] = (int8_t)bk; act.rev[act.tail] = 0; ++act.tail; }
@@ -1101,7 +1114,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
             else if (bc == 2) { --act.head; act.seg[act.head] = (int8_t)bk; act.rev[act.head] = 1; }
             else { act.seg[act.tail] = (int8_t)bk; act.rev[act.tail] = 1; ++act.tail; }
             act.npts += n2;
-            alive[bk] = false;
+            alive &= ~(1u << bk);
             merged = true;
           }
           lastd = bd; lastc = bc; lastk = bk; ++rank;

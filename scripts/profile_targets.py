@@ -39,6 +39,8 @@ elif target == "map":
         cb.mag_point_source_map(-1.5, -1.5, 3.0 / 9999, 3.0 / 9999, 10_000, 10_000, rows=(4000, 6000), walk=False, **bench.HP2)
 elif target in ("c4", "c4grad"):
     n = 100_000
+    if os.environ.get("OPEN_WSMALL"):
+        L.caustics_set_tuning(b"open_wsmall", int(os.environ["OPEN_WSMALL"]))
     if os.environ.get("EXT_MASK"):
         L.caustics_set_tuning(b"ext_variants", int(os.environ["EXT_MASK"]))
     w = torch.from_numpy(np.linspace(-2, 2, n) + 0.1j).cuda()

@@ -34,6 +34,8 @@ def timeit(fn, reps=3):
 
 
 def main():
+    if os.environ.get("OPEN_WSMALL"):
+        L.caustics_set_tuning(b"open_wsmall", int(os.environ["OPEN_WSMALL"]))
     masks = [int(x) for x in os.environ.get("MASKS", "-1,0,2,8,10").split(",")]
     for nl in (3, 2):
         if nl == 3:
