@@ -87,11 +87,13 @@ __global__ void __launch_bounds__(NT, (NL == 3 && !COMP) ? 4 : 1) k_round_solve(
 }
 template <int D>
 __global__ void __launch_bounds__(NT) k_tracks(ExtCfg cfg, ExtBuf b) {
-  tracks_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
+  __shared__ double2 stage[D > 5 ? D * NT : 1];
+  tracks_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x, stage + (D > 5 ? threadIdx.x : 0), NT);
 }
 template <int D>
 __global__ void __launch_bounds__(NT, SW_MINB) k_sweep(ExtCfg cfg, ExtBuf b) {
-  sweep_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x);
+  __shared__ double2 stage[D > 5 ? D * NT : 1];
+  sweep_body<D>(cfg, b, (int64_t)blockIdx.x * NT + threadIdx.x, stage + (D > 5 ? threadIdx.x : 0), NT);
 }
 // the sources sweep_body listed: open tracks -> segments -> stitched contours, added to the closed-track sum
 template <int D>

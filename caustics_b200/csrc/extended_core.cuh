@@ -518,6 +518,7 @@ struct TrackWalk {
   double cre[D], cim[D];                  // previous column in track order
   double nzr[D], nzi[D]; uint32_t nfw;    // raw column of the NEXT limb point, fetched while the current one is matched
   int nslot, slot;
+  cb200_d2* stg; int sstride;             // this thread's column in shared memory, [image * sstride] (dynamic index `best`)
   __device__ __forceinline__ void fetch(int p) {
     nslot = b.order[IS(p, s)];
     const cb200_d2* col = b.z + IZ(nslot, 0, s);
@@ -525,7 +526,8 @@ struct TrackWalk {
 #pragma unroll
     for (int j = 0; j < D; ++j) { const cb200_d2 v = col[j]; nzr[j] = v.x; nzi[j] = v.y; }
   }
-  __device__ __forceinline__ TrackWalk(const ExtCfg& c, const ExtBuf& bb, int64_t ss) : cfg(c), b(bb), s(ss) { fetch(0); }
+  __device__ __forceinline__ TrackWalk(const ExtCfg& c, const ExtBuf& bb, int64_t ss, cb200_d2* stage, int stride)
+      : cfg(c), b(bb), s(ss), stg(stage), sstride(stride) { fetch(0); }
   // WRITE_BACK: a duplicate's offset is also stored into the source's record, so that later random access
   // through the permutation (Tracks, perm mode) sees the value the matching saw
   template <bool WRITE_BACK>
@@ -565,6 +567,10 @@ struct TrackWalk {
       }
     }
     }
+    if (D > 5) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) stg[j * sstride] = make_cb200_d2(zr[j], zi[j]);
+    }
     unsigned used = 0;
     uint64_t perm = 0;
 #pragma unroll
@@ -586,10 +592,17 @@ struct TrackWalk {
       }
       used |= 1u << best;
       perm |= (uint64_t)best << (4 * i);
-      double r = 0, m = 0;
+      // the chosen image by a shared-memory read at a dynamic index (a D-way register select costs 4 D + D
+      // instructions per track: a quarter of this kernel)
+      if (D > 5) {
+        const cb200_d2 v = stg[best * sstride];
+        vr[i] = v.x; vi[i] = v.y;
+      } else {   // a handful of images: the register select is as cheap (measured: binary lens 6.63 vs 6.71 ms)
+        double r = 0, m = 0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) if (k == best) { r = zr[k]; m = zi[k]; }
-      vr[i] = r; vi[i] = m;
+        for (int k = 0; k < D; ++k) if (k == best) { r = zr[k]; m = zi[k]; }
+        vr[i] = r; vi[i] = m;
+      }
       vf[i] = (uint8_t)((fw >> (3 * best)) & 7u);
     }
     return perm;
@@ -602,9 +615,9 @@ struct TrackWalk {
 
 // the theta-ordered tracks as arrays (consumed by contours_body; limb-darkened, tangent and export calls)
 template <int D>
-__device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
+__device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s, cb200_d2* stage, int sstride) {
   if (s >= nsrc(cfg, b)) return;
-  TrackWalk<D> W(cfg, b, s);
+  TrackWalk<D> W(cfg, b, s, stage, sstride);
   for (int p = 0; p < cfg.NP; ++p) {
     double vr[D], vi[D];
     uint8_t vf[D];
@@ -628,11 +641,11 @@ __device__ void tracks_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
 // contours_body forms them (per track in theta order, closed tracks in track order, then the stitched
 // contours), so the two paths agree bit for bit.
 template <int D>
-__device__ void sweep_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s) {
+__device__ void sweep_body(const ExtCfg& cfg, const ExtBuf& b, int64_t s, cb200_d2* stage, int sstride) {
   if (s >= nsrc(cfg, b)) return;
   constexpr unsigned FULL = (1u << D) - 1u;
   const int NP = cfg.NP;
-  TrackWalk<D> W(cfg, b, s);
+  TrackWalk<D> W(cfg, b, s, stage, sstride);
   double sum[D];
   unsigned all_real = FULL, any_real = 0, f0 = 0;
   uint64_t* perm = b.perm + IS(0, s);

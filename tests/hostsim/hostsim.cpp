@@ -156,11 +156,13 @@ static void ext_pipeline(const ExtCfg& cfg, ExtBuf b, const LensConst& L, int64_
   if (!cfg.ld && !cfg.tracks) {
     // plain uniform disk: one pass, then the listed caustic-crossing sources
     *b.open_count = 0;
-    for (int64_t s = 0; s < ns; ++s) sweep_body<D>(cfg, b, s);
+    cb200_d2 stage[D];
+    for (int64_t s = 0; s < ns; ++s) sweep_body<D>(cfg, b, s, stage, 1);
     for (int32_t g = 0; g < *b.open_count; ++g) contours_body<D, false>(cfg, b, L, b.open_list[g], nullptr, true);
     return;
   }
-  for (int64_t s = 0; s < ns; ++s) tracks_body<D>(cfg, b, s);
+  cb200_d2 stage2[D];
+  for (int64_t s = 0; s < ns; ++s) tracks_body<D>(cfg, b, s, stage2, 1);
   for (int64_t s = 0; s < ns; ++s) {
     if (b.grad) contours_body<D, true>(cfg, b, L, s); else contours_body<D>(cfg, b, L, s);
   }
