@@ -335,8 +335,80 @@ __device__ __forceinline__ unsigned cb200_warp_max(unsigned v) { return __reduce
 // widths (rare) are ranked by theta.  Beyond 32 * SEL_REG limb points: n passes over shared memory, a butterfly
 // arg-max per pass (this is also what a one-lane host "warp" runs).
 constexpr int SEL_REG = 8;         // widths per lane held in registers: cur <= 32 * SEL_REG, else the generic passes
+#ifndef CB200_HOSTSIM
+// The same ranking with each lane's widths SORTED once per round (a compare-exchange network on the order-preserving
+// 64-bit keys: bit pattern + 1, 0 = no entry): a pass then only compares the lanes' heads -- two redux.sync and a
+// ballot -- and the winner shifts its registers, instead of every lane rescanning its R widths for every pick
+// (~45 warp instructions per pick against ~120).  Equal widths inside one lane (the theta tie-break of the reference
+// would have to order them) are detected by the network; the caller then takes the scanning form, which handles them.
+// Equal widths in different lanes are ranked by theta as before.  Returns false (nothing written) on an in-lane tie.
+template <int R>
+__device__ __forceinline__ bool refine_select_sorted(int cur, int n, int N0, const double* dval, const double* theta,
+                                                     uint16_t* left, int lane) {
+  unsigned kh[R], kl[R];
+  int ix[R];
+  bool tie = false;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int i = lane + k * 32;
+    const bool ok = i < cur && i != N0 - 1;
+    const double d = ok ? dval[i] : 0.0;
+    unsigned long long key = ok ? (unsigned long long)__double_as_longlong(d) + 1ull : 0ull;
+    kh[k] = (unsigned)(key >> 32); kl[k] = (unsigned)key; ix[k] = ok ? i : 0;
+  }
+  auto cex = [&](int a, int c) {      // descending
+    const bool lt = kh[a] < kh[c] || (kh[a] == kh[c] && kl[a] < kl[c]);
+    const unsigned th = kh[a], tl = kl[a]; const int ti = ix[a];
+    kh[a] = lt ? kh[c] : th; kl[a] = lt ? kl[c] : tl; ix[a] = lt ? ix[c] : ti;
+    kh[c] = lt ? th : kh[c]; kl[c] = lt ? tl : kl[c]; ix[c] = lt ? ti : ix[c];
+  };
+  if (R == 6) {
+    cex(0, 5); cex(1, 3); cex(2, 4); cex(1, 2); cex(3, 4); cex(0, 3); cex(2, 5); cex(0, 1); cex(2, 3); cex(4, 5); cex(1, 2); cex(3, 4);
+  } else {
+    static_assert(R == 6 || R == 8, "networks for 6 and 8 keys");
+    cex(0, 1); cex(2, 3); cex(4, 5); cex(6, 7); cex(0, 2); cex(1, 3); cex(4, 6); cex(5, 7); cex(1, 2); cex(5, 6);
+    cex(0, 4); cex(3, 7); cex(1, 5); cex(2, 6); cex(1, 4); cex(3, 6); cex(2, 4); cex(3, 5); cex(3, 4);
+  }
+  // equal keys end up next to each other
+#pragma unroll
+  for (int k = 0; k + 1 < R; ++k) tie = tie || (kh[k] == kh[k + 1] && kl[k] == kl[k + 1] && (kh[k] | kl[k]) != 0u);
+  if (__any_sync(0xffffffffu, tie)) return false;
+  for (int r = 0; r < n; ++r) {
+    const unsigned hi = kh[0];
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned lo = hi == mh ? kl[0] : 0u;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+    bool win = hi == mh && lo == ml;
+    unsigned winners = __ballot_sync(0xffffffffu, win);
+    if (winners & (winners - 1u)) {          // several lanes hold this width: the one latest in theta
+      const double th = win ? theta[ix[0]] : -1e300;
+      double mth = th;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) mth = fmax(mth, __shfl_xor_sync(0xffffffffu, mth, off));
+      win = win && th == mth;
+      winners = __ballot_sync(0xffffffffu, win);
+    }
+    const int wl = __ffs(winners) - 1;
+    const int pick = __shfl_sync(0xffffffffu, ix[0], wl);
+    if (lane == 0) left[r] = (uint16_t)pick;
+    if (lane == wl) {
+#pragma unroll
+      for (int k = 0; k + 1 < R; ++k) { kh[k] = kh[k + 1]; kl[k] = kl[k + 1]; ix[k] = ix[k + 1]; }
+      kh[R - 1] = 0u; kl[R - 1] = 0u;
+    }
+  }
+  return true;
+}
+#endif
 __device__ __forceinline__ void refine_select_warp(int cur, int n, int N0, uint16_t* next, const double* dval, double* theta,
                                                    uint16_t* left, uint16_t* right, int lane) {
+#ifndef CB200_HOSTSIM
+  bool done = false;
+  if (cur <= 32 * 6) done = refine_select_sorted<6>(cur, n, N0, dval, theta, left, lane);
+  else if (cur <= 32 * 8) done = refine_select_sorted<8>(cur, n, N0, dval, theta, left, lane);
+  if (done) {
+  } else
+#endif
   if (cur <= EXT_WARP * SEL_REG) {
     double dv[SEL_REG];
 #pragma unroll
