@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(32) k_contours_staged(ExtCfg cfg, ExtBuf b, Le
     const int64_t g = (int64_t)k * cfg.S + s;    // k = p * D + track, same order as the global planes
     re[k] = b.sre[g]; im[k] = b.sim[g]; f[k] = b.sflg[g];
   }
-  if (b.vth || b.grad)
+  if (b.vth)
     for (int pth = threadIdx.x; pth < cfg.NP; pth += 32)
       th[pth] = b.theta[s * cfg.NP + b.order[s * cfg.NP + pth]];
   __syncwarp();

@@ -794,7 +794,7 @@ struct Tracks {
     return mk(b.sre[(((int64_t)p * cfg.D + track) * cfg.S + s)], b.sim[(((int64_t)p * cfg.D + track) * cfg.S + s)]);
   }
   __device__ __forceinline__ double th(int p) const {
-    if (!b.vth && !b.grad) return 0.0;
+    if (!b.vth) return 0.0;
     if (st) return st->th[p];
     return b.theta[(int64_t)s * cfg.NP + b.order[(int64_t)s * cfg.NP + p]];
   }
@@ -901,26 +901,30 @@ constexpr int NGRAD = 8;
 template <int NL>
 struct GreenTangent {
   const LensConst& L;
-  double rho;
+  double inv_rho; cd wc;    // 1 / source radius, source centre (lens frame)
   double d[NGRAD];          // tangent of the current contour's area
   cd z0, z1, zp, zc;        // first two vertices; previous and current vertex
-  double th0, th1, thc;
   int cnt;
-  __device__ GreenTangent(const LensConst& L_, double rho_) : L(L_), rho(rho_) {}
+  __device__ GreenTangent(const LensConst& L_, double rho_, cd wc_) : L(L_), inv_rho(1.0 / rho_), wc(wc_) {}
   __device__ void start() {
 #pragma unroll
     for (int k = 0; k < NGRAD; ++k) d[k] = 0.0;
     cnt = 0;
   }
-  // vertex z (limb angle th) with neighbours zprev, znext
-  __device__ void vertex(cd z, double th, cd zprev, cd znext) {
+  // vertex z with neighbours zprev, znext.  The limb direction e^{i theta} that d w / d rho needs is read off the
+  // vertex itself: z solves lens_eq(z) = wc + rho e^{i theta}, and lens_eq(z) = z - sum_j eps_j u_j comes for two
+  // FMAs per lens from the u_j the step forms anyway (instead of two dependent, uncoalesced loads of the limb
+  // angle through the theta order and a sincos per vertex; it differs from the sampled direction by the root's
+  // residual / rho, ~1e-13)
+  __device__ void vertex(cd z, cd zprev, cd znext) {
     const cd zb = conj(z);
-    cd u[3], g = mk(0, 0);
+    cd u[3], g = mk(0, 0), wz = z;
     constexpr int M = NL == 1 ? 1 : NL;
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       u[j] = crecip(NL == 1 ? zb : zb - conj(L.r[j]));
       g = g + (NL == 1 ? 1.0 : L.eps[j]) * (u[j] * u[j]);
+      wz = wz - (NL == 1 ? 1.0 : L.eps[j]) * u[j];
     }
     const double den = 1.0 / (1.0 - norm2(g));
     const double wy = 0.5 * (znext.im - zprev.im), wx = 0.5 * (znext.re - zprev.re);
@@ -928,8 +932,7 @@ struct GreenTangent {
       const cd dz = den * (g * conj(Ft) - Ft);
       d[k] += dz.re * wy - dz.im * wx;
     };
-    double sn, cs;
-    sincos(th, &sn, &cs);
+    const double cs = inv_rho * (wz.re - wc.re), sn = inv_rho * (wz.im - wc.im);
     acc(5, mk(-1.0, 0.0));
     acc(6, mk(0.0, -1.0));
     acc(7, mk(-cs, -sn));
@@ -946,19 +949,19 @@ struct GreenTangent {
       }
     }
   }
-  __device__ void add(cd z, double th) {
-    if (cnt == 0) { z0 = z; th0 = th; }
-    else if (cnt == 1) { z1 = z; th1 = th; }
-    else vertex(zc, thc, zp, z);
+  __device__ void add(cd z) {
+    if (cnt == 0) z0 = z;
+    else if (cnt == 1) z1 = z;
+    else vertex(zc, zp, z);
     zp = cnt == 0 ? z : zc;
-    zc = z; thc = th;
+    zc = z;
     ++cnt;
   }
   // closes the polygon (the reference appends the first point again, :724-725) and adds parity * tangent to out
   __device__ void close(double par, double (&out)[NGRAD]) {
     if (cnt >= 2) {
-      vertex(zc, thc, zp, z0);        // last vertex: neighbours (previous, first)
-      vertex(z0, th0, zc, z1);        // first vertex: neighbours (last, second)
+      vertex(zc, zp, z0);             // last vertex: neighbours (previous, first)
+      vertex(z0, zc, z1);             // first vertex: neighbours (last, second)
     }
 #pragma unroll
     for (int k = 0; k < NGRAD; ++k) out[k] += par * d[k];
@@ -1092,7 +1095,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
                               const Seg* pre_parts = nullptr, int pre_nparts = 0, int8_t* chain_mem = nullptr) {
   if (s >= nsrc(cfg, b)) return;
   constexpr int NLG = D == 2 ? 1 : (D == 5 ? 2 : 3);
-  GreenTangent<NLG> GT(L, cfg.rho);
+  GreenTangent<NLG> GT(L, cfg.rho, GRAD ? source_centre(cfg, b, L, s) : mk(0, 0));
   double dtot[NGRAD];
   if (GRAD) {
 #pragma unroll
@@ -1126,14 +1129,22 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
     }
     if (!cfg.ld) {
       G.start();
+      if (!GRAD) {
 #pragma unroll 8
-      for (int p = 0; p < NP; ++p) G.add(T.pt(i, p));
-      total += par * G.close();
-      if (GRAD) {
+        for (int p = 0; p < NP; ++p) G.add(T.pt(i, p));
+      } else {
+        // area and tangent in one pass, the next vertex in flight while this one's implicit-function step runs
         GT.start();
-        for (int p = 0; p < NP; ++p) GT.add(T.pt(i, p), T.th(p));
+        cd zn = T.pt(i, 0);
+        for (int p = 0; p < NP; ++p) {
+          const cd z = zn;
+          if (p + 1 < NP) zn = T.pt(i, p + 1);
+          G.add(z);
+          GT.add(z);
+        }
         GT.close(par, dtot);
       }
+      total += par * G.close();
     }
   }
 
@@ -1219,7 +1230,7 @@ __device__ void contours_body(const ExtCfg& cfg, const ExtBuf& b, const LensCons
           const cd z = T.pt(g.track, pidx);
           if (emit) E.add(z, T.th(pidx));
           G.add(z);
-          if (GRAD) GT.add(z, T.th(pidx));
+          if (GRAD) GT.add(z);
         }
       }
       if (emit) E.close(par);
