@@ -315,9 +315,10 @@ int caustics_peer_close(void* ptr);
 int caustics_peer_enable(int peer_device);
 
 /* ---- launch-shape overrides for tests and experiments ---------------------------------------
- * key in {"grid_run", "path_run", "grid_extrap", "ext_variants", "open_wsmall"}; value -1 restores the
+ * key in {"grid_run", "path_run", "grid_extrap", "ext_variants", "open_wsmall", "host_slots", "host_chunk_log2"}; value -1 restores the
  * launcher's own rule.  ext_variants: phase-variant mask of the extended-source pipeline (csrc/extended.cu);
- * open_wsmall: sources with at most this many marked tracks go to the first open-pass launch (default 2).  (These replace environment variables: nothing in the library calls getenv.) */
+ * open_wsmall: sources with at most this many marked tracks go to the first open-pass launch (default 2);
+ * host_slots (1..8, default 4) / host_chunk_log2 (10..24, default 15): shape of the host-buffer pipeline.  (These replace environment variables: nothing in the library calls getenv.) */
 int caustics_set_tuning(const char* key, int value);
 
 /* ---- measurement aid -----------------------------------------------------------------------
