@@ -259,8 +259,10 @@ __global__ void __launch_bounds__(32) k_open_compact(ExtCfg cfg, ExtBuf b, LensC
     __syncwarp();
   }
 }
+// the tangent variant is memory-latency bound (long_scoreboard on top): 5 CTAs/SM (96 registers) 3.19 ms on C4, against
+// 3.72 unbounded (164 registers, 3 CTAs), 3.5 with 4, 3.67 with 6, 3.81 with 8; the plain variant does not care
 template <int D, bool GRAD>
-__global__ void __launch_bounds__(NT) k_contours(ExtCfg cfg, ExtBuf b, LensConst L) {
+__global__ void __launch_bounds__(NT, GRAD ? 5 : 1) k_contours(ExtCfg cfg, ExtBuf b, LensConst L) {
   contours_body<D, GRAD>(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
 // small batches: one warp per source; the lanes copy the source's tracks into shared memory, lane 0

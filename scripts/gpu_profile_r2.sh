@@ -30,7 +30,7 @@ for w in $WHAT; do
       cap k_round_select k_round_select c4 1
       cap k_round_solve k_round_solve c4 1
       cap k_sweep k_sweep c4 0
-      cap k_open_staged k_open_staged c4 0
+      cap k_open_compact k_open_compact c4 0
       cap k_contours_grad k_contours c4grad 0
       cap k_tracks k_tracks c4grad 0
       cap k_ld_pq k_ld_pq c3 1 ;;
