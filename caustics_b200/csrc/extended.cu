@@ -76,8 +76,13 @@ __global__ void __launch_bounds__(NT) k_limb_walk_single(ExtCfg cfg, ExtBuf b, L
   limb_walk_single_body(cfg, b, L, (int64_t)blockIdx.x * NT + threadIdx.x);
 }
 // the refinement: a selection kernel + a solve kernel per round
+// the selection streams 3.6 KB of state per source and waits on it (long_scoreboard 6.9 warps per issue at 36 warps/SM):
+// full occupancy (32 registers) 0.146 ms per launch on C4 against 0.156 at 48 warps and 0.170 at 36
+#ifndef SEL_MINB
+#define SEL_MINB 16
+#endif
 template <int D>
-__global__ void __launch_bounds__(NT) k_round_select(ExtCfg cfg, ExtBuf b, int round) {
+__global__ void __launch_bounds__(NT, SEL_MINB) k_round_select(ExtCfg cfg, ExtBuf b, int round) {
   round_select_body<D>(cfg, b, round, threadIdx.x & 31, (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5));
 }
 template <int NL, bool COMP>
