@@ -24,6 +24,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <mutex>
 
 #include "../../include/caustics_b200.h"
 #include "extended_core.cuh"
@@ -58,6 +59,9 @@ inline int small_mask(int64_t n, int nlenses) {
   if (n <= (nlenses == 2 ? 16384 : 8192)) m |= 6 | 8;
   return m;
 }
+
+// un-gated uniform-disk calls of at least this many sources run as two windows on two streams (split_rule below)
+constexpr int64_t SPLIT_MIN = 32768;
 
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUSTICS_ERR_CUDA_BASE + (int)e; }
 
@@ -447,7 +451,8 @@ size_t caustics_ext_workspace_bytes(int64_t n, int nlenses, int npts_limb, int l
   // a uniform-disk workspace serves the tangent and contour-export entry points too (they keep the image
   // tracks as arrays) unless the caller says it will only ask for magnifications
   c.tracks = (limb_darkening & CAUSTICS_WS_MAG_ONLY) ? 0 : 1;
-  return make_layout(c).total;
+  // + the alignment slack of a second window (ext_driver cuts large un-gated calls in two)
+  return make_layout(c).total + (n >= SPLIT_MIN ? 64 * 1024 : 0);
 }
 
 size_t caustics_mag_workspace_bytes(int64_t n, int64_t max_full, int nlenses, int npts_limb, int limb_darkening,
@@ -472,6 +477,39 @@ int64_t capacity_for(const ExtCfg& proto, int64_t n, size_t bytes) {
   int64_t lo = 1, hi = n;               // fits(lo), !fits(hi)
   while (hi - lo > 1) { const int64_t mid = lo + (hi - lo) / 2; (fits(mid) ? lo : hi) = mid; }
   return lo;
+}
+
+// Two windows of one un-gated call on two streams.  The phases of the pipeline are unlike -- FP64-bound solves, a
+// memory-bound selection, latency-bound matching and stitching -- and a single stream runs them one after the other, each
+// with its own idle resource (and the limb walk of 10^5 triple-lens sources with a second wave that fills 3/4 of the
+// machine).  Cut into two windows with workspaces of their own, on the caller's stream and on a side stream (fork / join
+// by events, so the call stays stream-ordered for the caller and can be captured in a CUDA graph), the windows' phases
+// overlap.  Sources are independent: the results are bit for bit those of the single window.
+constexpr int SIDE_MAXDEV = 16, SIDE_MAXWIN = 4;
+struct Side {
+  std::mutex mu; bool init = false;
+  cudaStream_t st[SIDE_MAXWIN - 1] = {}; cudaEvent_t fork = nullptr, join[SIDE_MAXWIN - 1] = {};
+};
+Side g_side[SIDE_MAXDEV];
+// The windows of an un-gated call: *first = length of the first one (on the caller's stream), the others share the
+// rest equally.  Returns their number (1 = one window).  Rule (measured, profiles/r02_ext_variants.txt): uniform disk,
+// binary or triple lens, at least 32 768 sources -> two windows, the first max(n / 2, min(65 536, n - 16 384)) long;
+// three and four windows are no better.  caustics_set_tuning("ext_split", nA) / ("ext_windows", K) override.
+inline int split_rule(int64_t n, const ExtCfg& cfg, int gate, int64_t* first) {
+  if (gate || cfg.ld || cfg.nl == 1) return 1;
+  const int t = tuning_get(TUNE_EXT_SPLIT), kw = tuning_get(TUNE_EXT_WINDOWS);
+  int K = 2;
+  if (kw >= 1) K = kw < SIDE_MAXWIN ? kw : SIDE_MAXWIN;
+  else if (t == 0 || (t < 0 && n < SPLIT_MIN)) K = 1;
+  if (K == 1 || n < 2 * K * NT) return 1;
+  int64_t f = (n + K - 1) / K;
+  if (K == 2 && t < 0 && kw < 1) {
+    const int64_t g = n - 16384 < 65536 ? n - 16384 : 65536;
+    if (g > f) f = g;
+  }
+  if (t > 0 && t < n) f = t;
+  *first = ((f + NT - 1) / NT) * NT;
+  return *first < n ? K : 1;
 }
 
 // Shared driver.
@@ -551,6 +589,57 @@ int ext_driver(const void* w, double* mag, double* grad, uint8_t* test_out, int6
     b.list = list; b.count = count;
   } else if (gate == 2) {
     b.list = ext_list; b.count = ext_count;
+  }
+  int64_t first = 0;
+  const int K = split_rule(n, cfg, gate, &first);
+  if (K > 1) {
+    int64_t off[SIDE_MAXWIN + 1];
+    off[0] = 0; off[1] = first;
+    const int64_t rest = (((n - first) / (K - 1) + NT - 1) / NT) * NT;
+    for (int i = 2; i <= K; ++i) off[i] = off[i - 1] + rest < n ? off[i - 1] + rest : n;
+    off[K] = n;
+    ExtCfg cw[SIDE_MAXWIN]; Layout lw[SIDE_MAXWIN];
+    size_t need = 0;
+    bool ok = true;
+    for (int i = 0; i < K; ++i) {
+      if (off[i + 1] <= off[i]) ok = false;
+      cw[i] = cfg; cw[i].S = ok ? off[i + 1] - off[i] : 1;
+      lw[i] = make_layout(cw[i]);
+      need += lw[i].total;
+    }
+    int dev = 0;
+    if (ok && need <= workspace_bytes && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < SIDE_MAXDEV) {
+      Side& sd = g_side[dev];
+      std::lock_guard<std::mutex> lk(sd.mu);
+      if (!sd.init) {
+        bool good = cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < SIDE_MAXWIN - 1 && good; ++i)
+          good = cudaStreamCreateWithFlags(&sd.st[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&sd.join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!good) return cuda_rc(cudaGetLastError());
+        sd.init = true;
+      }
+      cudaError_t e = cudaEventRecord(sd.fork, st);
+      for (int i = 1; i < K && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(sd.st[i - 1], sd.fork, 0);
+      if (e != cudaSuccess) return cuda_rc(e);
+      size_t at = 0;
+      for (int i = 0; i < K; ++i) {
+        ExtBuf bw = bind(cw[i], lw[i], base + at);
+        at += lw[i].total;
+        bw.w = (const double2*)w + off[i]; bw.mag = mag + off[i]; bw.grad = grad ? grad + off[i] : nullptr;
+        cudaStream_t si = i == 0 ? st : sd.st[i - 1];
+        const int ri = lens->nlenses == 2 ? run_pipeline<2>(cw[i], bw, L, si) : run_pipeline<3>(cw[i], bw, L, si);
+        if (ri && !rc) rc = ri;
+      }
+      // join whatever happened, so that nothing of this call is left running beside the caller's stream
+      for (int i = 1; i < K; ++i) {
+        cudaError_t ej = cudaEventRecord(sd.join[i - 1], sd.st[i - 1]);
+        if (ej == cudaSuccess) ej = cudaStreamWaitEvent(st, sd.join[i - 1], 0);
+        if (ej != cudaSuccess && e == cudaSuccess) e = ej;
+      }
+      if (rc) return rc;
+      return e == cudaSuccess ? CAUSTICS_OK : cuda_rc(e);
+    }
   }
   for (int64_t off = 0; off < n; off += cap) {
     b.list_off = off;

@@ -548,3 +548,50 @@ def test_open_pass_forms_agree_bitwise(cb):
     finally:
         L.caustics_set_tuning(b"ext_variants", -1)
         L.caustics_set_tuning(b"open_wsmall", -1)
+
+
+def test_two_windows_on_two_streams(cb, g):
+    """Large un-gated uniform-disk calls are cut into two windows with workspaces of their own, one on the caller's
+    stream and one on a side stream (fork / join by events).  Sources are independent, so the result is bit for
+    bit the single-window one -- forced here on a small batch (2, 3 and 4 windows, an uneven cut), for the plain
+    and the tangent entry point, and under CUDA-graph capture (the side stream joins the capture)."""
+    from caustics_b200 import _lib
+    L = _lib.lib()
+    w = torch.from_numpy(np.tile(np.concatenate([g["t_w_0.01"], g["t_w_0.01"].conj()]), 40)[:3000]).cuda()
+    n = len(w)
+    lens = cb.point_source._c_lens(3, 0.0, **dict(a=0.698, e1=0.02809, e2=0.9687, r3=-0.0197 - 0.95087j))
+    nb = L.caustics_ext_workspace_bytes(n, 3, 200, 0, 100) + (1 << 20)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    mag = torch.empty(n, dtype=torch.float64, device="cuda")
+    grad = torch.empty((8, n), dtype=torch.float64, device="cuda")
+
+    def plain(stream=None):
+        _lib.check(L.caustics_mag_extended_source(w.data_ptr(), mag.data_ptr(), n, 1e-2, lens, 200, 0, 0.0, 100, 2500, 0,
+                                                  ws.data_ptr(), nb, stream))
+
+    def tangent(stream=None):
+        _lib.check(L.caustics_mag_extended_source_grad(w.data_ptr(), mag.data_ptr(), grad.data_ptr(), n, 1e-2, lens, 200, 2500,
+                                                       0, ws.data_ptr(), nb, stream))
+    try:
+        L.caustics_set_tuning(b"ext_windows", 1)
+        plain(); m1 = mag.clone()
+        tangent(); g1 = grad.clone(); assert torch.equal(mag, m1)
+        for K, split in ((2, -1), (3, -1), (4, -1), (2, 1100)):
+            L.caustics_set_tuning(b"ext_windows", K)
+            L.caustics_set_tuning(b"ext_split", split)
+            mag.zero_(); plain(); assert torch.equal(mag, m1), (K, split)
+            mag.zero_(); grad.zero_(); tangent(); assert torch.equal(mag, m1) and torch.equal(grad, g1), (K, split)
+        # captured: fork and join become graph edges
+        L.caustics_set_tuning(b"ext_windows", 2)
+        L.caustics_set_tuning(b"ext_split", -1)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            plain(torch.cuda.current_stream().cuda_stream)
+        mag.zero_()
+        gr.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(mag, m1)
+    finally:
+        L.caustics_set_tuning(b"ext_windows", -1)
+        L.caustics_set_tuning(b"ext_split", -1)
