@@ -212,7 +212,11 @@ int caustics_mag_point_source_grid_host(double x0, double y0, double dx, double 
  * vertex), 1 | CAUSTICS_LD_ADAPTIVE the same with the half-order rule (npts_ld/4 nodes) on far panels that
  * are at most 8 rho long and stay 2 rho away from the vertex (the panel that ends on the limb
  * keeps its nodes).  Opt-in: it moves results by up to 7e-5, so the default stays the
- * reference's rule. */
+ * reference's rule.
+ * Streams: every launch is ordered on `stream`.  Un-gated uniform-disk calls (caustics_mag_extended_source,
+ * caustics_mag_extended_source_grad) of at least 32 768 sources run as two windows, the second on a library-owned
+ * side stream that forks from and joins `stream` by events inside the call: to the caller the call is still one
+ * stream-ordered operation (and one capturable sub-graph); results are bit for bit those of a single window. */
 #define CAUSTICS_LD_ADAPTIVE 2
 /* caustics_ext_workspace_bytes only, OR-ed into limb_darkening = 0: the workspace will serve
  * caustics_mag_extended_source alone (not the tangent / contour-export entry points, which keep the image
@@ -315,10 +319,13 @@ int caustics_peer_close(void* ptr);
 int caustics_peer_enable(int peer_device);
 
 /* ---- launch-shape overrides for tests and experiments ---------------------------------------
- * key in {"grid_run", "path_run", "grid_extrap", "ext_variants", "open_wsmall", "host_slots", "host_chunk_log2"}; value -1 restores the
- * launcher's own rule.  ext_variants: phase-variant mask of the extended-source pipeline (csrc/extended.cu);
+ * key in {"grid_run", "path_run", "grid_extrap", "ext_variants", "open_wsmall", "host_slots",
+ * "host_chunk_log2", "ext_split", "ext_windows"}; value -1 restores the launcher's own rule.
+ * ext_variants: phase-variant mask of the extended-source pipeline (csrc/extended.cu);
  * open_wsmall: sources with at most this many marked tracks go to the first open-pass launch (default 2);
- * host_slots (1..8, default 4) / host_chunk_log2 (10..24, default 15): shape of the host-buffer pipeline.  (These replace environment variables: nothing in the library calls getenv.) */
+ * host_slots (1..8, default 4) / host_chunk_log2 (10..24, default 15): shape of the host-buffer pipeline;
+ * ext_windows (1..4) / ext_split (length of the first window, 0 = one window): the windows of an un-gated call.
+ * (These replace environment variables: nothing in the library calls getenv.) */
 int caustics_set_tuning(const char* key, int value);
 
 /* ---- measurement aid -----------------------------------------------------------------------
