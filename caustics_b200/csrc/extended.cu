@@ -61,7 +61,7 @@ inline int small_mask(int64_t n, int nlenses) {
 }
 
 // un-gated uniform-disk calls of at least this many sources run as two windows on two streams (split_rule below)
-constexpr int64_t SPLIT_MIN = 32768;
+constexpr int64_t SPLIT_MIN = 4096;
 
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CAUSTICS_OK : CAUSTICS_ERR_CUDA_BASE + (int)e; }
 
@@ -493,7 +493,7 @@ struct Side {
 Side g_side[SIDE_MAXDEV];
 // The windows of an un-gated call: *first = length of the first one (on the caller's stream), the others share the
 // rest equally.  Returns their number (1 = one window).  Rule (measured, profiles/r02_ext_variants.txt): uniform disk,
-// binary or triple lens, at least 32 768 sources -> two windows, the first max(n / 2, min(65 536, n - 16 384)) long;
+// binary or triple lens, at least 4 096 sources -> two windows, the first max(n / 2, min(65 536, n - 16 384)) long;
 // three and four windows are no better.  caustics_set_tuning("ext_split", nA) / ("ext_windows", K) override.
 inline int split_rule(int64_t n, const ExtCfg& cfg, int gate, int64_t* first) {
   if (gate || cfg.ld || cfg.nl == 1) return 1;

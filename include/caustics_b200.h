@@ -214,7 +214,7 @@ int caustics_mag_point_source_grid_host(double x0, double y0, double dx, double 
  * keeps its nodes).  Opt-in: it moves results by up to 7e-5, so the default stays the
  * reference's rule.
  * Streams: every launch is ordered on `stream`.  Un-gated uniform-disk calls (caustics_mag_extended_source,
- * caustics_mag_extended_source_grad) of at least 32 768 sources run as two windows, the second on a library-owned
+ * caustics_mag_extended_source_grad) of at least 4 096 sources run as two windows, the second on a library-owned
  * side stream that forks from and joins `stream` by events inside the call: to the caller the call is still one
  * stream-ordered operation (and one capturable sub-graph); results are bit for bit those of a single window. */
 #define CAUSTICS_LD_ADAPTIVE 2

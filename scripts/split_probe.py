@@ -27,7 +27,7 @@ def timeit(fn, reps=5):
     return best
 
 
-for nl, n in ((3, 100_000), (3, 200_000), (2, 100_000), (3, 50_000), (2, 50_000), (3, 25_000)):
+for nl, n in [tuple(int(v) for v in x.split(':')) for x in os.environ.get('CASES', '3:100000,3:200000,2:100000,3:50000,2:50000,3:25000').split(',')]:
     if nl == 3:
         lens = cb.point_source._c_lens(3, 0.0, **bench.LENS)
     else:
