@@ -22,6 +22,8 @@ import caustics_b200 as cb  # noqa: E402
 from caustics_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
+if os.environ.get("EXT_WINDOWS"):
+    L.caustics_set_tuning(b"ext_windows", int(os.environ["EXT_WINDOWS"]))
 target = sys.argv[1]
 reps = 3
 if target == "comp10":

@@ -20,6 +20,8 @@ import caustics_b200 as cb  # noqa: E402
 from caustics_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
+if os.environ.get("EXT_WINDOWS"):
+    L.caustics_set_tuning(b"ext_windows", int(os.environ["EXT_WINDOWS"]))
 C2P = dict(a=0.698, e1=0.02809, e2=0.9687, r3=-0.0197 - 0.95087j)
 
 
