@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """The kernels round 2 profiles, each launched a few times on its BASELINE workload (run under ncu by
 scripts/gpu_profile_r2.sh):  python scripts/profile_targets.py <target>
+  plain10  ea_kernel<10, false>  the headline: plain degree-10 solve of the C2 batch
   comp10   ea_kernel<10, true>   compensated degree-10 solve of the C2 batch (kernel (1) of north_star)
   deg5     ea_kernel<5, false>   10^6 degree-5 polynomials (C1 at GPU-filling size)
   map      ps_kernel<2, 0, 0>    2000 rows of the C5 map, per-pixel cold solves
@@ -26,7 +27,11 @@ if os.environ.get("EXT_WINDOWS"):
     L.caustics_set_tuning(b"ext_windows", int(os.environ["EXT_WINDOWS"]))
 target = sys.argv[1]
 reps = 3
-if target == "comp10":
+if target == "plain10":
+    c = torch.from_numpy(bench.make_coeffs(0, 1)).cuda()
+    for _ in range(reps):
+        cb.poly_roots(c, itmax=2500)
+elif target == "comp10":
     c = torch.from_numpy(bench.make_coeffs(0, 1)).cuda()
     for _ in range(reps):
         cb.poly_roots(c, itmax=2500, compensated=True)
