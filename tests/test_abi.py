@@ -110,6 +110,9 @@ def test_round2_entry_points_without_compute(built_lib):
     L = built_lib
     assert L.caustics_set_tuning(b"path_run", 8) == 0 and L.caustics_set_tuning(b"path_run", -1) == 0
     assert L.caustics_set_tuning(b"no_such_knob", 1) == 1 and L.caustics_set_tuning(None, 1) == 1
+    for key in (b"grid_run", b"path_run", b"grid_extrap", b"ext_variants", b"open_wsmall", b"host_slots", b"host_chunk_log2",
+                b"ext_split", b"ext_windows"):      # every key include/caustics_b200.h documents
+        assert L.caustics_set_tuning(key, 1) == 0 and L.caustics_set_tuning(key, -1) == 0, key
     for f in os.listdir(os.path.join(ROOT, "caustics_b200", "csrc")):
         assert "getenv" not in open(os.path.join(ROOT, "caustics_b200", "csrc", f)).read().replace("no getenv", ""), f
     # a gated call's workspace: per-source arrays for max_full sources + a list of n points
